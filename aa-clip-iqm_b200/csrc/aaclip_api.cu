@@ -1,0 +1,658 @@
+// C-ABI + host orchestration of the B200-native AA-CLIP hot path. See include/aaclip.h for the contract.
+// Compiled with: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/aaclip.h"
+#include "attention_tcgen05.cuh"
+#include "elementwise.cuh"
+#include "gemm_tcgen05.cuh"
+
+namespace {
+
+using namespace aaclip;
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                                   \
+  do {                                                                                                   \
+    cudaError_t _e = (expr);                                                                             \
+    if (_e != cudaSuccess) return fail(AACLIP_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                                       __FILE__, __LINE__);                                              \
+  } while (0)
+
+#define LAUNCH_CHECK(what)                                                                               \
+  do {                                                                                                   \
+    cudaError_t _e = cudaGetLastError();                                                                 \
+    if (_e != cudaSuccess) return fail(AACLIP_ECUDA, "launch of %s failed: %s", what, cudaGetErrorString(_e)); \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------ TMA descriptors
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+  }
+  return fn;
+}
+
+// bf16 tensor, innermost dim contiguous; rank 2 or 3; 128-byte swizzle; OOB reads return zero.
+int make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) return fail(AACLIP_ENOSYS, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+  cuuint64_t gdim[3];
+  cuuint64_t gstr[2];
+  cuuint32_t bx[3], estr[3];
+  for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; estr[i] = 1; }
+  for (int i = 0; i < rank - 1; ++i) gstr[i] = strides_bytes[i];
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdim, gstr, bx, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(AACLIP_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return AACLIP_OK;
+}
+
+int g_num_sms = 0;
+int ensure_device() {
+  if (g_num_sms > 0) return AACLIP_OK;
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) return fail(AACLIP_ENOSYS, "device '%s' is sm_%d%d; this library is sm_100a only", prop.name,
+                                    prop.major, prop.minor);
+  g_num_sms = prop.multiProcessorCount;
+  return AACLIP_OK;
+}
+
+// ------------------------------------------------------------------------------------------ kernel launchers
+template <int EPI>
+int launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const GemmEpi& epi,
+                  cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(gemm_tcgen05_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  gemm_cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int tiles = ((M + gemm_cfg::BM - 1) / gemm_cfg::BM) * (N / gemm_cfg::BN);
+  const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+  gemm_tcgen05_kernel<EPI><<<grid, gemm_cfg::THREADS, gemm_cfg::SMEM_BYTES, st>>>(ta, tb, M, N, K, epi);
+  LAUNCH_CHECK("gemm_tcgen05_kernel");
+  return AACLIP_OK;
+}
+
+int launch_gemm(int epi_mode, const void* A, const void* W, int M, int N, int K, const GemmEpi& epi,
+                cudaStream_t st) {
+  if (int rc = ensure_device()) return rc;
+  if (M <= 0 || N <= 0 || K <= 0 || N % gemm_cfg::BN != 0 || K % gemm_cfg::BK != 0)
+    return fail(AACLIP_EINVAL, "gemm: unsupported shape M=%d N=%d K=%d (need N%%256==0, K%%64==0)", M, N, K);
+  if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(W) & 15))
+    return fail(AACLIP_EINVAL, "gemm: operands must be 16-byte aligned");
+  CUtensorMap ta, tb;
+  {
+    const uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
+    const uint64_t str[1] = {(uint64_t)K * 2};
+    const uint32_t box[2] = {gemm_cfg::BK, gemm_cfg::BM};
+    if (int rc = make_tmap_bf16(&ta, A, 2, dims, str, box)) return rc;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
+    const uint64_t str[1] = {(uint64_t)K * 2};
+    const uint32_t box[2] = {gemm_cfg::BK, gemm_cfg::BN};
+    if (int rc = make_tmap_bf16(&tb, W, 2, dims, str, box)) return rc;
+  }
+  switch (epi_mode) {
+    case EPI_BIAS_BF16: return launch_gemm_t<EPI_BIAS_BF16>(ta, tb, M, N, K, epi, st);
+    case EPI_BIAS_GELU_BF16: return launch_gemm_t<EPI_BIAS_GELU_BF16>(ta, tb, M, N, K, epi, st);
+    case EPI_BIAS_QGELU_BF16: return launch_gemm_t<EPI_BIAS_QGELU_BF16>(ta, tb, M, N, K, epi, st);
+    case EPI_BIAS_RESID_F32: return launch_gemm_t<EPI_BIAS_RESID_F32>(ta, tb, M, N, K, epi, st);
+    case EPI_F32: return launch_gemm_t<EPI_F32>(ta, tb, M, N, K, epi, st);
+    case EPI_LEAKY_F32: return launch_gemm_t<EPI_LEAKY_F32>(ta, tb, M, N, K, epi, st);
+    case EPI_PATCH_F32: return launch_gemm_t<EPI_PATCH_F32>(ta, tb, M, N, K, epi, st);
+    case EPI_BIAS_F32: return launch_gemm_t<EPI_BIAS_F32>(ta, tb, M, N, K, epi, st);
+    default: return fail(AACLIP_EINVAL, "gemm: unknown epilogue %d", epi_mode);
+  }
+}
+
+int launch_attention(const void* qkv, void* out, int B, int N, int D, int causal, cudaStream_t st) {
+  if (int rc = ensure_device()) return rc;
+  if (B <= 0 || N <= 0 || D <= 0 || D % 64 != 0) return fail(AACLIP_EINVAL, "attention: bad shape B=%d N=%d D=%d", B, N, D);
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(attention_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  attn_cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  CUtensorMap tq;
+  const uint64_t dims[3] = {(uint64_t)3 * D, (uint64_t)N, (uint64_t)B};
+  const uint64_t str[2] = {(uint64_t)3 * D * 2, (uint64_t)N * 3 * D * 2};
+  const uint32_t box[3] = {attn_cfg::HD, attn_cfg::BKV, 1};
+  if (int rc = make_tmap_bf16(&tq, qkv, 3, dims, str, box)) return rc;
+  const int H = D / 64;
+  dim3 grid((N + attn_cfg::BQ * attn_cfg::QT - 1) / (attn_cfg::BQ * attn_cfg::QT), H, B);
+  const float scale_log2 = 0.125f * 1.4426950408889634f;  // head_dim^-0.5 * log2(e)
+  attention_tcgen05_kernel<<<grid, attn_cfg::THREADS, attn_cfg::SMEM_BYTES, st>>>(
+      tq, reinterpret_cast<__nv_bfloat16*>(out), N, D, causal, scale_log2);
+  LAUNCH_CHECK("attention_tcgen05_kernel");
+  return AACLIP_OK;
+}
+
+int launch_layernorm(const float* x, const float* g, const float* b, void* out_bf16, float* out_f32, int rows, int D,
+                     int skipP, bool normalize, cudaStream_t st) {
+  if (rows <= 0) return AACLIP_OK;
+  const int threads = 256, rows_per_block = threads / 32;
+  const int grid = (rows + rows_per_block - 1) / rows_per_block;
+  __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(out_bf16);
+  if (D == 1024) {
+    if (normalize) layernorm_kernel<1024, true><<<grid, threads, 0, st>>>(x, g, b, ob, out_f32, rows, skipP, 1e-5f);
+    else layernorm_kernel<1024, false><<<grid, threads, 0, st>>>(x, g, b, ob, out_f32, rows, skipP, 1e-5f);
+  } else if (D == 768) {
+    if (normalize) layernorm_kernel<768, true><<<grid, threads, 0, st>>>(x, g, b, ob, out_f32, rows, skipP, 1e-5f);
+    else layernorm_kernel<768, false><<<grid, threads, 0, st>>>(x, g, b, ob, out_f32, rows, skipP, 1e-5f);
+  } else {
+    return fail(AACLIP_EINVAL, "layernorm: D=%d unsupported (768 or 1024)", D);
+  }
+  LAUNCH_CHECK("layernorm_kernel");
+  return AACLIP_OK;
+}
+
+__global__ void pack_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long R,
+                                 long long C, long long Cp) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= R * Cp) return;
+  const long long r = i / Cp, c = i - r * Cp;
+  dst[i] = __float2bfloat16_rn(c < C ? src[r * C + c] : 0.f);
+}
+
+__global__ void gather_cls_kernel(const float* __restrict__ x, float* __restrict__ out, int tokens, int D) {
+  const int b = blockIdx.x;
+  for (int i = threadIdx.x; i < D; i += blockDim.x) out[static_cast<size_t>(b) * D + i] = x[static_cast<size_t>(b) * tokens * D + i];
+}
+
+int launch_pack(const float* src, void* dst, long long R, long long C, long long Cp, cudaStream_t st) {
+  const long long n = R * Cp;
+  if (n <= 0) return AACLIP_OK;
+  pack_bf16_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), R, C, Cp);
+  LAUNCH_CHECK("pack_bf16_kernel");
+  return AACLIP_OK;
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+// =========================================================================================== handle
+struct BlockW {
+  float *ln1_g, *ln1_b, *ln2_g, *ln2_b, *b_qkv, *b_out, *b_fc, *b_proj;
+  __nv_bfloat16 *w_qkv, *w_out, *w_fc, *w_proj;
+};
+
+struct AaclipHandle {
+  AaclipCfg cfg;
+  int G, P, N, KP;        // grid side, patches, tokens, padded patch K
+  uint8_t* arena = nullptr;
+  size_t arena_bytes = 0;
+  // fp32 params
+  float *cls, *pos, *lnpre_g, *lnpre_b, *lnpost_g, *lnpost_b;
+  __nv_bfloat16* w_conv;  // [W, KP]
+  std::vector<BlockW> blk;
+  std::vector<__nv_bfloat16*> w_adapter;  // [W,W] each
+  std::vector<__nv_bfloat16*> w_seg;      // [E,W] each
+  __nv_bfloat16* w_det;                   // [E,W]
+  std::vector<std::string> missing;
+  int last_launches = 0;
+};
+
+namespace {
+
+struct ArenaPlan {
+  size_t off = 0;
+  template <typename T>
+  size_t take(size_t n) {
+    size_t o = off;
+    off = align_up(off + n * sizeof(T), 256);
+    return o;
+  }
+};
+
+void mark_loaded(AaclipHandle* h, const std::string& key) {
+  for (size_t i = 0; i < h->missing.size(); ++i)
+    if (h->missing[i] == key) { h->missing.erase(h->missing.begin() + i); return; }
+}
+
+int64_t numel(const int64_t* shape, int ndim) {
+  int64_t n = 1;
+  for (int i = 0; i < ndim; ++i) n *= shape[i];
+  return n;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* aaclip_version(void) { return "aaclip_b200 0.1 sm_100a"; }
+const char* aaclip_last_error(void) { return g_err; }
+
+int aaclip_create(const AaclipCfg* cfg, AaclipHandle** out) {
+  if (cfg == nullptr || out == nullptr) return fail(AACLIP_EINVAL, "aaclip_create: null argument");
+  *out = nullptr;
+  if (int rc = ensure_device()) return rc;
+  const AaclipCfg& c = *cfg;
+  if (c.patch <= 0 || c.img_size < c.patch) return fail(AACLIP_EINVAL, "bad img_size/patch %d/%d", c.img_size, c.patch);
+  if (c.width != 1024 && c.width != 768) return fail(AACLIP_EINVAL, "width %d unsupported (768 or 1024)", c.width);
+  if (c.heads * 64 != c.width) return fail(AACLIP_EINVAL, "head dim must be 64 (width %d, heads %d)", c.width, c.heads);
+  if (c.mlp_dim % 256 != 0 || c.embed_dim % 256 != 0 || (c.embed_dim != 768 && c.embed_dim != 1024))
+    return fail(AACLIP_EINVAL, "mlp_dim/embed_dim unsupported (%d/%d)", c.mlp_dim, c.embed_dim);
+  if (c.layers <= 0 || c.adapt_until < 0 || c.adapt_until > c.layers) return fail(AACLIP_EINVAL, "bad layers/adapt_until");
+  if (c.n_levels <= 0 || c.n_levels > AACLIP_MAX_LEVELS) return fail(AACLIP_EINVAL, "n_levels must be 1..4");
+  for (int l = 0; l < c.n_levels; ++l) {
+    if (c.levels[l] < 1 || c.levels[l] > c.layers || (l > 0 && c.levels[l] <= c.levels[l - 1]))
+      return fail(AACLIP_EINVAL, "levels must be ascending in 1..layers");
+  }
+  if (c.max_batch <= 0) return fail(AACLIP_EINVAL, "max_batch must be > 0");
+
+  AaclipHandle* h = new AaclipHandle();
+  h->cfg = c;
+  h->G = c.img_size / c.patch;
+  h->P = h->G * h->G;
+  h->N = h->P + 1;
+  const int k_raw = 3 * c.patch * c.patch;
+  h->KP = (k_raw + 63) / 64 * 64;
+  const size_t W = c.width, F = c.mlp_dim, E = c.embed_dim;
+
+  ArenaPlan plan;
+  const size_t o_cls = plan.take<float>(W), o_pos = plan.take<float>((size_t)h->N * W);
+  const size_t o_lpg = plan.take<float>(W), o_lpb = plan.take<float>(W), o_log = plan.take<float>(W), o_lob = plan.take<float>(W);
+  const size_t o_conv = plan.take<__nv_bfloat16>(W * h->KP);
+  struct BO { size_t ln1g, ln1b, ln2g, ln2b, bqkv, bout, bfc, bproj, wqkv, wout, wfc, wproj; };
+  std::vector<BO> bo(c.layers);
+  for (int i = 0; i < c.layers; ++i) {
+    bo[i].ln1g = plan.take<float>(W); bo[i].ln1b = plan.take<float>(W);
+    bo[i].ln2g = plan.take<float>(W); bo[i].ln2b = plan.take<float>(W);
+    bo[i].bqkv = plan.take<float>(3 * W); bo[i].bout = plan.take<float>(W);
+    bo[i].bfc = plan.take<float>(F); bo[i].bproj = plan.take<float>(W);
+    bo[i].wqkv = plan.take<__nv_bfloat16>(3 * W * W); bo[i].wout = plan.take<__nv_bfloat16>(W * W);
+    bo[i].wfc = plan.take<__nv_bfloat16>(F * W); bo[i].wproj = plan.take<__nv_bfloat16>(W * F);
+  }
+  std::vector<size_t> o_ad(c.adapt_until), o_seg(c.n_levels);
+  for (int i = 0; i < c.adapt_until; ++i) o_ad[i] = plan.take<__nv_bfloat16>(W * W);
+  for (int l = 0; l < c.n_levels; ++l) o_seg[l] = plan.take<__nv_bfloat16>(E * W);
+  const size_t o_det = plan.take<__nv_bfloat16>(E * W);
+
+  h->arena_bytes = plan.off;
+  cudaError_t e = cudaMalloc(&h->arena, h->arena_bytes);
+  if (e != cudaSuccess) {
+    delete h;
+    return fail(AACLIP_ECUDA, "cudaMalloc(%zu) for the weight arena failed: %s", plan.off, cudaGetErrorString(e));
+  }
+  e = cudaMemset(h->arena, 0, h->arena_bytes);
+  if (e != cudaSuccess) {
+    cudaFree(h->arena);
+    delete h;
+    return fail(AACLIP_ECUDA, "cudaMemset of the weight arena failed: %s", cudaGetErrorString(e));
+  }
+  uint8_t* a = h->arena;
+  h->cls = (float*)(a + o_cls); h->pos = (float*)(a + o_pos);
+  h->lnpre_g = (float*)(a + o_lpg); h->lnpre_b = (float*)(a + o_lpb);
+  h->lnpost_g = (float*)(a + o_log); h->lnpost_b = (float*)(a + o_lob);
+  h->w_conv = (__nv_bfloat16*)(a + o_conv);
+  h->blk.resize(c.layers);
+  for (int i = 0; i < c.layers; ++i) {
+    BlockW& b = h->blk[i];
+    b.ln1_g = (float*)(a + bo[i].ln1g); b.ln1_b = (float*)(a + bo[i].ln1b);
+    b.ln2_g = (float*)(a + bo[i].ln2g); b.ln2_b = (float*)(a + bo[i].ln2b);
+    b.b_qkv = (float*)(a + bo[i].bqkv); b.b_out = (float*)(a + bo[i].bout);
+    b.b_fc = (float*)(a + bo[i].bfc); b.b_proj = (float*)(a + bo[i].bproj);
+    b.w_qkv = (__nv_bfloat16*)(a + bo[i].wqkv); b.w_out = (__nv_bfloat16*)(a + bo[i].wout);
+    b.w_fc = (__nv_bfloat16*)(a + bo[i].wfc); b.w_proj = (__nv_bfloat16*)(a + bo[i].wproj);
+  }
+  for (int i = 0; i < c.adapt_until; ++i) h->w_adapter.push_back((__nv_bfloat16*)(a + o_ad[i]));
+  for (int l = 0; l < c.n_levels; ++l) h->w_seg.push_back((__nv_bfloat16*)(a + o_seg[l]));
+  h->w_det = (__nv_bfloat16*)(a + o_det);
+
+  // the set of tensors that must arrive through aaclip_set_weight before forward may run
+  auto need = [&](const std::string& k) { h->missing.push_back(k); };
+  need("conv1.weight"); need("class_embedding"); need("positional_embedding");
+  need("ln_pre.weight"); need("ln_pre.bias"); need("ln_post.weight"); need("ln_post.bias");
+  for (int i = 0; i < c.layers; ++i) {
+    const std::string p = "blk." + std::to_string(i) + ".";
+    for (const char* s : {"ln_1.weight", "ln_1.bias", "ln_2.weight", "ln_2.bias", "attn.in_proj_weight",
+                          "attn.in_proj_bias", "attn.out_proj.weight", "attn.out_proj.bias", "mlp.c_fc.weight",
+                          "mlp.c_fc.bias", "mlp.c_proj.weight", "mlp.c_proj.bias"})
+      need(p + s);
+  }
+  for (int i = 0; i < c.adapt_until; ++i) need("adapter." + std::to_string(i));
+  for (int l = 0; l < c.n_levels; ++l) need("seg." + std::to_string(l));
+  need("det");
+  *out = h;
+  return AACLIP_OK;
+}
+
+void aaclip_destroy(AaclipHandle* h) {
+  if (h == nullptr) return;
+  if (h->arena) cudaFree(h->arena);
+  delete h;
+}
+
+int aaclip_missing_weights(AaclipHandle* h) { return h ? static_cast<int>(h->missing.size()) : -1; }
+
+int aaclip_set_weight(AaclipHandle* h, const char* name, const float* data, const int64_t* shape, int32_t ndim,
+                      void* stream) {
+  if (!h || !name || !data || !shape || ndim <= 0) return fail(AACLIP_EINVAL, "aaclip_set_weight: null/empty argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const AaclipCfg& c = h->cfg;
+  const int64_t W = c.width, F = c.mlp_dim, E = c.embed_dim;
+  const int64_t n = numel(shape, ndim);
+  std::string k(name);
+  for (const char* pre : {"image_encoder.", "clipmodel.visual.", "visual."}) {
+    if (k.rfind(pre, 0) == 0) { k = k.substr(strlen(pre)); break; }
+  }
+  auto copy_f32 = [&](float* dst, int64_t expect, const std::string& key) -> int {
+    if (n != expect) return fail(AACLIP_EINVAL, "%s: expected %lld elements, got %lld", name, (long long)expect, (long long)n);
+    CUDA_TRY(cudaMemcpyAsync(dst, data, expect * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    mark_loaded(h, key);
+    return AACLIP_OK;
+  };
+  auto pack = [&](__nv_bfloat16* dst, int64_t R, int64_t C, int64_t Cp, const std::string& key) -> int {
+    if (n != R * C) return fail(AACLIP_EINVAL, "%s: expected %lld x %lld elements, got %lld", name, (long long)R, (long long)C, (long long)n);
+    if (int rc = launch_pack(data, dst, R, C, Cp, st)) return rc;
+    mark_loaded(h, key);
+    return AACLIP_OK;
+  };
+
+  if (k == "conv1.weight") return pack(h->w_conv, W, 3 * c.patch * c.patch, h->KP, k);
+  if (k == "class_embedding") return copy_f32(h->cls, W, k);
+  if (k == "positional_embedding") return copy_f32(h->pos, (int64_t)h->N * W, k);
+  if (k == "ln_pre.weight") return copy_f32(h->lnpre_g, W, k);
+  if (k == "ln_pre.bias") return copy_f32(h->lnpre_b, W, k);
+  if (k == "ln_post.weight") return copy_f32(h->lnpost_g, W, k);
+  if (k == "ln_post.bias") return copy_f32(h->lnpost_b, W, k);
+
+  int idx = -1;
+  char tail[96];
+  if (sscanf(k.c_str(), "transformer.resblocks.%d.%95s", &idx, tail) == 2) {
+    if (idx < 0 || idx >= c.layers) return fail(AACLIP_EINVAL, "%s: block index out of range", name);
+    BlockW& b = h->blk[idx];
+    const std::string t(tail), key = "blk." + std::to_string(idx) + "." + t;
+    if (t == "ln_1.weight") return copy_f32(b.ln1_g, W, key);
+    if (t == "ln_1.bias") return copy_f32(b.ln1_b, W, key);
+    if (t == "ln_2.weight") return copy_f32(b.ln2_g, W, key);
+    if (t == "ln_2.bias") return copy_f32(b.ln2_b, W, key);
+    if (t == "attn.in_proj_bias") return copy_f32(b.b_qkv, 3 * W, key);
+    if (t == "attn.out_proj.bias") return copy_f32(b.b_out, W, key);
+    if (t == "mlp.c_fc.bias") return copy_f32(b.b_fc, F, key);
+    if (t == "mlp.c_proj.bias") return copy_f32(b.b_proj, W, key);
+    if (t == "attn.in_proj_weight") return pack(b.w_qkv, 3 * W, W, W, key);
+    if (t == "attn.out_proj.weight") return pack(b.w_out, W, W, W, key);
+    if (t == "mlp.c_fc.weight") return pack(b.w_fc, F, W, W, key);
+    if (t == "mlp.c_proj.weight") return pack(b.w_proj, W, F, F, key);
+    return fail(AACLIP_EINVAL, "%s: unknown block tensor", name);
+  }
+  if (sscanf(k.c_str(), "image_adapter.layer_adapters.%d.%95s", &idx, tail) == 2) {
+    if (strcmp(tail, "fc.0.weight") != 0) return fail(AACLIP_EINVAL, "%s: unknown tensor", name);
+    if (idx < 0 || idx >= c.adapt_until) return fail(AACLIP_EINVAL, "%s: adapter index out of range", name);
+    return pack(h->w_adapter[idx], W, W, W, "adapter." + std::to_string(idx));
+  }
+  if (sscanf(k.c_str(), "image_adapter.seg_proj.%d.fc.%95s", &idx, tail) == 2) {
+    if (idx < 0 || idx >= c.n_levels) return fail(AACLIP_EINVAL, "%s: seg_proj index out of range", name);
+    if (strcmp(tail, "weight") != 0 && strcmp(tail, "0.weight") != 0) return fail(AACLIP_EINVAL, "%s: unknown tensor", name);
+    return pack(h->w_seg[idx], E, W, W, "seg." + std::to_string(idx));
+  }
+  if (k == "image_adapter.det_proj.fc.weight" || k == "image_adapter.det_proj.fc.0.weight") return pack(h->w_det, E, W, W, "det");
+  return fail(AACLIP_EINVAL, "%s: unknown tensor name", name);
+}
+
+// workspace carve-up shared by aaclip_workspace_bytes and aaclip_forward
+struct WsPlan {
+  size_t x, xn, qkv, att, hid, abuf, patchA, tok, det, total;
+};
+static WsPlan plan_ws(const AaclipHandle* h, int B) {
+  const size_t W = h->cfg.width, F = h->cfg.mlp_dim, E = h->cfg.embed_dim;
+  const size_t M = (size_t)B * h->N, MP = (size_t)B * h->P;
+  ArenaPlan p;
+  WsPlan w;
+  w.x = p.take<float>(M * W);
+  w.xn = p.take<__nv_bfloat16>(M * W);
+  w.qkv = p.take<__nv_bfloat16>(M * 3 * W);
+  w.att = p.take<__nv_bfloat16>(M * W);
+  w.hid = p.take<__nv_bfloat16>(M * F);
+  w.abuf = p.take<float>(M * W);
+  w.patchA = p.take<__nv_bfloat16>(MP * h->KP);
+  w.tok = p.take<__nv_bfloat16>(MP * W);
+  w.det = p.take<float>(MP * E);
+  w.total = p.off;
+  return w;
+}
+
+size_t aaclip_workspace_bytes(AaclipHandle* h, int32_t B) {
+  if (!h || B <= 0) return 0;
+  return plan_ws(h, B).total;
+}
+
+int aaclip_forward(AaclipHandle* h, const float* images, int32_t B, void* workspace, size_t workspace_bytes,
+                   float* const* seg_out, float* det_out, float* const* tokens_out, float* cls_out, void* stream) {
+  if (!h || !images || !workspace || !seg_out || !det_out) return fail(AACLIP_EINVAL, "aaclip_forward: null argument");
+  if (B <= 0 || B > h->cfg.max_batch) return fail(AACLIP_EINVAL, "aaclip_forward: batch %d outside 1..%d", B, h->cfg.max_batch);
+  if (!h->missing.empty())
+    return fail(AACLIP_ESTATE, "aaclip_forward: %zu weight tensors not set (first: %s)", h->missing.size(), h->missing[0].c_str());
+  const WsPlan ws = plan_ws(h, B);
+  if (workspace_bytes < ws.total) return fail(AACLIP_EINVAL, "aaclip_forward: workspace %zu < required %zu", workspace_bytes, ws.total);
+  if (reinterpret_cast<uintptr_t>(workspace) & 255) return fail(AACLIP_EINVAL, "aaclip_forward: workspace must be 256-byte aligned");
+  for (int l = 0; l < h->cfg.n_levels; ++l)
+    if (!seg_out[l]) return fail(AACLIP_EINVAL, "aaclip_forward: seg_out[%d] is null", l);
+
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const AaclipCfg& c = h->cfg;
+  const int W = c.width, F = c.mlp_dim, E = c.embed_dim, N = h->N, P = h->P;
+  const int M = B * N, MP = B * P;
+  uint8_t* wsb = static_cast<uint8_t*>(workspace);
+  float* x = (float*)(wsb + ws.x);
+  __nv_bfloat16* xn = (__nv_bfloat16*)(wsb + ws.xn);
+  __nv_bfloat16* qkv = (__nv_bfloat16*)(wsb + ws.qkv);
+  __nv_bfloat16* att = (__nv_bfloat16*)(wsb + ws.att);
+  __nv_bfloat16* hid = (__nv_bfloat16*)(wsb + ws.hid);
+  float* abuf = (float*)(wsb + ws.abuf);
+  __nv_bfloat16* patchA = (__nv_bfloat16*)(wsb + ws.patchA);
+  __nv_bfloat16* tok = (__nv_bfloat16*)(wsb + ws.tok);
+  float* detbuf = (float*)(wsb + ws.det);
+  int launches = 0;
+  int rc;
+
+  // ---- patch embedding + CLS + positional embedding + ln_pre (model/adapter.py:139-156)
+  patch_gather_kernel<<<dim3(h->G, B), 256, 0, st>>>(images, patchA, c.img_size, h->G, c.patch, h->KP);
+  LAUNCH_CHECK("patch_gather_kernel"); ++launches;
+  {
+    GemmEpi e; e.out_f32 = x; e.ldo = W; e.pos = h->pos; e.patches = P;
+    if ((rc = launch_gemm(EPI_PATCH_F32, patchA, h->w_conv, MP, W, h->KP, e, st))) return rc;
+    ++launches;
+  }
+  cls_row_kernel<<<B, 256, 0, st>>>(x, h->cls, h->pos, N, W);
+  LAUNCH_CHECK("cls_row_kernel"); ++launches;
+  if ((rc = launch_layernorm(x, h->lnpre_g, h->lnpre_b, nullptr, x, M, W, 0, true, st))) return rc;
+  ++launches;
+
+  // ---- residual attention blocks (model/transformer.py:239-258) + adapters (model/adapter.py:161-172)
+  int level_idx = 0;
+  for (int i = 0; i < c.layers; ++i) {
+    const BlockW& b = h->blk[i];
+    if ((rc = launch_layernorm(x, b.ln1_g, b.ln1_b, xn, nullptr, M, W, 0, true, st))) return rc;
+    { GemmEpi e; e.bias = b.b_qkv; e.out_bf16 = qkv; e.ldo = 3 * W;
+      if ((rc = launch_gemm(EPI_BIAS_BF16, xn, b.w_qkv, M, 3 * W, W, e, st))) return rc; }
+    if ((rc = launch_attention(qkv, att, B, N, W, 0, st))) return rc;
+    { GemmEpi e; e.bias = b.b_out; e.out_f32 = x; e.ldo = W;
+      if ((rc = launch_gemm(EPI_BIAS_RESID_F32, att, b.w_out, M, W, W, e, st))) return rc; }
+    if ((rc = launch_layernorm(x, b.ln2_g, b.ln2_b, xn, nullptr, M, W, 0, true, st))) return rc;
+    { GemmEpi e; e.bias = b.b_fc; e.out_bf16 = hid; e.ldo = F;
+      if ((rc = launch_gemm(c.act == AACLIP_ACT_QUICK_GELU ? EPI_BIAS_QGELU_BF16 : EPI_BIAS_GELU_BF16, xn, b.w_fc, M, F, W, e, st))) return rc; }
+    const bool adapt = i < c.adapt_until;
+    { GemmEpi e; e.bias = b.b_proj; e.out_f32 = x; e.ldo = W; e.out_bf16 = adapt ? xn : nullptr;
+      if ((rc = launch_gemm(EPI_BIAS_RESID_F32, hid, b.w_proj, M, W, F, e, st))) return rc; }
+    launches += 7;
+    if (adapt) {
+      { GemmEpi e; e.out_f32 = abuf; e.ldo = W;
+        if ((rc = launch_gemm(EPI_LEAKY_F32, xn, h->w_adapter[i], M, W, W, e, st))) return rc; }
+      const int grid = (M + 7) / 8;
+      if (W == 1024) adapter_blend_kernel<1024><<<grid, 256, 0, st>>>(x, abuf, M, c.adapt_weight, 1.0f - c.adapt_weight);
+      else adapter_blend_kernel<768><<<grid, 256, 0, st>>>(x, abuf, M, c.adapt_weight, 1.0f - c.adapt_weight);
+      LAUNCH_CHECK("adapter_blend_kernel");
+      launches += 2;
+    }
+    if (level_idx < c.n_levels && c.levels[level_idx] == i + 1) {
+      float* tok_f32 = (tokens_out != nullptr) ? tokens_out[level_idx] : nullptr;
+      if ((rc = launch_layernorm(x, h->lnpost_g, h->lnpost_b, tok, tok_f32, MP, W, P, true, st))) return rc;
+      const int proj_epi = c.proj_relu ? EPI_LEAKY_F32 : EPI_F32;
+      { GemmEpi e; e.out_f32 = seg_out[level_idx]; e.ldo = E;
+        if ((rc = launch_gemm(proj_epi, tok, h->w_seg[level_idx], MP, E, W, e, st))) return rc; }
+      const int grid = (MP + 7) / 8;
+      if (E == 768) l2norm_rows_kernel<768><<<grid, 256, 0, st>>>(seg_out[level_idx], MP);
+      else l2norm_rows_kernel<1024><<<grid, 256, 0, st>>>(seg_out[level_idx], MP);
+      LAUNCH_CHECK("l2norm_rows_kernel");
+      launches += 3;
+      if (level_idx == c.n_levels - 1) {
+        { GemmEpi e; e.out_f32 = detbuf; e.ldo = E;
+          if ((rc = launch_gemm(proj_epi, tok, h->w_det, MP, E, W, e, st))) return rc; }
+        if (E == 768) l2norm_rows_kernel<768><<<grid, 256, 0, st>>>(detbuf, MP);
+        else l2norm_rows_kernel<1024><<<grid, 256, 0, st>>>(detbuf, MP);
+        LAUNCH_CHECK("l2norm_rows_kernel");
+        mean_over_patches_kernel<<<dim3((E + 127) / 128, B), 128, 0, st>>>(detbuf, det_out, P, E);
+        LAUNCH_CHECK("mean_over_patches_kernel");
+        launches += 3;
+      }
+      ++level_idx;
+    }
+  }
+  if (cls_out != nullptr) {
+    gather_cls_kernel<<<B, 256, 0, st>>>(x, cls_out, N, W);
+    LAUNCH_CHECK("gather_cls_kernel"); ++launches;
+  }
+  h->last_launches = launches;
+  return AACLIP_OK;
+}
+
+int aaclip_last_launch_count(AaclipHandle* h) { return h ? h->last_launches : -1; }
+
+size_t aaclip_score_workspace_bytes(int32_t B, int32_t n_levels, int32_t P) {
+  if (B <= 0 || n_levels <= 0 || P <= 0) return 0;
+  return align_up((size_t)B * n_levels * 2 * P * sizeof(float), 256);
+}
+
+int aaclip_score_maps(const float* const* seg, int32_t n_levels, const float* text, int32_t text_per_image,
+                      int32_t B, int32_t G, int32_t E, int32_t S, int32_t test_mode, int32_t ksize, float sigma,
+                      void* workspace, size_t workspace_bytes, float* maps_out, const float* det, float* score_out,
+                      void* stream) {
+  if (!seg || !text || !workspace || !maps_out) return fail(AACLIP_EINVAL, "aaclip_score_maps: null argument");
+  if (n_levels <= 0 || n_levels > AACLIP_MAX_LEVELS) return fail(AACLIP_EINVAL, "aaclip_score_maps: n_levels must be 1..4");
+  if (B <= 0 || G <= 0 || E <= 0 || S <= 0) return fail(AACLIP_EINVAL, "aaclip_score_maps: bad shape");
+  if (!test_mode && n_levels != 1) return fail(AACLIP_EINVAL, "aaclip_score_maps: test_mode=0 takes exactly one level");
+  if (test_mode && (ksize < 1 || ksize > MAP_MAXK || (ksize & 1) == 0 || !(sigma > 0.f)))
+    return fail(AACLIP_EINVAL, "aaclip_score_maps: ksize must be odd in 1..15 and sigma > 0");
+  if (test_mode && ksize / 2 >= G) return fail(AACLIP_EINVAL, "aaclip_score_maps: reflect border needs ksize/2 < G");
+  const int P = G * G;
+  if (workspace_bytes < aaclip_score_workspace_bytes(B, n_levels, P)) return fail(AACLIP_EINVAL, "aaclip_score_maps: workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* s = static_cast<float*>(workspace);
+  SegPtrs sp;
+  for (int l = 0; l < 4; ++l) sp.p[l] = (l < n_levels) ? seg[l] : nullptr;
+  for (int l = 0; l < n_levels; ++l) if (!seg[l]) return fail(AACLIP_EINVAL, "aaclip_score_maps: seg[%d] is null", l);
+  const long long tstride = text_per_image ? (long long)E * 2 : 0;
+  {
+    const long long rows = (long long)B * n_levels * P;
+    const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
+    similarity_kernel<<<grid, 256, 0, st>>>(sp, text, tstride, s, B, n_levels, P, E);
+    LAUNCH_CHECK("similarity_kernel");
+  }
+  MapTaps taps;
+  memset(&taps, 0, sizeof(taps));
+  if (test_mode) {
+    // kornia/torchvision Gaussian taps: exp(-x^2 / (2 sigma^2)) on x = -(k-1)/2 .. (k-1)/2, normalised
+    float sum = 0.f;
+    for (int k = 0; k < ksize; ++k) {
+      const float xk = static_cast<float>(k) - 0.5f * static_cast<float>(ksize - 1);
+      taps.w[k] = expf(-0.5f * (xk / sigma) * (xk / sigma));
+      sum += taps.w[k];
+    }
+    for (int k = 0; k < ksize; ++k) taps.w[k] /= sum;
+  }
+  {
+    static bool attr_set = false;
+    const size_t smem = 3 * (size_t)P * sizeof(float);
+    if (smem > 200 * 1024) return fail(AACLIP_EINVAL, "aaclip_score_maps: grid %dx%d too large", G, G);
+    if (!attr_set) {
+      CUDA_TRY(cudaFuncSetAttribute(anomaly_map_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr_set = true;
+    }
+    dim3 grid((S + MAP_ROWS - 1) / MAP_ROWS, B);
+    anomaly_map_kernel<<<grid, 256, smem, st>>>(s, maps_out, n_levels, G, S, test_mode, ksize, taps);
+    LAUNCH_CHECK("anomaly_map_kernel");
+  }
+  if (det != nullptr && score_out != nullptr) {
+    image_score_kernel<<<(B + 7) / 8, 256, 0, st>>>(det, text, tstride, score_out, B, E);
+    LAUNCH_CHECK("image_score_kernel");
+  }
+  return AACLIP_OK;
+}
+
+int aaclip_gemm_bf16(const void* A_bf16, const void* W_bf16, int32_t M, int32_t N, int32_t K, int32_t epi,
+                     const float* bias, float* out_f32, void* out_bf16, int32_t ldo, void* stream) {
+  if (!A_bf16 || !W_bf16) return fail(AACLIP_EINVAL, "aaclip_gemm_bf16: null operand");
+  if (epi == EPI_PATCH_F32) return fail(AACLIP_EINVAL, "aaclip_gemm_bf16: patch epilogue is internal");
+  const bool needs_bias = epi == EPI_BIAS_BF16 || epi == EPI_BIAS_GELU_BF16 || epi == EPI_BIAS_QGELU_BF16 ||
+                          epi == EPI_BIAS_RESID_F32 || epi == EPI_BIAS_F32;
+  const bool bf16_out = epi == EPI_BIAS_BF16 || epi == EPI_BIAS_GELU_BF16 || epi == EPI_BIAS_QGELU_BF16;
+  if (needs_bias && !bias) return fail(AACLIP_EINVAL, "aaclip_gemm_bf16: epilogue %d needs a bias", epi);
+  if (bf16_out && !out_bf16) return fail(AACLIP_EINVAL, "aaclip_gemm_bf16: epilogue %d needs out_bf16", epi);
+  if (!bf16_out && !out_f32) return fail(AACLIP_EINVAL, "aaclip_gemm_bf16: epilogue %d needs out_f32", epi);
+  if (ldo < N || ldo % 8 != 0) return fail(AACLIP_EINVAL, "aaclip_gemm_bf16: ldo must be >= N and a multiple of 8");
+  GemmEpi e;
+  e.bias = bias; e.out_f32 = out_f32; e.out_bf16 = reinterpret_cast<__nv_bfloat16*>(out_bf16); e.ldo = ldo;
+  return launch_gemm(epi, A_bf16, W_bf16, M, N, K, e, static_cast<cudaStream_t>(stream));
+}
+
+int aaclip_attention(const void* qkv_bf16, void* out_bf16, int32_t B, int32_t N, int32_t D, int32_t causal,
+                     void* stream) {
+  if (!qkv_bf16 || !out_bf16) return fail(AACLIP_EINVAL, "aaclip_attention: null argument");
+  return launch_attention(qkv_bf16, out_bf16, B, N, D, causal, static_cast<cudaStream_t>(stream));
+}
+
+int aaclip_layernorm(const float* x, const float* gamma, const float* beta, void* out_bf16, float* out_f32,
+                     int32_t rows_out, int32_t D, int32_t skip_cls_P, void* stream) {
+  if (!x || !gamma || !beta) return fail(AACLIP_EINVAL, "aaclip_layernorm: null argument");
+  if (!out_bf16 && !out_f32) return fail(AACLIP_EINVAL, "aaclip_layernorm: no output requested");
+  return launch_layernorm(x, gamma, beta, out_bf16, out_f32, rows_out, D, skip_cls_P, true, static_cast<cudaStream_t>(stream));
+}
+
+int aaclip_pack_bf16(const float* src, void* dst_bf16, int64_t R, int64_t C, int64_t Cp, void* stream) {
+  if (!src || !dst_bf16 || R <= 0 || C <= 0 || Cp < C) return fail(AACLIP_EINVAL, "aaclip_pack_bf16: bad argument");
+  return launch_pack(src, dst_bf16, R, C, Cp, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,317 @@
+// Memory-bound kernels of the AA-CLIP hot path (everything that is not a tensor-core contraction).
+// All are coalesced / float4-vectorised, one warp per token row where a row reduction is needed, and have a
+// fixed reduction order (batch-invariant: a row's result never depends on which other rows are in the batch).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include "ptx.cuh"
+
+namespace aaclip {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Patch gather ("im2col") for the 14x14/stride-14 patch-embedding conv (model/adapter.py:139,
+// model/transformer.py:359-365):  images fp32 NCHW [B,3,S,S]  ->  A bf16 [B*G*G, KP]  with
+// k = c*ps*ps + ky*ps + kx (the flattening order of conv1.weight[1024,3,14,14]); columns >= 3*ps*ps stay 0.
+// grid = (G, B), block = 256: one CTA per row of patches; reads are fully coalesced image rows.
+__global__ void patch_gather_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ A, int S, int G,
+                                    int ps, int KP) {
+  const int py = blockIdx.x, b = blockIdx.y;
+  const int W = G * ps;  // pixels actually covered by patches (== S when S % ps == 0)
+  for (int cr = 0; cr < 3 * ps; ++cr) {
+    const int c = cr / ps, ky = cr - c * ps;
+    const float* src = img + ((static_cast<size_t>(b) * 3 + c) * S + (py * ps + ky)) * S;
+    for (int x = threadIdx.x; x < W; x += blockDim.x) {
+      const int px = x / ps, kx = x - px * ps;
+      const size_t row = (static_cast<size_t>(b) * G + py) * G + px;
+      A[row * KP + (c * ps + ky) * ps + kx] = __float2bfloat16_rn(src[x]);
+    }
+  }
+  // zero the K padding (the workspace is caller-owned and may hold anything)
+  const int k_raw = 3 * ps * ps, pad = KP - k_raw;
+  for (int i = threadIdx.x; i < G * pad; i += blockDim.x) {
+    const int px = i / pad, k = k_raw + (i - px * pad);
+    A[((static_cast<size_t>(b) * G + py) * G + px) * KP + k] = __float2bfloat16_rn(0.f);
+  }
+}
+
+// x[b*(P+1), :] = class_embedding + positional_embedding[0, :]      (model/adapter.py:143-153)
+__global__ void cls_row_kernel(float* __restrict__ x, const float* __restrict__ cls, const float* __restrict__ pos,
+                               int tokens, int D) {
+  const int b = blockIdx.x;
+  for (int i = threadIdx.x; i < D; i += blockDim.x) x[static_cast<size_t>(b) * tokens * D + i] = cls[i] + pos[i];
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// LayerNorm over D (eps 1e-5), fp32 statistics, one warp per row (model/transformer.py LayerNorm; ln_pre,
+// ln_1, ln_2, ln_post, ln_final). Two-pass in registers: mean, then sum of squared deviations.
+// skipP > 0: output row r = b*skipP + p reads input row b*(skipP+1) + 1 + p (drops the CLS row: x[1:], adapter.py:172).
+// NORMALIZE=false degrades to a plain fp32 -> bf16 cast (operand staging for the adapter GEMM).
+template <int D, bool NORMALIZE>
+__global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, __nv_bfloat16* __restrict__ out_bf16,
+                                 float* __restrict__ out_f32, int rows, int skipP, float eps) {
+  constexpr int V = D / 128;  // float4 per lane
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  size_t in_row = warp;
+  if (skipP > 0) {
+    const int b = warp / skipP;
+    in_row = static_cast<size_t>(b) * (skipP + 1) + 1 + (warp - b * skipP);
+  }
+  const float4* xr = reinterpret_cast<const float4*>(x + in_row * D);
+  float4 v[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) v[j] = xr[lane + 32 * j];
+  if constexpr (NORMALIZE) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < V; ++j) s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+    const float mean = warp_sum(s) * (1.0f / D);
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      const float a = v[j].x - mean, b2 = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
+      ss += (a * a + b2 * b2) + (c * c + d * d);
+    }
+    const float rstd = rsqrtf(warp_sum(ss) * (1.0f / D) + eps);
+    const float4* g4 = reinterpret_cast<const float4*>(gamma);
+    const float4* b4 = reinterpret_cast<const float4*>(beta);
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      const float4 g = __ldg(g4 + lane + 32 * j), bb = __ldg(b4 + lane + 32 * j);
+      v[j].x = (v[j].x - mean) * rstd * g.x + bb.x;
+      v[j].y = (v[j].y - mean) * rstd * g.y + bb.y;
+      v[j].z = (v[j].z - mean) * rstd * g.z + bb.z;
+      v[j].w = (v[j].w - mean) * rstd * g.w + bb.w;
+    }
+  }
+  if (out_bf16 != nullptr) {
+    uint2* o = reinterpret_cast<uint2*>(out_bf16 + static_cast<size_t>(warp) * D);
+#pragma unroll
+    for (int j = 0; j < V; ++j)
+      o[lane + 32 * j] = make_uint2(ptx::pack_bf16x2(v[j].x, v[j].y), ptx::pack_bf16x2(v[j].z, v[j].w));
+  }
+  if (out_f32 != nullptr) {
+    float4* o = reinterpret_cast<float4*>(out_f32 + static_cast<size_t>(warp) * D);
+#pragma unroll
+    for (int j = 0; j < V; ++j) o[lane + 32 * j] = v[j];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Residual adapter blend (model/adapter.py:163-170 visual, :286-295 text):
+//   a <- a * ||x||_2 / ||a||_2  (per token, no eps) ;  x <- w*a + (1-w)*x.   a = LeakyReLU(x W^T) from the GEMM.
+// Optionally also emits bf16(x_new) (operand for the next GEMM). One warp per row.
+template <int D>
+__global__ void adapter_blend_kernel(float* __restrict__ x, const float* __restrict__ a, int rows, float w,
+                                     float one_minus_w) {
+  constexpr int V = D / 128;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  float4* xr = reinterpret_cast<float4*>(x + static_cast<size_t>(warp) * D);
+  const float4* ar = reinterpret_cast<const float4*>(a + static_cast<size_t>(warp) * D);
+  float4 xv[V], av[V];
+  float sx = 0.f, sa = 0.f;
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    xv[j] = xr[lane + 32 * j];
+    av[j] = ar[lane + 32 * j];
+    sx += (xv[j].x * xv[j].x + xv[j].y * xv[j].y) + (xv[j].z * xv[j].z + xv[j].w * xv[j].w);
+    sa += (av[j].x * av[j].x + av[j].y * av[j].y) + (av[j].z * av[j].z + av[j].w * av[j].w);
+  }
+  const float nx = sqrtf(warp_sum(sx)), na = sqrtf(warp_sum(sa));
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    float4 o;
+    o.x = w * (av[j].x * nx / na) + one_minus_w * xv[j].x;
+    o.y = w * (av[j].y * nx / na) + one_minus_w * xv[j].y;
+    o.z = w * (av[j].z * nx / na) + one_minus_w * xv[j].z;
+    o.w = w * (av[j].w * nx / na) + one_minus_w * xv[j].w;
+    xr[lane + 32 * j] = o;
+  }
+}
+
+// F.normalize(t, dim=-1) in place: t / max(||t||_2, 1e-12)   (model/adapter.py:182-184). One warp per row.
+template <int D>
+__global__ void l2norm_rows_kernel(float* __restrict__ t, int rows) {
+  constexpr int V = D / 128;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  float4* r = reinterpret_cast<float4*>(t + static_cast<size_t>(warp) * D);
+  float4 v[V];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    v[j] = r[lane + 32 * j];
+    s += (v[j].x * v[j].x + v[j].y * v[j].y) + (v[j].z * v[j].z + v[j].w * v[j].w);
+  }
+  const float inv = 1.0f / fmaxf(sqrtf(warp_sum(s)), 1e-12f);
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    v[j].x *= inv; v[j].y *= inv; v[j].z *= inv; v[j].w *= inv;
+    r[lane + 32 * j] = v[j];
+  }
+}
+
+// det_token = normalized_rows.mean(dim=1): [B,P,E] -> [B,E]   (model/adapter.py:184). Fixed summation order.
+__global__ void mean_over_patches_kernel(const float* __restrict__ t, float* __restrict__ out, int P, int E) {
+  const int b = blockIdx.y;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const float* src = t + static_cast<size_t>(b) * P * E + e;
+  float s = 0.f;
+  for (int p = 0; p < P; ++p) s += src[static_cast<size_t>(p) * E];
+  out[static_cast<size_t>(b) * E + e] = s / static_cast<float>(P);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Patch-text similarity, forward_utils.py:199: s[b,l,c,p] = 100 * <f_l[b,p,:], text[(b),:,c]>, c in {0,1}.
+// One warp per patch row, both anchors in one pass over the row. text_bstride = 0 for a shared [E,2] anchor,
+// E*2 for per-image anchors [B,E,2].
+struct SegPtrs { const float* p[4]; };
+
+__global__ void similarity_kernel(SegPtrs seg, const float* __restrict__ text, long long text_bstride,
+                                  float* __restrict__ s, int B, int L, int P, int E) {
+  const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long total = static_cast<long long>(B) * L * P;
+  if (warp >= total) return;
+  const int p = static_cast<int>(warp % P);
+  const int l = static_cast<int>((warp / P) % L);
+  const int b = static_cast<int>(warp / (static_cast<long long>(P) * L));
+  const float* f = seg.p[l] + (static_cast<size_t>(b) * P + p) * E;
+  const float* t = text + static_cast<size_t>(b) * text_bstride;
+  float s0 = 0.f, s1 = 0.f;
+  for (int i = lane; i < E; i += 32) {
+    const float fv = f[i];
+    const float2 tv = __ldg(reinterpret_cast<const float2*>(t) + i);
+    s0 = fmaf(fv, tv.x, s0);
+    s1 = fmaf(fv, tv.y, s1);
+  }
+  s0 = warp_sum(s0);
+  s1 = warp_sum(s1);
+  if (lane == 0) {
+    float* o = s + ((static_cast<size_t>(b) * L + l) * 2) * P + p;
+    o[0] = 100.0f * s0;
+    o[P] = 100.0f * s1;
+  }
+}
+
+// image score, test_last.py:90-92 at the well-posed level: ((det[b,:] @ text[(b),:,1]) + 1) / 2
+__global__ void image_score_kernel(const float* __restrict__ det, const float* __restrict__ text,
+                                   long long text_bstride, float* __restrict__ score, int B, int E) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= B) return;
+  const float* d = det + static_cast<size_t>(warp) * E;
+  const float* t = text + static_cast<size_t>(warp) * text_bstride;
+  float s = 0.f;
+  for (int i = lane; i < E; i += 32) s = fmaf(d[i], __ldg(t + 2 * i + 1), s);
+  s = warp_sum(s);
+  if (lane == 0) score[warp] = (s + 1.0f) * 0.5f;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Anomaly-map tail, forward_utils.py:200-215 (+ the level sum of test_last.py:143,149).
+//  test mode : g_l = (s1 + 1 - s0)/2 on the GxG grid; Gaussian blur ksize x ksize (reflect border, kornia
+//              gaussian_blur2d); bilinear upsample align_corners=True to SxS; summed over the L levels given.
+//              out [B, S, S]  (L = 1 reproduces a single calculate_similarity_map(test=True) call).
+//  train mode: both channels upsampled, then softmax over the channel pair. out [B, 2, S, S], L must be 1.
+// grid = (ceil(S / ROWS), B); every CTA rebuilds the (tiny) blurred grid in smem and writes ROWS output rows
+// with fully coalesced stores.
+constexpr int MAP_ROWS = 14;
+constexpr int MAP_MAXK = 15;
+
+struct MapTaps { float w[MAP_MAXK]; };
+
+__device__ __forceinline__ int reflect_idx(int i, int n) {
+  if (i < 0) i = -i;
+  if (i >= n) i = 2 * n - 2 - i;
+  return i;
+}
+
+__global__ void anomaly_map_kernel(const float* __restrict__ s, float* __restrict__ out, int L, int G, int S,
+                                   int test_mode, int ksize, MapTaps taps) {
+  extern __shared__ float sm[];
+  const int P = G * G;
+  float* g0 = sm;            // test: summed blurred grid ; train: channel 0
+  float* g1 = sm + P;        // scratch / channel 1
+  float* g2 = sm + 2 * P;    // scratch
+  const int b = blockIdx.y;
+  const float* sb = s + static_cast<size_t>(b) * L * 2 * P;
+
+  if (test_mode) {
+    for (int i = threadIdx.x; i < P; i += blockDim.x) g0[i] = 0.f;
+    __syncthreads();
+    const int r = ksize / 2;
+    for (int l = 0; l < L; ++l) {
+      const float* s0 = sb + static_cast<size_t>(l) * 2 * P;
+      const float* s1 = s0 + P;
+      for (int i = threadIdx.x; i < P; i += blockDim.x) g1[i] = (s1[i] + 1.0f - s0[i]) / 2.0f;
+      __syncthreads();
+      // horizontal pass
+      for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        const int y = i / G, x = i - y * G;
+        float acc = 0.f;
+        for (int k = 0; k < ksize; ++k) acc = fmaf(taps.w[k], g1[y * G + reflect_idx(x + k - r, G)], acc);
+        g2[i] = acc;
+      }
+      __syncthreads();
+      // vertical pass, accumulated over levels
+      for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        const int y = i / G, x = i - y * G;
+        float acc = 0.f;
+        for (int k = 0; k < ksize; ++k) acc = fmaf(taps.w[k], g2[reflect_idx(y + k - r, G) * G + x], acc);
+        g0[i] += acc;
+      }
+      __syncthreads();
+    }
+  } else {
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+      g0[i] = sb[i];
+      g1[i] = sb[P + i];
+    }
+    __syncthreads();
+  }
+
+  // bilinear, align_corners=True (ATen upsample_bilinear2d index/lambda arithmetic)
+  const float scale = (S > 1) ? static_cast<float>(G - 1) / static_cast<float>(S - 1) : 0.f;
+  const int y_begin = blockIdx.x * MAP_ROWS;
+  const int y_end = min(S, y_begin + MAP_ROWS);
+  for (int y = y_begin; y < y_end; ++y) {
+    const float fy = scale * y;
+    const int y0 = static_cast<int>(fy);
+    const int yp = (y0 < G - 1) ? 1 : 0;
+    const float ly1 = fy - y0, ly0 = 1.0f - ly1;
+    for (int x = threadIdx.x; x < S; x += blockDim.x) {
+      const float fx = scale * x;
+      const int x0 = static_cast<int>(fx);
+      const int xp = (x0 < G - 1) ? 1 : 0;
+      const float lx1 = fx - x0, lx0 = 1.0f - lx1;
+      const int i00 = y0 * G + x0, i01 = i00 + xp, i10 = i00 + yp * G, i11 = i10 + xp;
+      const float v0 = ly0 * (lx0 * g0[i00] + lx1 * g0[i01]) + ly1 * (lx0 * g0[i10] + lx1 * g0[i11]);
+      if (test_mode) {
+        out[(static_cast<size_t>(b) * S + y) * S + x] = v0;
+      } else {
+        const float v1 = ly0 * (lx0 * g1[i00] + lx1 * g1[i01]) + ly1 * (lx0 * g1[i10] + lx1 * g1[i11]);
+        const float m = fmaxf(v0, v1);
+        const float e0 = expf(v0 - m), e1 = expf(v1 - m);
+        const float inv = 1.0f / (e0 + e1);
+        out[((static_cast<size_t>(b) * 2 + 0) * S + y) * S + x] = e0 * inv;
+        out[((static_cast<size_t>(b) * 2 + 1) * S + y) * S + x] = e1 * inv;
+      }
+    }
+  }
+}
+
+}  // namespace aaclip

@@ -1,0 +1,230 @@
+"""Torch-tensor front end of the C ABI (include/aaclip.h). PyTorch is used only for device memory and streams.
+
+Everything here requires a CUDA (sm_100) device and the in-tree libaaclip_b200.so; nothing falls back to PyTorch
+ops or to the CPU.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+
+
+def _ptr(t: Optional[torch.Tensor]) -> ctypes.c_void_p:
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _stream() -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(*tensors: torch.Tensor):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("aaclip_b200: tensors must live on a CUDA (sm_100a) device; there is no CPU path")
+
+
+def _ptr_array(tensors: Sequence[Optional[torch.Tensor]]):
+    arr = (ctypes.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = 0 if t is None else t.data_ptr()
+    return arr
+
+
+# ---------------------------------------------------------------------------------------- building blocks
+def pack_bf16(src: torch.Tensor, padded_cols: Optional[int] = None) -> torch.Tensor:
+    """fp32 [R,C] -> bf16 [R,Cp] zero padded (aaclip_pack_bf16)."""
+    _need_cuda(src)
+    src = src.contiguous().float()
+    R, C = src.shape
+    Cp = C if padded_cols is None else padded_cols
+    dst = torch.empty((R, Cp), dtype=torch.bfloat16, device=src.device)
+    _lib.check(_lib.load().aaclip_pack_bf16(_ptr(src), _ptr(dst), R, C, Cp, _stream()), "aaclip_pack_bf16")
+    return dst
+
+
+def gemm_bf16(a: torch.Tensor, w: torch.Tensor, epi: int, bias: Optional[torch.Tensor] = None,
+              out_f32: Optional[torch.Tensor] = None, out_bf16: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """C = A[M,K] @ W[N,K]^T with fused epilogue `epi` (aaclip_gemm_bf16). Returns the primary output."""
+    _need_cuda(a, w)
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.is_contiguous() and w.is_contiguous()
+    M, K = a.shape
+    N = w.shape[0]
+    assert w.shape[1] == K
+    bf16_out = epi in (_lib.EPI_BIAS_BF16, _lib.EPI_BIAS_GELU_BF16, _lib.EPI_BIAS_QGELU_BF16)
+    if bf16_out and out_bf16 is None:
+        out_bf16 = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
+    if not bf16_out and out_f32 is None:
+        out_f32 = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    _lib.check(
+        _lib.load().aaclip_gemm_bf16(_ptr(a), _ptr(w), M, N, K, epi, _ptr(bias), _ptr(out_f32), _ptr(out_bf16), N,
+                                     _stream()),
+        "aaclip_gemm_bf16")
+    return out_bf16 if bf16_out else out_f32
+
+
+def attention(qkv: torch.Tensor, causal: bool = False) -> torch.Tensor:
+    """qkv bf16 [B,N,3D] -> bf16 [B,N,D] (aaclip_attention)."""
+    _need_cuda(qkv)
+    assert qkv.dtype == torch.bfloat16 and qkv.is_contiguous() and qkv.dim() == 3
+    B, N, D3 = qkv.shape
+    D = D3 // 3
+    out = torch.empty((B, N, D), dtype=torch.bfloat16, device=qkv.device)
+    _lib.check(_lib.load().aaclip_attention(_ptr(qkv), _ptr(out), B, N, D, int(causal), _stream()),
+               "aaclip_attention")
+    return out
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, skip_cls_P: int = 0,
+              want_bf16: bool = True, want_f32: bool = False) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
+    """LayerNorm(eps=1e-5) over the last dim of fp32 x [rows, D] (aaclip_layernorm)."""
+    _need_cuda(x, gamma, beta)
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 2
+    rows_in, D = x.shape
+    rows = rows_in if skip_cls_P == 0 else rows_in // (skip_cls_P + 1) * skip_cls_P
+    ob = torch.empty((rows, D), dtype=torch.bfloat16, device=x.device) if want_bf16 else None
+    of = torch.empty((rows, D), dtype=torch.float32, device=x.device) if want_f32 else None
+    _lib.check(_lib.load().aaclip_layernorm(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(ob), _ptr(of), rows, D,
+                                            skip_cls_P, _stream()), "aaclip_layernorm")
+    return ob, of
+
+
+def score_maps(seg: Sequence[torch.Tensor], text: torch.Tensor, img_size: int, test: bool = True, ksize: int = 7,
+               sigma: float = 1.0, det: Optional[torch.Tensor] = None
+               ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """Similarity -> (blur) -> bilinear upsample (-> level sum | softmax) and optional image score (aaclip_score_maps).
+
+    seg: list of [B,P,E] fp32 unit-norm patch features; text: [E,2] or [B,E,2].
+    test=True  -> maps [B,S,S], summed over the given levels; test=False -> one level, maps [B,2,S,S].
+    """
+    _need_cuda(text, *seg)
+    seg = [s.contiguous().float() for s in seg]
+    text = text.contiguous().float()
+    B, P, E = seg[0].shape
+    G = int(round(P ** 0.5))
+    if G * G != P:
+        raise ValueError(f"patch count {P} is not a perfect square")
+    per_image = int(text.dim() == 3)
+    if text.shape[-2:] != (E, 2) or (per_image and text.shape[0] != B):
+        raise ValueError(f"text anchors must be [E,2] or [B,E,2], got {tuple(text.shape)}")
+    L = len(seg)
+    lib = _lib.load()
+    ws_bytes = lib.aaclip_score_workspace_bytes(B, L, P)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=text.device)
+    maps = torch.empty((B, img_size, img_size) if test else (B, 2, img_size, img_size), dtype=torch.float32,
+                       device=text.device)
+    score = None
+    if det is not None:
+        det = det.contiguous().float()
+        score = torch.empty((B,), dtype=torch.float32, device=text.device)
+    _lib.check(
+        lib.aaclip_score_maps(_ptr_array(seg), L, _ptr(text), per_image, B, G, E, img_size, int(test), ksize,
+                              float(sigma), _ptr(ws), ws_bytes, _ptr(maps), _ptr(det), _ptr(score), _stream()),
+        "aaclip_score_maps")
+    return maps, score
+
+
+# ---------------------------------------------------------------------------------------- the tower
+DEFAULT_CFG = dict(img_size=518, patch=14, width=1024, heads=16, layers=24, mlp_dim=4096, embed_dim=768,
+                   adapt_until=6, levels=(6, 12, 18, 24), act=_lib.ACT_GELU_ERF, proj_relu=0, adapt_weight=0.1,
+                   max_batch=64)
+
+
+class AaclipEngine:
+    """Owns one AaclipHandle: packed weights on the device + the forward entry point."""
+
+    def __init__(self, device: torch.device | str = "cuda", **cfg):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("AaclipEngine needs a CUDA (sm_100a) device; there is no CPU path")
+        full = dict(DEFAULT_CFG)
+        full.update(cfg)
+        self.cfg = full
+        c = _lib.AaclipCfg()
+        for k in ("img_size", "patch", "width", "heads", "layers", "mlp_dim", "embed_dim", "adapt_until", "act",
+                  "proj_relu", "max_batch"):
+            setattr(c, k, int(full[k]))
+        c.adapt_weight = float(full["adapt_weight"])
+        levels = list(full["levels"])
+        c.n_levels = len(levels)
+        for i, lv in enumerate(levels):
+            c.levels[i] = int(lv)
+        self._lib = _lib.load()
+        self._h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.aaclip_create(ctypes.byref(c), ctypes.byref(self._h)), "aaclip_create")
+        self.G = full["img_size"] // full["patch"]
+        self.P = self.G * self.G
+        self.N = self.P + 1
+        self.n_levels = len(levels)
+        self._ws: Optional[torch.Tensor] = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.aaclip_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- weights
+    def set_weight(self, name: str, t: torch.Tensor):
+        t = t.detach().to(self.device, torch.float32).contiguous()
+        shape = (ctypes.c_int64 * t.dim())(*t.shape)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.aaclip_set_weight(self._h, name.encode(), _ptr(t), shape, t.dim(), _stream()),
+                       f"aaclip_set_weight({name})")
+            # the engine copies on the current stream; keep `t` alive until the copy has been enqueued and done
+            torch.cuda.current_stream().synchronize()
+
+    def load_state_dict(self, sd: Dict[str, torch.Tensor], prefixes=("image_encoder.", "image_adapter.")):
+        """Feed every tensor of an AdaptedCLIP state_dict whose key starts with one of `prefixes`."""
+        n = 0
+        for k, v in sd.items():
+            if k.startswith(prefixes) and not k.endswith("proj") and ".attn_pool" not in k:
+                self.set_weight(k, v)
+                n += 1
+        return n
+
+    @property
+    def missing(self) -> int:
+        return self._lib.aaclip_missing_weights(self._h)
+
+    def workspace_bytes(self, B: int) -> int:
+        return self._lib.aaclip_workspace_bytes(self._h, B)
+
+    # -- forward
+    def forward(self, images: torch.Tensor, want_tokens: bool = False, want_cls: bool = False):
+        """images [B,3,S,S] fp32 on the engine's device -> (seg list of [B,P,E], det [B,E], tokens|None, cls|None)."""
+        _need_cuda(images)
+        images = images.contiguous().float()
+        B = images.shape[0]
+        S = self.cfg["img_size"]
+        if tuple(images.shape[1:]) != (3, S, S):
+            raise ValueError(f"expected images [B,3,{S},{S}], got {tuple(images.shape)}")
+        E, W = self.cfg["embed_dim"], self.cfg["width"]
+        need = self.workspace_bytes(B)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        dev = self.device
+        seg = [torch.empty((B, self.P, E), dtype=torch.float32, device=dev) for _ in range(self.n_levels)]
+        det = torch.empty((B, E), dtype=torch.float32, device=dev)
+        tokens = [torch.empty((B, self.P, W), dtype=torch.float32, device=dev) for _ in range(self.n_levels)] \
+            if want_tokens else None
+        cls = torch.empty((B, W), dtype=torch.float32, device=dev) if want_cls else None
+        tok_arr = _ptr_array(tokens) if tokens is not None else None
+        with torch.cuda.device(dev):
+            _lib.check(
+                self._lib.aaclip_forward(self._h, _ptr(images), B, _ptr(self._ws), self._ws.numel(), _ptr_array(seg),
+                                         _ptr(det), tok_arr, _ptr(cls), _stream()), "aaclip_forward")
+        return seg, det, tokens, cls
+
+    @property
+    def last_launch_count(self) -> int:
+        return self._lib.aaclip_last_launch_count(self._h)

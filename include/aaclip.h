@@ -1,0 +1,153 @@
+/*
+ * aaclip.h -- C ABI of the B200-native AA-CLIP inference hot path (libaaclip_b200.so, sm_100a).
+ *
+ * The reference (liu20050510/AA-CLIP-IQM) has no FFI/plugin interface: its hot path sits behind plain Python
+ * methods. Each entry point below names the reference code it replaces (file:line relative to the reference
+ * root). The only caller is this repo's Python mirror of that surface (aa-clip-iqm_b200/model/adapter.py,
+ * aa-clip-iqm_b200/forward_utils.py); INTEGRATION.md shows the ctypes binding a reference maintainer would add.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every data pointer is CALLER-OWNED DEVICE memory (e.g. torch-allocated)
+ *    unless the parameter name ends in _host;
+ *  - all work is enqueued asynchronously on the `stream` argument (a cudaStream_t passed as void*); no hidden
+ *    synchronisation, no allocation after aaclip_create(), so calls may be captured in a CUDA graph;
+ *  - return 0 on success, a negative AACLIP_E* code on failure; never throws across the ABI;
+ *    aaclip_last_error() returns a thread-local message for the last failure;
+ *  - a handle is bound to the device that was current at aaclip_create() and is not thread-safe.
+ */
+#ifndef AACLIP_H_
+#define AACLIP_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AACLIP_OK 0
+#define AACLIP_EINVAL (-1)   /* bad argument / unsupported shape */
+#define AACLIP_ECUDA (-2)    /* CUDA runtime / driver error */
+#define AACLIP_ESTATE (-3)   /* weights missing, wrong call order */
+#define AACLIP_ENOSYS (-4)   /* not an sm_100 device / driver entry point missing */
+
+#define AACLIP_MAX_LEVELS 4
+
+/* activation of the MLP: the reference runs nn.GELU (erf) -- model/model.py:84; QuickGELU only with
+ * force_quick_gelu=True -- model/clip.py:151-153, model/transformer.py:46-49 */
+#define AACLIP_ACT_GELU_ERF 0
+#define AACLIP_ACT_QUICK_GELU 1
+
+/* epilogue selectors of aaclip_gemm_bf16 (unit-test / building-block entry point) */
+#define AACLIP_EPI_BIAS_BF16 0
+#define AACLIP_EPI_BIAS_GELU_BF16 1
+#define AACLIP_EPI_BIAS_QGELU_BF16 2
+#define AACLIP_EPI_BIAS_RESID_F32 3
+#define AACLIP_EPI_F32 4
+#define AACLIP_EPI_LEAKY_F32 5
+#define AACLIP_EPI_BIAS_F32 7
+
+/* Static description of the adapted visual tower (model/model_configs/ViT-L-14-336.json +
+ * AdaptedCLIP.__init__, model/adapter.py:11-47). */
+typedef struct AaclipCfg {
+  int32_t img_size;      /* 518 (any multiple of patch) */
+  int32_t patch;         /* 14 */
+  int32_t width;         /* 1024 */
+  int32_t heads;         /* 16 (head dim must be 64) */
+  int32_t layers;        /* 24 */
+  int32_t mlp_dim;       /* 4096 */
+  int32_t embed_dim;     /* 768 */
+  int32_t adapt_until;   /* residual adapters after blocks 0..adapt_until-1 (6) */
+  int32_t n_levels;      /* 4 */
+  int32_t levels[AACLIP_MAX_LEVELS]; /* 1-based tapped blocks: 6,12,18,24 (ascending; last one feeds det_proj) */
+  int32_t act;           /* AACLIP_ACT_* */
+  int32_t proj_relu;     /* SimpleProj(relu=...) : LeakyReLU after seg/det projections */
+  float adapt_weight;    /* i_w = 0.1 */
+  int32_t max_batch;     /* largest B accepted by aaclip_forward */
+} AaclipCfg;
+
+typedef struct AaclipHandle AaclipHandle;
+
+/* Library / build info: "aaclip_b200 <version> sm_100a". */
+const char* aaclip_version(void);
+/* Thread-local description of the last error returned on this thread. */
+const char* aaclip_last_error(void);
+
+/* Allocates the packed-weight arena (bf16 GEMM operands, fp32 norms/biases) on the current device.
+ * Replaces: building the nn.Module tree in create_model (model/clip.py:84-202) + AdaptedCLIP.__init__. */
+int aaclip_create(const AaclipCfg* cfg, AaclipHandle** out);
+void aaclip_destroy(AaclipHandle* h);
+
+/* Hands one fp32 DEVICE tensor to the engine, which copies and repacks it (caller keeps ownership).
+ * `name` is the reference state_dict key relative to AdaptedCLIP, e.g.
+ *   "image_encoder.conv1.weight" [W,3,p,p]      "image_encoder.class_embedding" [W]
+ *   "image_encoder.positional_embedding" [N,W]  "image_encoder.ln_pre.weight" / ".bias" / "ln_post.*"
+ *   "image_encoder.transformer.resblocks.<i>.{ln_1,ln_2}.{weight,bias}"
+ *   "image_encoder.transformer.resblocks.<i>.attn.{in_proj_weight,in_proj_bias}", ".attn.out_proj.{weight,bias}"
+ *   "image_encoder.transformer.resblocks.<i>.mlp.{c_fc,c_proj}.{weight,bias}"
+ *   "image_adapter.layer_adapters.<i>.fc.0.weight", "image_adapter.seg_proj.<l>.fc.weight" (or ".fc.0.weight"),
+ *   "image_adapter.det_proj.fc.weight" (or ".fc.0.weight")
+ * Replaces: load_state_dict (model/clip.py:132) / checkpoint loading (test_last.py:231-247). */
+int aaclip_set_weight(AaclipHandle* h, const char* name, const float* data, const int64_t* shape, int32_t ndim,
+                      void* stream);
+/* Number of tensors still missing before aaclip_forward may run (0 = ready). */
+int aaclip_missing_weights(AaclipHandle* h);
+
+/* Bytes of scratch aaclip_forward needs for a batch of B images (256-byte aligned pointer expected). */
+size_t aaclip_workspace_bytes(AaclipHandle* h, int32_t B);
+
+/* Adapted visual tower. Replaces AdaptedCLIP.forward lines model/adapter.py:137-184:
+ * patch embed, CLS + positional embedding, ln_pre, 24 pre-LN residual attention blocks
+ * (model/transformer.py:239-258) with residual adapters on the first `adapt_until`, token taps + ln_post,
+ * seg/det projections, L2 normalisation, patch-mean of the det token.
+ *   images      [B,3,S,S] fp32 NCHW
+ *   seg_out[l]  [B,P,E] fp32, unit-norm rows            (l < n_levels)
+ *   det_out     [B,E]   fp32
+ *   tokens_out  optional (NULL or array of n_levels pointers, each NULL or [B,P,W] fp32): ln_post(tokens[l]),
+ *               the input of the reference's IQM branch (model/adapter.py:202-205)
+ *   cls_out     optional [B,W] fp32: x[:,0,:] after the last block, no ln_post (model/adapter.py:190) */
+int aaclip_forward(AaclipHandle* h, const float* images, int32_t B, void* workspace, size_t workspace_bytes,
+                   float* const* seg_out, float* det_out, float* const* tokens_out, float* cls_out, void* stream);
+
+/* Bytes of scratch aaclip_score_maps needs. */
+size_t aaclip_score_workspace_bytes(int32_t B, int32_t n_levels, int32_t P);
+
+/* Patch-text similarity maps. Replaces forward_utils.calculate_similarity_map (forward_utils.py:196-216), the
+ * level sum of test_last.py:143,149 and the image score of test_last.py:90-92 (well-posed form).
+ *   seg[l]      [B,P,E] fp32 (n_levels pointers; P = G*G)
+ *   text        [E,2] (text_per_image = 0) or [B,E,2] (text_per_image = 1) fp32; column 0 normal, 1 abnormal
+ *   test_mode=1: maps_out [B,S,S] = sum_l upsample(blur((s1 + 1 - s0)/2))      ksize/sigma: 7/1.0 Industrial,
+ *                9/1.5 Medical (forward_utils.py:205-206); ksize odd <= 15
+ *   test_mode=0: n_levels must be 1; maps_out [B,2,S,S] = softmax_c(upsample(s_c))  (training-time form)
+ *   det/score_out optional: score_out[b] = (det[b,:] . text[:,1] + 1) / 2 */
+int aaclip_score_maps(const float* const* seg, int32_t n_levels, const float* text, int32_t text_per_image,
+                      int32_t B, int32_t G, int32_t E, int32_t S, int32_t test_mode, int32_t ksize, float sigma,
+                      void* workspace, size_t workspace_bytes, float* maps_out, const float* det, float* score_out,
+                      void* stream);
+
+/* Kernel launches enqueued by the last aaclip_forward on this handle (for bench.py's gpu_launches). */
+int aaclip_last_launch_count(AaclipHandle* h);
+
+/* ---- building blocks, exported for the parity tests (each is exactly what aaclip_forward launches) ---- */
+
+/* C[M,N] = A[M,K] * W[N,K]^T with a fused epilogue (tcgen05/TMEM/TMA GEMM). A, W bf16 row-major.
+ * N % 256 == 0, K % 64 == 0. out_f32 / out_bf16 as required by `epi`; ldo = leading dim of outputs. */
+int aaclip_gemm_bf16(const void* A_bf16, const void* W_bf16, int32_t M, int32_t N, int32_t K, int32_t epi,
+                     const float* bias, float* out_f32, void* out_bf16, int32_t ldo, void* stream);
+
+/* Fused multi-head attention: qkv bf16 [B,N,3*D] -> out bf16 [B,N,D]; head dim 64; softmax scale 1/8. */
+int aaclip_attention(const void* qkv_bf16, void* out_bf16, int32_t B, int32_t N, int32_t D, int32_t causal,
+                     void* stream);
+
+/* LayerNorm(eps=1e-5) rows of fp32 x [rows_in, D] (D in {768,1024}); out_bf16 and/or out_f32 may be NULL.
+ * skip_cls_P > 0 drops the first row of every (P+1)-row group (x[1:] of each image). */
+int aaclip_layernorm(const float* x, const float* gamma, const float* beta, void* out_bf16, float* out_f32,
+                     int32_t rows_out, int32_t D, int32_t skip_cls_P, void* stream);
+
+/* fp32 [R,C] -> bf16 [R,Cp] (Cp >= C, zero padded): the weight / operand packing used by aaclip_set_weight. */
+int aaclip_pack_bf16(const float* src, void* dst_bf16, int64_t R, int64_t C, int64_t Cp, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AACLIP_H_ */
