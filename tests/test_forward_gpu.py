@@ -1,0 +1,116 @@
+"""GPU parity (through the C ABI): the sm_100a tower + scoring kernels against
+  (1) the committed golden vectors made by executing the unmodified reference (tests/golden, oracle/gen_golden.py),
+  (2) the CPU oracle restatement run on the box on the same seeded inputs.
+Tolerances are BASELINE.json's: anomaly maps <= 1e-2 abs (bf16 tensor-core operands), image scores <= 1e-3."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden
+
+pytestmark = pytest.mark.gpu
+
+MAP_TOL = 1e-2     # north_star: anomaly maps within 1e-2 abs in bf16 mode
+SCORE_TOL = 1e-3   # north_star: image scores within 1e-3
+FEAT_TOL = 2e-3    # unit-norm patch features (cosine-level error, not in north_star; keeps the maps honest)
+
+
+def _engine_outputs(name, domain="Industrial"):
+    import aaclip_b200  # noqa: F401
+    from aaclip_b200 import engine, weights
+    fx = golden(name)
+    S, B, seed, relu = int(fx["img_size"]), int(fx["batch"]), int(fx["seed"]), bool(fx["relu"])
+    sd = weights.make_visual_state_dict(seed=seed, img_size=S, relu=relu)
+    eng = engine.AaclipEngine("cuda", img_size=S, proj_relu=int(relu), max_batch=max(B, 4))
+    eng.load_state_dict(sd)
+    assert eng.missing == 0
+    images = weights.make_images(seed, B, S).cuda()
+    text = weights.make_text_anchor(seed).cuda()
+    seg, det, tokens, cls = eng.forward(images, want_tokens=True, want_cls=True)
+    ks, sg = (7, 1.0) if domain == "Industrial" else (9, 1.5)
+    maps, score = engine.score_maps(seg, text, S, test=True, ksize=ks, sigma=sg, det=det)
+    torch.cuda.synchronize()
+    return fx, eng, sd, images, text, seg, det, tokens, cls, maps, score
+
+
+@pytest.mark.parametrize("name", ["vitl_224_b2", "vitl_224_b1_relu", "vitl_518_b1"])
+def test_forward_matches_reference_golden(name):
+    fx, eng, sd, images, text, seg, det, tokens, cls, maps, score = _engine_outputs(name)
+    rows = torch.as_tensor(fx["rows"]).cuda()
+    for l in range(4):
+        err = (seg[l][:, rows, :].cpu().numpy() - fx["seg_rows"][l])
+        assert np.abs(err).max() < FEAT_TOL, f"level {l} patch features off by {np.abs(err).max():.3e}"
+        n = seg[l].norm(dim=-1)
+        assert torch.allclose(n, torch.ones_like(n), atol=1e-5)
+    assert np.abs(det.cpu().numpy() - fx["det"]).max() < FEAT_TOL
+    assert np.abs(score.cpu().numpy() - fx["score"]).max() < SCORE_TOL
+    merr = np.abs(maps.cpu().numpy() - fx["maps_industrial"])
+    print(f"{name}: map max abs err {merr.max():.4e} mean {merr.mean():.4e} (range {fx['maps_industrial'].min():.2f}.."
+          f"{fx['maps_industrial'].max():.2f})")
+    assert merr.max() < MAP_TOL
+    assert eng.last_launch_count > 150
+
+
+def test_medical_domain_and_train_mode_maps():
+    from aaclip_b200 import engine
+    fx, eng, sd, images, text, seg, det, tokens, cls, maps, score = _engine_outputs("vitl_224_b2", domain="Medical")
+    assert np.abs(maps.cpu().numpy()[:, ::2, ::2] - fx["maps_medical"]).max() < MAP_TOL
+    S = int(fx["img_size"])
+    tr, _ = engine.score_maps(seg[:1], text, S, test=False)
+    assert np.abs(tr.cpu().numpy()[:, :, ::4, ::4] - fx["train0"]).max() < 5e-3
+    # per-image anchors == shared anchor when equal
+    m1, s1 = engine.score_maps(seg, text, S, test=True, ksize=9, sigma=1.5, det=det)
+    m2, s2 = engine.score_maps(seg, text[None].repeat(seg[0].shape[0], 1, 1).contiguous(), S, test=True, ksize=9,
+                               sigma=1.5, det=det)
+    assert torch.equal(m1, m2) and torch.equal(s1, s2)
+
+
+def test_forward_matches_cpu_oracle_on_the_box_and_exports_iqm_inputs():
+    """Same seeded inputs through the oracle on the box's CPU (224 px so it takes seconds)."""
+    from oracle import aaclip_oracle as orc
+    fx, eng, sd, images, text, seg, det, tokens, cls, maps, score = _engine_outputs("vitl_224_b2")
+    with torch.no_grad():
+        o = orc.predict(sd, images.cpu(), text.cpu(), int(fx["img_size"]), domain="Industrial")
+    assert (maps.cpu() - o["maps"]).abs().max().item() < MAP_TOL
+    assert (score.cpu() - o["score"]).abs().max().item() < SCORE_TOL
+    for l in range(4):
+        assert (seg[l].cpu() - o["seg"][l]).abs().max().item() < FEAT_TOL
+        # ln_post(tokens): the IQM branch's input (model/adapter.py:202-205); values are O(1)
+        assert (tokens[l].cpu() - o["tokens"][l]).abs().max().item() < 5e-2
+    assert (cls.cpu() - o["cls"]).abs().max().item() < 5e-2
+
+
+def test_batch_invariance_and_determinism():
+    """Data-parallel sharding must not change per-image results: image 0 alone == image 0 inside a batch, bit for bit."""
+    import aaclip_b200  # noqa: F401
+    from aaclip_b200 import engine, weights
+    S = 224
+    sd = weights.make_visual_state_dict(seed=5, img_size=S)
+    eng = engine.AaclipEngine("cuda", img_size=S, max_batch=8)
+    eng.load_state_dict(sd)
+    images = weights.make_images(9, 5, S).cuda()
+    text = weights.make_text_anchor(9).cuda()
+    seg5, det5, _, _ = eng.forward(images)
+    m5, s5 = engine.score_maps(seg5, text, S, det=det5)
+    seg1, det1, _, _ = eng.forward(images[2:3])
+    m1, s1 = engine.score_maps(seg1, text, S, det=det1)
+    seg5b, det5b, _, _ = eng.forward(images)
+    torch.cuda.synchronize()
+    assert torch.equal(det5, det5b) and all(torch.equal(a, b) for a, b in zip(seg5, seg5b))
+    assert torch.equal(det5[2:3], det1) and torch.equal(m5[2:3], m1) and torch.equal(s5[2:3], s1)
+
+
+def test_argument_errors():
+    import aaclip_b200  # noqa: F401
+    from aaclip_b200 import engine
+    eng = engine.AaclipEngine("cuda", img_size=224, max_batch=2)
+    with pytest.raises(RuntimeError, match="weight tensors not set"):
+        eng.forward(torch.zeros(1, 3, 224, 224, device="cuda"))
+    with pytest.raises(ValueError):
+        eng.forward(torch.zeros(1, 3, 336, 336, device="cuda"))
+    with pytest.raises(RuntimeError, match="unknown tensor"):
+        eng.set_weight("image_encoder.nope", torch.zeros(4))
+    with pytest.raises(RuntimeError, match="expected"):
+        eng.set_weight("image_encoder.class_embedding", torch.zeros(4))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        eng.forward(torch.zeros(1, 3, 224, 224))

@@ -1,0 +1,130 @@
+"""GPU parity of the building-block kernels (through the C ABI) against plain torch fp32 of the same op."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import aaclip_b200  # noqa: F401
+    from aaclip_b200 import _lib, engine
+    return _lib, engine
+
+
+def _ab(M, N, K):
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
+    a = (torch.randn(M, K, device="cuda", generator=g) * 0.5).bfloat16()
+    w = (torch.randn(N, K, device="cuda", generator=g) * K ** -0.5).bfloat16()
+    b = torch.randn(N, device="cuda", generator=g) * 0.1
+    return a, w, b
+
+
+@pytest.mark.parametrize("M,N,K", [(1, 256, 64), (128, 256, 64), (129, 512, 192), (300, 768, 1024), (2740, 1024, 4096),
+                                   (1369 * 3, 1024, 640)])
+def test_gemm_f32_epilogues(eng, M, N, K):
+    _lib, engine = eng
+    a, w, b = _ab(M, N, K)
+    ref = a.float() @ w.float().t()
+    assert (engine.gemm_bf16(a, w, _lib.EPI_F32) - ref).abs().max().item() < 1e-3
+    assert (engine.gemm_bf16(a, w, _lib.EPI_BIAS_F32, bias=b) - (ref + b)).abs().max().item() < 1e-3
+    assert (engine.gemm_bf16(a, w, _lib.EPI_LEAKY_F32) - F.leaky_relu(ref, 0.01)).abs().max().item() < 1e-3
+    res = torch.randn(M, N, device="cuda")
+    out, cp = res.clone(), torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    engine.gemm_bf16(a, w, _lib.EPI_BIAS_RESID_F32, bias=b, out_f32=out, out_bf16=cp)
+    assert (out - (res + ref + b)).abs().max().item() < 1e-3
+    assert (cp.float() - out).abs().max().item() <= out.abs().max().item() * 2 ** -8
+
+
+@pytest.mark.parametrize("M,N,K", [(257, 3072, 1024), (2740, 4096, 1024)])
+def test_gemm_bf16_epilogues(eng, M, N, K):
+    _lib, engine = eng
+    a, w, b = _ab(M, N, K)
+    y = a.float() @ w.float().t() + b
+    tol = lambda r: r.abs().max().item() * 2 ** -8 + 1e-3  # one bf16 rounding of the result
+    assert (engine.gemm_bf16(a, w, _lib.EPI_BIAS_BF16, bias=b).float() - y).abs().max().item() < tol(y)
+    g = F.gelu(y)
+    assert (engine.gemm_bf16(a, w, _lib.EPI_BIAS_GELU_BF16, bias=b).float() - g).abs().max().item() < tol(g)
+    q = y * torch.sigmoid(1.702 * y)
+    assert (engine.gemm_bf16(a, w, _lib.EPI_BIAS_QGELU_BF16, bias=b).float() - q).abs().max().item() < tol(q)
+
+
+def test_gemm_rejects_bad_shapes(eng):
+    _lib, engine = eng
+    a, w, b = _ab(64, 200, 64)
+    with pytest.raises(RuntimeError, match="unsupported shape"):
+        engine.gemm_bf16(a, w, _lib.EPI_F32)
+    a, w, b = _ab(64, 256, 64)
+    with pytest.raises(RuntimeError, match="needs a bias"):
+        engine.gemm_bf16(a, w, _lib.EPI_BIAS_F32)
+
+
+def _attn_ref(qkv, causal):
+    B, N, D3 = qkv.shape
+    D = D3 // 3
+    H = D // 64
+    q, k, v = qkv.float().split(D, dim=-1)
+    q, k, v = (t.view(B, N, H, 64).transpose(1, 2) for t in (q, k, v))
+    s = (q * 0.125) @ k.transpose(-1, -2)
+    if causal:
+        s = s + torch.full((N, N), float("-inf"), device=qkv.device).triu(1)
+    return (torch.softmax(s, dim=-1) @ v).transpose(1, 2).reshape(B, N, D)
+
+
+@pytest.mark.parametrize("B,N,D,causal", [(1, 1, 64, False), (1, 128, 64, False), (2, 129, 128, False),
+                                          (1, 577, 1024, False), (2, 1370, 1024, False), (3, 77, 768, True),
+                                          (1, 300, 128, True)])
+def test_attention(eng, B, N, D, causal):
+    _lib, engine = eng
+    g = torch.Generator(device="cuda").manual_seed(N + D)
+    qkv = (torch.randn(B, N, 3 * D, device="cuda", generator=g) * 1.5).bfloat16()
+    out = engine.attention(qkv, causal=causal).float()
+    ref = _attn_ref(qkv, causal)
+    assert torch.isfinite(out).all()
+    assert (out - ref).abs().max().item() < 2e-2
+
+
+def test_attention_extreme_logits(eng):
+    """Large score range: the online-softmax rescale path (running max changes across K/V tiles)."""
+    _lib, engine = eng
+    g = torch.Generator(device="cuda").manual_seed(3)
+    qkv = torch.randn(1, 700, 3 * 64, device="cuda", generator=g)
+    qkv[:, :, :128] *= 6.0  # |q.k|/8 up to ~100s
+    qkv = qkv.bfloat16()
+    out = engine.attention(qkv).float()
+    assert torch.isfinite(out).all()
+    assert (out - _attn_ref(qkv, False)).abs().max().item() < 3e-2
+
+
+@pytest.mark.parametrize("D", [768, 1024])
+def test_layernorm(eng, D):
+    _lib, engine = eng
+    x = torch.randn(3 * 50, D, device="cuda") * 3 + 0.5
+    g = torch.randn(D, device="cuda") * 0.1 + 1
+    b = torch.randn(D, device="cuda") * 0.1
+    ob, of = engine.layernorm(x, g, b, want_bf16=True, want_f32=True)
+    ref = F.layer_norm(x, (D,), g, b, 1e-5)
+    assert (of - ref).abs().max().item() < 1e-5
+    assert (ob.float() - ref).abs().max().item() < ref.abs().max().item() * 2 ** -8
+    _, of2 = engine.layernorm(x, g, b, skip_cls_P=49, want_bf16=False, want_f32=True)
+    assert torch.equal(of2, of.view(3, 50, D)[:, 1:].reshape(-1, D))
+
+
+def test_score_maps_against_torch(eng):
+    _lib, engine = eng
+    B, G, E, S = 2, 37, 768, 518
+    seg = [F.normalize(torch.randn(B, G * G, E, device="cuda"), dim=-1) for _ in range(4)]
+    text = F.normalize(torch.randn(E, 2, device="cuda"), dim=0)
+    det = F.normalize(torch.randn(B, G * G, E, device="cuda"), dim=-1).mean(1)
+    from oracle import aaclip_oracle as orc
+    for dom, (k, sg) in {"Industrial": (7, 1.0), "Medical": (9, 1.5)}.items():
+        maps, score = engine.score_maps(seg, text, S, test=True, ksize=k, sigma=sg, det=det)
+        ref = orc.anomaly_maps([s.cpu() for s in seg], text.cpu(), S, dom)
+        assert (maps.cpu() - ref).abs().max().item() < 1e-4
+        assert (score.cpu() - orc.image_score(det.cpu(), text.cpu())).abs().max().item() < 1e-5
+    tr, _ = engine.score_maps(seg[:1], text, S, test=False)
+    ref = orc.calculate_similarity_map(seg[0].cpu(), text.cpu(), S, test=False)
+    assert (tr.cpu() - ref).abs().max().item() < 1e-5
+    with pytest.raises(RuntimeError, match="exactly one level"):
+        engine.score_maps(seg, text, S, test=False)
