@@ -35,6 +35,9 @@ EPI_F32 = 4
 EPI_LEAKY_F32 = 5
 EPI_BIAS_F32 = 7
 
+DT_F16 = 0
+DT_BF16 = 1
+
 ACT_GELU_ERF = 0
 ACT_QUICK_GELU = 1
 
@@ -57,6 +60,7 @@ class AaclipCfg(ctypes.Structure):
         ("proj_relu", ctypes.c_int32),
         ("adapt_weight", ctypes.c_float),
         ("max_batch", ctypes.c_int32),
+        ("operand_dtype", ctypes.c_int32),
     ]
 
 
@@ -120,21 +124,21 @@ def _declare(lib):
                                       vp, vp]
     lib.aaclip_last_launch_count.restype = i32
     lib.aaclip_last_launch_count.argtypes = [vp]
-    lib.aaclip_gemm_bf16.restype = i32
-    lib.aaclip_gemm_bf16.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp, i32, vp]
+    lib.aaclip_gemm16.restype = i32
+    lib.aaclip_gemm16.argtypes = [i32, vp, vp, i32, i32, i32, i32, vp, vp, vp, i32, vp]
     lib.aaclip_attention.restype = i32
-    lib.aaclip_attention.argtypes = [vp, vp, i32, i32, i32, i32, vp]
+    lib.aaclip_attention.argtypes = [i32, vp, vp, i32, i32, i32, i32, vp]
     lib.aaclip_layernorm.restype = i32
-    lib.aaclip_layernorm.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, vp]
-    lib.aaclip_pack_bf16.restype = i32
-    lib.aaclip_pack_bf16.argtypes = [vp, vp, i64, i64, i64, vp]
+    lib.aaclip_layernorm.argtypes = [i32, vp, vp, vp, vp, vp, i32, i32, i32, vp]
+    lib.aaclip_pack16.restype = i32
+    lib.aaclip_pack16.argtypes = [i32, vp, vp, i64, i64, i64, vp]
 
 
 EXPORTED_SYMBOLS = [
     "aaclip_version", "aaclip_last_error", "aaclip_create", "aaclip_destroy", "aaclip_set_weight",
     "aaclip_missing_weights", "aaclip_workspace_bytes", "aaclip_forward", "aaclip_score_workspace_bytes",
-    "aaclip_score_maps", "aaclip_last_launch_count", "aaclip_gemm_bf16", "aaclip_attention", "aaclip_layernorm",
-    "aaclip_pack_bf16",
+    "aaclip_score_maps", "aaclip_last_launch_count", "aaclip_gemm16", "aaclip_attention", "aaclip_layernorm",
+    "aaclip_pack16",
 ]
 
 

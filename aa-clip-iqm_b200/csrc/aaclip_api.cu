@@ -63,9 +63,9 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// bf16 tensor, innermost dim contiguous; rank 2 or 3; 128-byte swizzle; OOB reads return zero.
-int make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                   const uint32_t* box) {
+// fp16/bf16 tensor, innermost dim contiguous; rank 2 or 3; 128-byte swizzle; OOB reads return zero.
+int make_tmap_16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                 const uint32_t* box, bool bf16) {
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) return fail(AACLIP_ENOSYS, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
   cuuint64_t gdim[3];
@@ -73,7 +73,7 @@ int make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t*
   cuuint32_t bx[3], estr[3];
   for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; estr[i] = 1; }
   for (int i = 0; i < rank - 1; ++i) gstr[i] = strides_bytes[i];
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdim, gstr, bx, estr,
+  CUresult r = fn(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(base), gdim, gstr, bx, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(AACLIP_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
@@ -94,23 +94,23 @@ int ensure_device() {
 }
 
 // ------------------------------------------------------------------------------------------ kernel launchers
-template <int EPI>
+template <int EPI, bool BF16>
 int launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const GemmEpi& epi,
                   cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(gemm_tcgen05_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CUDA_TRY(cudaFuncSetAttribute(gemm_tcgen05_kernel<EPI, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   gemm_cfg::SMEM_BYTES));
     attr_set = true;
   }
   const int tiles = ((M + gemm_cfg::BM - 1) / gemm_cfg::BM) * (N / gemm_cfg::BN);
   const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-  gemm_tcgen05_kernel<EPI><<<grid, gemm_cfg::THREADS, gemm_cfg::SMEM_BYTES, st>>>(ta, tb, M, N, K, epi);
+  gemm_tcgen05_kernel<EPI, BF16><<<grid, gemm_cfg::THREADS, gemm_cfg::SMEM_BYTES, st>>>(ta, tb, M, N, K, epi);
   LAUNCH_CHECK("gemm_tcgen05_kernel");
   return AACLIP_OK;
 }
 
-int launch_gemm(int epi_mode, const void* A, const void* W, int M, int N, int K, const GemmEpi& epi,
+int launch_gemm(int epi_mode, bool bf16, const void* A, const void* W, int M, int N, int K, const GemmEpi& epi,
                 cudaStream_t st) {
   if (int rc = ensure_device()) return rc;
   if (M <= 0 || N <= 0 || K <= 0 || N % gemm_cfg::BN != 0 || K % gemm_cfg::BK != 0)
@@ -122,62 +122,76 @@ int launch_gemm(int epi_mode, const void* A, const void* W, int M, int N, int K,
     const uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
     const uint64_t str[1] = {(uint64_t)K * 2};
     const uint32_t box[2] = {gemm_cfg::BK, gemm_cfg::BM};
-    if (int rc = make_tmap_bf16(&ta, A, 2, dims, str, box)) return rc;
+    if (int rc = make_tmap_16(&ta, A, 2, dims, str, box, bf16)) return rc;
   }
   {
     const uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
     const uint64_t str[1] = {(uint64_t)K * 2};
     const uint32_t box[2] = {gemm_cfg::BK, gemm_cfg::BN};
-    if (int rc = make_tmap_bf16(&tb, W, 2, dims, str, box)) return rc;
+    if (int rc = make_tmap_16(&tb, W, 2, dims, str, box, bf16)) return rc;
   }
+#define AACLIP_GEMM_CASE(E)                                                              \
+  case E:                                                                                \
+    return bf16 ? launch_gemm_t<E, true>(ta, tb, M, N, K, epi, st) : launch_gemm_t<E, false>(ta, tb, M, N, K, epi, st);
   switch (epi_mode) {
-    case EPI_BIAS_BF16: return launch_gemm_t<EPI_BIAS_BF16>(ta, tb, M, N, K, epi, st);
-    case EPI_BIAS_GELU_BF16: return launch_gemm_t<EPI_BIAS_GELU_BF16>(ta, tb, M, N, K, epi, st);
-    case EPI_BIAS_QGELU_BF16: return launch_gemm_t<EPI_BIAS_QGELU_BF16>(ta, tb, M, N, K, epi, st);
-    case EPI_BIAS_RESID_F32: return launch_gemm_t<EPI_BIAS_RESID_F32>(ta, tb, M, N, K, epi, st);
-    case EPI_F32: return launch_gemm_t<EPI_F32>(ta, tb, M, N, K, epi, st);
-    case EPI_LEAKY_F32: return launch_gemm_t<EPI_LEAKY_F32>(ta, tb, M, N, K, epi, st);
-    case EPI_PATCH_F32: return launch_gemm_t<EPI_PATCH_F32>(ta, tb, M, N, K, epi, st);
-    case EPI_BIAS_F32: return launch_gemm_t<EPI_BIAS_F32>(ta, tb, M, N, K, epi, st);
+    AACLIP_GEMM_CASE(EPI_BIAS_BF16)
+    AACLIP_GEMM_CASE(EPI_BIAS_GELU_BF16)
+    AACLIP_GEMM_CASE(EPI_BIAS_QGELU_BF16)
+    AACLIP_GEMM_CASE(EPI_BIAS_RESID_F32)
+    AACLIP_GEMM_CASE(EPI_F32)
+    AACLIP_GEMM_CASE(EPI_LEAKY_F32)
+    AACLIP_GEMM_CASE(EPI_PATCH_F32)
+    AACLIP_GEMM_CASE(EPI_BIAS_F32)
+#undef AACLIP_GEMM_CASE
     default: return fail(AACLIP_EINVAL, "gemm: unknown epilogue %d", epi_mode);
   }
 }
 
-int launch_attention(const void* qkv, void* out, int B, int N, int D, int causal, cudaStream_t st) {
-  if (int rc = ensure_device()) return rc;
-  if (B <= 0 || N <= 0 || D <= 0 || D % 64 != 0) return fail(AACLIP_EINVAL, "attention: bad shape B=%d N=%d D=%d", B, N, D);
+template <bool BF16>
+int launch_attention_t(const CUtensorMap& tq, void* out, int B, int N, int D, int causal, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(attention_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CUDA_TRY(cudaFuncSetAttribute(attention_tcgen05_kernel<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   attn_cfg::SMEM_BYTES));
     attr_set = true;
   }
-  CUtensorMap tq;
-  const uint64_t dims[3] = {(uint64_t)3 * D, (uint64_t)N, (uint64_t)B};
-  const uint64_t str[2] = {(uint64_t)3 * D * 2, (uint64_t)N * 3 * D * 2};
-  const uint32_t box[3] = {attn_cfg::HD, attn_cfg::BKV, 1};
-  if (int rc = make_tmap_bf16(&tq, qkv, 3, dims, str, box)) return rc;
-  const int H = D / 64;
-  dim3 grid((N + attn_cfg::BQ * attn_cfg::QT - 1) / (attn_cfg::BQ * attn_cfg::QT), H, B);
+  dim3 grid((N + attn_cfg::BQ * attn_cfg::QT - 1) / (attn_cfg::BQ * attn_cfg::QT), D / 64, B);
   const float scale_log2 = 0.125f * 1.4426950408889634f;  // head_dim^-0.5 * log2(e)
-  attention_tcgen05_kernel<<<grid, attn_cfg::THREADS, attn_cfg::SMEM_BYTES, st>>>(
-      tq, reinterpret_cast<__nv_bfloat16*>(out), N, D, causal, scale_log2);
+  attention_tcgen05_kernel<BF16><<<grid, attn_cfg::THREADS, attn_cfg::SMEM_BYTES, st>>>(
+      tq, reinterpret_cast<uint16_t*>(out), N, D, causal, scale_log2);
   LAUNCH_CHECK("attention_tcgen05_kernel");
   return AACLIP_OK;
 }
 
-int launch_layernorm(const float* x, const float* g, const float* b, void* out_bf16, float* out_f32, int rows, int D,
-                     int skipP, bool normalize, cudaStream_t st) {
+int launch_attention(bool bf16, const void* qkv, void* out, int B, int N, int D, int causal, cudaStream_t st) {
+  if (int rc = ensure_device()) return rc;
+  if (B <= 0 || N <= 0 || D <= 0 || D % 64 != 0) return fail(AACLIP_EINVAL, "attention: bad shape B=%d N=%d D=%d", B, N, D);
+  CUtensorMap tq;
+  const uint64_t dims[3] = {(uint64_t)3 * D, (uint64_t)N, (uint64_t)B};
+  const uint64_t str[2] = {(uint64_t)3 * D * 2, (uint64_t)N * 3 * D * 2};
+  const uint32_t box[3] = {attn_cfg::HD, attn_cfg::BKV, 1};
+  if (int rc = make_tmap_16(&tq, qkv, 3, dims, str, box, bf16)) return rc;
+  return bf16 ? launch_attention_t<true>(tq, out, B, N, D, causal, st) : launch_attention_t<false>(tq, out, B, N, D, causal, st);
+}
+
+template <int D, bool BF16>
+void launch_layernorm_t(const float* x, const float* g, const float* b, void* out16, float* out_f32, int rows,
+                        int skipP, bool normalize, cudaStream_t st) {
+  const int threads = 256, grid = (rows + 7) / 8;
+  uint16_t* o = reinterpret_cast<uint16_t*>(out16);
+  if (normalize) layernorm_kernel<D, true, BF16><<<grid, threads, 0, st>>>(x, g, b, o, out_f32, rows, skipP, 1e-5f);
+  else layernorm_kernel<D, false, BF16><<<grid, threads, 0, st>>>(x, g, b, o, out_f32, rows, skipP, 1e-5f);
+}
+
+int launch_layernorm(bool bf16, const float* x, const float* g, const float* b, void* out16, float* out_f32, int rows,
+                     int D, int skipP, bool normalize, cudaStream_t st) {
   if (rows <= 0) return AACLIP_OK;
-  const int threads = 256, rows_per_block = threads / 32;
-  const int grid = (rows + rows_per_block - 1) / rows_per_block;
-  __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(out_bf16);
   if (D == 1024) {
-    if (normalize) layernorm_kernel<1024, true><<<grid, threads, 0, st>>>(x, g, b, ob, out_f32, rows, skipP, 1e-5f);
-    else layernorm_kernel<1024, false><<<grid, threads, 0, st>>>(x, g, b, ob, out_f32, rows, skipP, 1e-5f);
+    if (bf16) launch_layernorm_t<1024, true>(x, g, b, out16, out_f32, rows, skipP, normalize, st);
+    else launch_layernorm_t<1024, false>(x, g, b, out16, out_f32, rows, skipP, normalize, st);
   } else if (D == 768) {
-    if (normalize) layernorm_kernel<768, true><<<grid, threads, 0, st>>>(x, g, b, ob, out_f32, rows, skipP, 1e-5f);
-    else layernorm_kernel<768, false><<<grid, threads, 0, st>>>(x, g, b, ob, out_f32, rows, skipP, 1e-5f);
+    if (bf16) launch_layernorm_t<768, true>(x, g, b, out16, out_f32, rows, skipP, normalize, st);
+    else launch_layernorm_t<768, false>(x, g, b, out16, out_f32, rows, skipP, normalize, st);
   } else {
     return fail(AACLIP_EINVAL, "layernorm: D=%d unsupported (768 or 1024)", D);
   }
@@ -185,12 +199,13 @@ int launch_layernorm(const float* x, const float* g, const float* b, void* out_b
   return AACLIP_OK;
 }
 
-__global__ void pack_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long R,
-                                 long long C, long long Cp) {
+template <bool BF16>
+__global__ void pack16_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, long long R, long long C,
+                              long long Cp) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= R * Cp) return;
   const long long r = i / Cp, c = i - r * Cp;
-  dst[i] = __float2bfloat16_rn(c < C ? src[r * C + c] : 0.f);
+  dst[i] = ptx::cvt16<BF16>(c < C ? src[r * C + c] : 0.f);
 }
 
 __global__ void gather_cls_kernel(const float* __restrict__ x, float* __restrict__ out, int tokens, int D) {
@@ -198,11 +213,13 @@ __global__ void gather_cls_kernel(const float* __restrict__ x, float* __restrict
   for (int i = threadIdx.x; i < D; i += blockDim.x) out[static_cast<size_t>(b) * D + i] = x[static_cast<size_t>(b) * tokens * D + i];
 }
 
-int launch_pack(const float* src, void* dst, long long R, long long C, long long Cp, cudaStream_t st) {
+int launch_pack(bool bf16, const float* src, void* dst, long long R, long long C, long long Cp, cudaStream_t st) {
   const long long n = R * Cp;
   if (n <= 0) return AACLIP_OK;
-  pack_bf16_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), R, C, Cp);
-  LAUNCH_CHECK("pack_bf16_kernel");
+  const unsigned grid = static_cast<unsigned>((n + 255) / 256);
+  if (bf16) pack16_kernel<true><<<grid, 256, 0, st>>>(src, reinterpret_cast<uint16_t*>(dst), R, C, Cp);
+  else pack16_kernel<false><<<grid, 256, 0, st>>>(src, reinterpret_cast<uint16_t*>(dst), R, C, Cp);
+  LAUNCH_CHECK("pack16_kernel");
   return AACLIP_OK;
 }
 
@@ -213,21 +230,22 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 // =========================================================================================== handle
 struct BlockW {
   float *ln1_g, *ln1_b, *ln2_g, *ln2_b, *b_qkv, *b_out, *b_fc, *b_proj;
-  __nv_bfloat16 *w_qkv, *w_out, *w_fc, *w_proj;
+  uint16_t *w_qkv, *w_out, *w_fc, *w_proj;
 };
 
 struct AaclipHandle {
   AaclipCfg cfg;
+  bool bf16 = false;      // 16-bit operand dtype: fp16 (default) or bf16
   int G, P, N, KP;        // grid side, patches, tokens, padded patch K
   uint8_t* arena = nullptr;
   size_t arena_bytes = 0;
   // fp32 params
   float *cls, *pos, *lnpre_g, *lnpre_b, *lnpost_g, *lnpost_b;
-  __nv_bfloat16* w_conv;  // [W, KP]
+  uint16_t* w_conv;  // [W, KP]
   std::vector<BlockW> blk;
-  std::vector<__nv_bfloat16*> w_adapter;  // [W,W] each
-  std::vector<__nv_bfloat16*> w_seg;      // [E,W] each
-  __nv_bfloat16* w_det;                   // [E,W]
+  std::vector<uint16_t*> w_adapter;  // [W,W] each
+  std::vector<uint16_t*> w_seg;      // [E,W] each
+  uint16_t* w_det;                   // [E,W]
   std::vector<std::string> missing;
   int last_launches = 0;
 };
@@ -279,9 +297,11 @@ int aaclip_create(const AaclipCfg* cfg, AaclipHandle** out) {
       return fail(AACLIP_EINVAL, "levels must be ascending in 1..layers");
   }
   if (c.max_batch <= 0) return fail(AACLIP_EINVAL, "max_batch must be > 0");
+  if (c.operand_dtype != AACLIP_DT_F16 && c.operand_dtype != AACLIP_DT_BF16) return fail(AACLIP_EINVAL, "operand_dtype must be AACLIP_DT_F16 or AACLIP_DT_BF16");
 
   AaclipHandle* h = new AaclipHandle();
   h->cfg = c;
+  h->bf16 = (c.operand_dtype == AACLIP_DT_BF16);
   h->G = c.img_size / c.patch;
   h->P = h->G * h->G;
   h->N = h->P + 1;
@@ -292,7 +312,7 @@ int aaclip_create(const AaclipCfg* cfg, AaclipHandle** out) {
   ArenaPlan plan;
   const size_t o_cls = plan.take<float>(W), o_pos = plan.take<float>((size_t)h->N * W);
   const size_t o_lpg = plan.take<float>(W), o_lpb = plan.take<float>(W), o_log = plan.take<float>(W), o_lob = plan.take<float>(W);
-  const size_t o_conv = plan.take<__nv_bfloat16>(W * h->KP);
+  const size_t o_conv = plan.take<uint16_t>(W * h->KP);
   struct BO { size_t ln1g, ln1b, ln2g, ln2b, bqkv, bout, bfc, bproj, wqkv, wout, wfc, wproj; };
   std::vector<BO> bo(c.layers);
   for (int i = 0; i < c.layers; ++i) {
@@ -300,13 +320,13 @@ int aaclip_create(const AaclipCfg* cfg, AaclipHandle** out) {
     bo[i].ln2g = plan.take<float>(W); bo[i].ln2b = plan.take<float>(W);
     bo[i].bqkv = plan.take<float>(3 * W); bo[i].bout = plan.take<float>(W);
     bo[i].bfc = plan.take<float>(F); bo[i].bproj = plan.take<float>(W);
-    bo[i].wqkv = plan.take<__nv_bfloat16>(3 * W * W); bo[i].wout = plan.take<__nv_bfloat16>(W * W);
-    bo[i].wfc = plan.take<__nv_bfloat16>(F * W); bo[i].wproj = plan.take<__nv_bfloat16>(W * F);
+    bo[i].wqkv = plan.take<uint16_t>(3 * W * W); bo[i].wout = plan.take<uint16_t>(W * W);
+    bo[i].wfc = plan.take<uint16_t>(F * W); bo[i].wproj = plan.take<uint16_t>(W * F);
   }
   std::vector<size_t> o_ad(c.adapt_until), o_seg(c.n_levels);
-  for (int i = 0; i < c.adapt_until; ++i) o_ad[i] = plan.take<__nv_bfloat16>(W * W);
-  for (int l = 0; l < c.n_levels; ++l) o_seg[l] = plan.take<__nv_bfloat16>(E * W);
-  const size_t o_det = plan.take<__nv_bfloat16>(E * W);
+  for (int i = 0; i < c.adapt_until; ++i) o_ad[i] = plan.take<uint16_t>(W * W);
+  for (int l = 0; l < c.n_levels; ++l) o_seg[l] = plan.take<uint16_t>(E * W);
+  const size_t o_det = plan.take<uint16_t>(E * W);
 
   h->arena_bytes = plan.off;
   cudaError_t e = cudaMalloc(&h->arena, h->arena_bytes);
@@ -324,7 +344,7 @@ int aaclip_create(const AaclipCfg* cfg, AaclipHandle** out) {
   h->cls = (float*)(a + o_cls); h->pos = (float*)(a + o_pos);
   h->lnpre_g = (float*)(a + o_lpg); h->lnpre_b = (float*)(a + o_lpb);
   h->lnpost_g = (float*)(a + o_log); h->lnpost_b = (float*)(a + o_lob);
-  h->w_conv = (__nv_bfloat16*)(a + o_conv);
+  h->w_conv = (uint16_t*)(a + o_conv);
   h->blk.resize(c.layers);
   for (int i = 0; i < c.layers; ++i) {
     BlockW& b = h->blk[i];
@@ -332,12 +352,12 @@ int aaclip_create(const AaclipCfg* cfg, AaclipHandle** out) {
     b.ln2_g = (float*)(a + bo[i].ln2g); b.ln2_b = (float*)(a + bo[i].ln2b);
     b.b_qkv = (float*)(a + bo[i].bqkv); b.b_out = (float*)(a + bo[i].bout);
     b.b_fc = (float*)(a + bo[i].bfc); b.b_proj = (float*)(a + bo[i].bproj);
-    b.w_qkv = (__nv_bfloat16*)(a + bo[i].wqkv); b.w_out = (__nv_bfloat16*)(a + bo[i].wout);
-    b.w_fc = (__nv_bfloat16*)(a + bo[i].wfc); b.w_proj = (__nv_bfloat16*)(a + bo[i].wproj);
+    b.w_qkv = (uint16_t*)(a + bo[i].wqkv); b.w_out = (uint16_t*)(a + bo[i].wout);
+    b.w_fc = (uint16_t*)(a + bo[i].wfc); b.w_proj = (uint16_t*)(a + bo[i].wproj);
   }
-  for (int i = 0; i < c.adapt_until; ++i) h->w_adapter.push_back((__nv_bfloat16*)(a + o_ad[i]));
-  for (int l = 0; l < c.n_levels; ++l) h->w_seg.push_back((__nv_bfloat16*)(a + o_seg[l]));
-  h->w_det = (__nv_bfloat16*)(a + o_det);
+  for (int i = 0; i < c.adapt_until; ++i) h->w_adapter.push_back((uint16_t*)(a + o_ad[i]));
+  for (int l = 0; l < c.n_levels; ++l) h->w_seg.push_back((uint16_t*)(a + o_seg[l]));
+  h->w_det = (uint16_t*)(a + o_det);
 
   // the set of tensors that must arrive through aaclip_set_weight before forward may run
   auto need = [&](const std::string& k) { h->missing.push_back(k); };
@@ -382,9 +402,9 @@ int aaclip_set_weight(AaclipHandle* h, const char* name, const float* data, cons
     mark_loaded(h, key);
     return AACLIP_OK;
   };
-  auto pack = [&](__nv_bfloat16* dst, int64_t R, int64_t C, int64_t Cp, const std::string& key) -> int {
+  auto pack = [&](uint16_t* dst, int64_t R, int64_t C, int64_t Cp, const std::string& key) -> int {
     if (n != R * C) return fail(AACLIP_EINVAL, "%s: expected %lld x %lld elements, got %lld", name, (long long)R, (long long)C, (long long)n);
-    if (int rc = launch_pack(data, dst, R, C, Cp, st)) return rc;
+    if (int rc = launch_pack(h->bf16, data, dst, R, C, Cp, st)) return rc;
     mark_loaded(h, key);
     return AACLIP_OK;
   };
@@ -441,13 +461,13 @@ static WsPlan plan_ws(const AaclipHandle* h, int B) {
   ArenaPlan p;
   WsPlan w;
   w.x = p.take<float>(M * W);
-  w.xn = p.take<__nv_bfloat16>(M * W);
-  w.qkv = p.take<__nv_bfloat16>(M * 3 * W);
-  w.att = p.take<__nv_bfloat16>(M * W);
-  w.hid = p.take<__nv_bfloat16>(M * F);
+  w.xn = p.take<uint16_t>(M * W);
+  w.qkv = p.take<uint16_t>(M * 3 * W);
+  w.att = p.take<uint16_t>(M * W);
+  w.hid = p.take<uint16_t>(M * F);
   w.abuf = p.take<float>(M * W);
-  w.patchA = p.take<__nv_bfloat16>(MP * h->KP);
-  w.tok = p.take<__nv_bfloat16>(MP * W);
+  w.patchA = p.take<uint16_t>(MP * h->KP);
+  w.tok = p.take<uint16_t>(MP * W);
   w.det = p.take<float>(MP * E);
   w.total = p.off;
   return w;
@@ -476,50 +496,52 @@ int aaclip_forward(AaclipHandle* h, const float* images, int32_t B, void* worksp
   const int M = B * N, MP = B * P;
   uint8_t* wsb = static_cast<uint8_t*>(workspace);
   float* x = (float*)(wsb + ws.x);
-  __nv_bfloat16* xn = (__nv_bfloat16*)(wsb + ws.xn);
-  __nv_bfloat16* qkv = (__nv_bfloat16*)(wsb + ws.qkv);
-  __nv_bfloat16* att = (__nv_bfloat16*)(wsb + ws.att);
-  __nv_bfloat16* hid = (__nv_bfloat16*)(wsb + ws.hid);
+  uint16_t* xn = (uint16_t*)(wsb + ws.xn);
+  uint16_t* qkv = (uint16_t*)(wsb + ws.qkv);
+  uint16_t* att = (uint16_t*)(wsb + ws.att);
+  uint16_t* hid = (uint16_t*)(wsb + ws.hid);
   float* abuf = (float*)(wsb + ws.abuf);
-  __nv_bfloat16* patchA = (__nv_bfloat16*)(wsb + ws.patchA);
-  __nv_bfloat16* tok = (__nv_bfloat16*)(wsb + ws.tok);
+  uint16_t* patchA = (uint16_t*)(wsb + ws.patchA);
+  uint16_t* tok = (uint16_t*)(wsb + ws.tok);
   float* detbuf = (float*)(wsb + ws.det);
   int launches = 0;
   int rc;
+  const bool bf = h->bf16;
 
   // ---- patch embedding + CLS + positional embedding + ln_pre (model/adapter.py:139-156)
-  patch_gather_kernel<<<dim3(h->G, B), 256, 0, st>>>(images, patchA, c.img_size, h->G, c.patch, h->KP);
+  if (bf) patch_gather_kernel<true><<<dim3(h->G, B), 256, 0, st>>>(images, patchA, c.img_size, h->G, c.patch, h->KP);
+  else patch_gather_kernel<false><<<dim3(h->G, B), 256, 0, st>>>(images, patchA, c.img_size, h->G, c.patch, h->KP);
   LAUNCH_CHECK("patch_gather_kernel"); ++launches;
   {
     GemmEpi e; e.out_f32 = x; e.ldo = W; e.pos = h->pos; e.patches = P;
-    if ((rc = launch_gemm(EPI_PATCH_F32, patchA, h->w_conv, MP, W, h->KP, e, st))) return rc;
+    if ((rc = launch_gemm(EPI_PATCH_F32, bf, patchA, h->w_conv, MP, W, h->KP, e, st))) return rc;
     ++launches;
   }
   cls_row_kernel<<<B, 256, 0, st>>>(x, h->cls, h->pos, N, W);
   LAUNCH_CHECK("cls_row_kernel"); ++launches;
-  if ((rc = launch_layernorm(x, h->lnpre_g, h->lnpre_b, nullptr, x, M, W, 0, true, st))) return rc;
+  if ((rc = launch_layernorm(bf, x, h->lnpre_g, h->lnpre_b, nullptr, x, M, W, 0, true, st))) return rc;
   ++launches;
 
   // ---- residual attention blocks (model/transformer.py:239-258) + adapters (model/adapter.py:161-172)
   int level_idx = 0;
   for (int i = 0; i < c.layers; ++i) {
     const BlockW& b = h->blk[i];
-    if ((rc = launch_layernorm(x, b.ln1_g, b.ln1_b, xn, nullptr, M, W, 0, true, st))) return rc;
-    { GemmEpi e; e.bias = b.b_qkv; e.out_bf16 = qkv; e.ldo = 3 * W;
-      if ((rc = launch_gemm(EPI_BIAS_BF16, xn, b.w_qkv, M, 3 * W, W, e, st))) return rc; }
-    if ((rc = launch_attention(qkv, att, B, N, W, 0, st))) return rc;
+    if ((rc = launch_layernorm(bf, x, b.ln1_g, b.ln1_b, xn, nullptr, M, W, 0, true, st))) return rc;
+    { GemmEpi e; e.bias = b.b_qkv; e.out_16 = qkv; e.ldo = 3 * W;
+      if ((rc = launch_gemm(EPI_BIAS_BF16, bf, xn, b.w_qkv, M, 3 * W, W, e, st))) return rc; }
+    if ((rc = launch_attention(bf, qkv, att, B, N, W, 0, st))) return rc;
     { GemmEpi e; e.bias = b.b_out; e.out_f32 = x; e.ldo = W;
-      if ((rc = launch_gemm(EPI_BIAS_RESID_F32, att, b.w_out, M, W, W, e, st))) return rc; }
-    if ((rc = launch_layernorm(x, b.ln2_g, b.ln2_b, xn, nullptr, M, W, 0, true, st))) return rc;
-    { GemmEpi e; e.bias = b.b_fc; e.out_bf16 = hid; e.ldo = F;
-      if ((rc = launch_gemm(c.act == AACLIP_ACT_QUICK_GELU ? EPI_BIAS_QGELU_BF16 : EPI_BIAS_GELU_BF16, xn, b.w_fc, M, F, W, e, st))) return rc; }
+      if ((rc = launch_gemm(EPI_BIAS_RESID_F32, bf, att, b.w_out, M, W, W, e, st))) return rc; }
+    if ((rc = launch_layernorm(bf, x, b.ln2_g, b.ln2_b, xn, nullptr, M, W, 0, true, st))) return rc;
+    { GemmEpi e; e.bias = b.b_fc; e.out_16 = hid; e.ldo = F;
+      if ((rc = launch_gemm(c.act == AACLIP_ACT_QUICK_GELU ? EPI_BIAS_QGELU_BF16 : EPI_BIAS_GELU_BF16, bf, xn, b.w_fc, M, F, W, e, st))) return rc; }
     const bool adapt = i < c.adapt_until;
-    { GemmEpi e; e.bias = b.b_proj; e.out_f32 = x; e.ldo = W; e.out_bf16 = adapt ? xn : nullptr;
-      if ((rc = launch_gemm(EPI_BIAS_RESID_F32, hid, b.w_proj, M, W, F, e, st))) return rc; }
+    { GemmEpi e; e.bias = b.b_proj; e.out_f32 = x; e.ldo = W; e.out_16 = adapt ? xn : nullptr;
+      if ((rc = launch_gemm(EPI_BIAS_RESID_F32, bf, hid, b.w_proj, M, W, F, e, st))) return rc; }
     launches += 7;
     if (adapt) {
       { GemmEpi e; e.out_f32 = abuf; e.ldo = W;
-        if ((rc = launch_gemm(EPI_LEAKY_F32, xn, h->w_adapter[i], M, W, W, e, st))) return rc; }
+        if ((rc = launch_gemm(EPI_LEAKY_F32, bf, xn, h->w_adapter[i], M, W, W, e, st))) return rc; }
       const int grid = (M + 7) / 8;
       if (W == 1024) adapter_blend_kernel<1024><<<grid, 256, 0, st>>>(x, abuf, M, c.adapt_weight, 1.0f - c.adapt_weight);
       else adapter_blend_kernel<768><<<grid, 256, 0, st>>>(x, abuf, M, c.adapt_weight, 1.0f - c.adapt_weight);
@@ -528,10 +550,10 @@ int aaclip_forward(AaclipHandle* h, const float* images, int32_t B, void* worksp
     }
     if (level_idx < c.n_levels && c.levels[level_idx] == i + 1) {
       float* tok_f32 = (tokens_out != nullptr) ? tokens_out[level_idx] : nullptr;
-      if ((rc = launch_layernorm(x, h->lnpost_g, h->lnpost_b, tok, tok_f32, MP, W, P, true, st))) return rc;
+      if ((rc = launch_layernorm(bf, x, h->lnpost_g, h->lnpost_b, tok, tok_f32, MP, W, P, true, st))) return rc;
       const int proj_epi = c.proj_relu ? EPI_LEAKY_F32 : EPI_F32;
       { GemmEpi e; e.out_f32 = seg_out[level_idx]; e.ldo = E;
-        if ((rc = launch_gemm(proj_epi, tok, h->w_seg[level_idx], MP, E, W, e, st))) return rc; }
+        if ((rc = launch_gemm(proj_epi, bf, tok, h->w_seg[level_idx], MP, E, W, e, st))) return rc; }
       const int grid = (MP + 7) / 8;
       if (E == 768) l2norm_rows_kernel<768><<<grid, 256, 0, st>>>(seg_out[level_idx], MP);
       else l2norm_rows_kernel<1024><<<grid, 256, 0, st>>>(seg_out[level_idx], MP);
@@ -539,7 +561,7 @@ int aaclip_forward(AaclipHandle* h, const float* images, int32_t B, void* worksp
       launches += 3;
       if (level_idx == c.n_levels - 1) {
         { GemmEpi e; e.out_f32 = detbuf; e.ldo = E;
-          if ((rc = launch_gemm(proj_epi, tok, h->w_det, MP, E, W, e, st))) return rc; }
+          if ((rc = launch_gemm(proj_epi, bf, tok, h->w_det, MP, E, W, e, st))) return rc; }
         if (E == 768) l2norm_rows_kernel<768><<<grid, 256, 0, st>>>(detbuf, MP);
         else l2norm_rows_kernel<1024><<<grid, 256, 0, st>>>(detbuf, MP);
         LAUNCH_CHECK("l2norm_rows_kernel");
@@ -621,38 +643,43 @@ int aaclip_score_maps(const float* const* seg, int32_t n_levels, const float* te
   return AACLIP_OK;
 }
 
-int aaclip_gemm_bf16(const void* A_bf16, const void* W_bf16, int32_t M, int32_t N, int32_t K, int32_t epi,
-                     const float* bias, float* out_f32, void* out_bf16, int32_t ldo, void* stream) {
-  if (!A_bf16 || !W_bf16) return fail(AACLIP_EINVAL, "aaclip_gemm_bf16: null operand");
-  if (epi == EPI_PATCH_F32) return fail(AACLIP_EINVAL, "aaclip_gemm_bf16: patch epilogue is internal");
+int aaclip_gemm16(int32_t dtype, const void* A, const void* W, int32_t M, int32_t N, int32_t K, int32_t epi,
+                  const float* bias, float* out_f32, void* out_16, int32_t ldo, void* stream) {
+  if (!A || !W) return fail(AACLIP_EINVAL, "aaclip_gemm16: null operand");
+  if (dtype != AACLIP_DT_F16 && dtype != AACLIP_DT_BF16) return fail(AACLIP_EINVAL, "aaclip_gemm16: bad dtype %d", dtype);
+  if (epi == EPI_PATCH_F32) return fail(AACLIP_EINVAL, "aaclip_gemm16: patch epilogue is internal");
   const bool needs_bias = epi == EPI_BIAS_BF16 || epi == EPI_BIAS_GELU_BF16 || epi == EPI_BIAS_QGELU_BF16 ||
                           epi == EPI_BIAS_RESID_F32 || epi == EPI_BIAS_F32;
-  const bool bf16_out = epi == EPI_BIAS_BF16 || epi == EPI_BIAS_GELU_BF16 || epi == EPI_BIAS_QGELU_BF16;
-  if (needs_bias && !bias) return fail(AACLIP_EINVAL, "aaclip_gemm_bf16: epilogue %d needs a bias", epi);
-  if (bf16_out && !out_bf16) return fail(AACLIP_EINVAL, "aaclip_gemm_bf16: epilogue %d needs out_bf16", epi);
-  if (!bf16_out && !out_f32) return fail(AACLIP_EINVAL, "aaclip_gemm_bf16: epilogue %d needs out_f32", epi);
-  if (ldo < N || ldo % 8 != 0) return fail(AACLIP_EINVAL, "aaclip_gemm_bf16: ldo must be >= N and a multiple of 8");
+  const bool out16 = epi == EPI_BIAS_BF16 || epi == EPI_BIAS_GELU_BF16 || epi == EPI_BIAS_QGELU_BF16;
+  if (needs_bias && !bias) return fail(AACLIP_EINVAL, "aaclip_gemm16: epilogue %d needs a bias", epi);
+  if (out16 && !out_16) return fail(AACLIP_EINVAL, "aaclip_gemm16: epilogue %d needs out_16", epi);
+  if (!out16 && !out_f32) return fail(AACLIP_EINVAL, "aaclip_gemm16: epilogue %d needs out_f32", epi);
+  if (ldo < N || ldo % 8 != 0) return fail(AACLIP_EINVAL, "aaclip_gemm16: ldo must be >= N and a multiple of 8");
   GemmEpi e;
-  e.bias = bias; e.out_f32 = out_f32; e.out_bf16 = reinterpret_cast<__nv_bfloat16*>(out_bf16); e.ldo = ldo;
-  return launch_gemm(epi, A_bf16, W_bf16, M, N, K, e, static_cast<cudaStream_t>(stream));
+  e.bias = bias; e.out_f32 = out_f32; e.out_16 = reinterpret_cast<uint16_t*>(out_16); e.ldo = ldo;
+  return launch_gemm(epi, dtype == AACLIP_DT_BF16, A, W, M, N, K, e, static_cast<cudaStream_t>(stream));
 }
 
-int aaclip_attention(const void* qkv_bf16, void* out_bf16, int32_t B, int32_t N, int32_t D, int32_t causal,
+int aaclip_attention(int32_t dtype, const void* qkv, void* out, int32_t B, int32_t N, int32_t D, int32_t causal,
                      void* stream) {
-  if (!qkv_bf16 || !out_bf16) return fail(AACLIP_EINVAL, "aaclip_attention: null argument");
-  return launch_attention(qkv_bf16, out_bf16, B, N, D, causal, static_cast<cudaStream_t>(stream));
+  if (!qkv || !out) return fail(AACLIP_EINVAL, "aaclip_attention: null argument");
+  if (dtype != AACLIP_DT_F16 && dtype != AACLIP_DT_BF16) return fail(AACLIP_EINVAL, "aaclip_attention: bad dtype %d", dtype);
+  return launch_attention(dtype == AACLIP_DT_BF16, qkv, out, B, N, D, causal, static_cast<cudaStream_t>(stream));
 }
 
-int aaclip_layernorm(const float* x, const float* gamma, const float* beta, void* out_bf16, float* out_f32,
-                     int32_t rows_out, int32_t D, int32_t skip_cls_P, void* stream) {
+int aaclip_layernorm(int32_t dtype, const float* x, const float* gamma, const float* beta, void* out_16,
+                     float* out_f32, int32_t rows_out, int32_t D, int32_t skip_cls_P, void* stream) {
   if (!x || !gamma || !beta) return fail(AACLIP_EINVAL, "aaclip_layernorm: null argument");
-  if (!out_bf16 && !out_f32) return fail(AACLIP_EINVAL, "aaclip_layernorm: no output requested");
-  return launch_layernorm(x, gamma, beta, out_bf16, out_f32, rows_out, D, skip_cls_P, true, static_cast<cudaStream_t>(stream));
+  if (!out_16 && !out_f32) return fail(AACLIP_EINVAL, "aaclip_layernorm: no output requested");
+  if (dtype != AACLIP_DT_F16 && dtype != AACLIP_DT_BF16) return fail(AACLIP_EINVAL, "aaclip_layernorm: bad dtype %d", dtype);
+  return launch_layernorm(dtype == AACLIP_DT_BF16, x, gamma, beta, out_16, out_f32, rows_out, D, skip_cls_P, true,
+                          static_cast<cudaStream_t>(stream));
 }
 
-int aaclip_pack_bf16(const float* src, void* dst_bf16, int64_t R, int64_t C, int64_t Cp, void* stream) {
-  if (!src || !dst_bf16 || R <= 0 || C <= 0 || Cp < C) return fail(AACLIP_EINVAL, "aaclip_pack_bf16: bad argument");
-  return launch_pack(src, dst_bf16, R, C, Cp, static_cast<cudaStream_t>(stream));
+int aaclip_pack16(int32_t dtype, const float* src, void* dst_16, int64_t R, int64_t C, int64_t Cp, void* stream) {
+  if (!src || !dst_16 || R <= 0 || C <= 0 || Cp < C) return fail(AACLIP_EINVAL, "aaclip_pack16: bad argument");
+  if (dtype != AACLIP_DT_F16 && dtype != AACLIP_DT_BF16) return fail(AACLIP_EINVAL, "aaclip_pack16: bad dtype %d", dtype);
+  return launch_pack(dtype == AACLIP_DT_BF16, src, dst_16, R, C, Cp, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -46,8 +46,9 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+template <bool BF16>
 __global__ void __launch_bounds__(attn_cfg::THREADS, 1)
-attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16* __restrict__ out, int n_tok,
+attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, uint16_t* __restrict__ out, int n_tok,
                          int D, int causal, float scale_log2) {
   using namespace attn_cfg;
   extern __shared__ uint8_t smem_raw[];
@@ -110,8 +111,8 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bflo
   } else if (warp == 9) {
     // ===================== MMA issuer (single thread) =====================
     if (lane == 0) {
-      constexpr uint32_t idesc_s = ptx::make_idesc_bf16(BQ, BKV, 0);   // S = Q K^T : both operands K-major
-      constexpr uint32_t idesc_pv = ptx::make_idesc_bf16(BQ, HD, 1);   // PV = P V  : V is MN-major
+      constexpr uint32_t idesc_s = ptx::make_idesc_16(BQ, BKV, 0, BF16);   // S = Q K^T : both operands K-major
+      constexpr uint32_t idesc_pv = ptx::make_idesc_16(BQ, HD, 1, BF16);   // PV = P V  : V is MN-major
       const uint32_t q_addr = ptx::smem_u32(smem + OFF_Q);
       const uint32_t kv_addr = ptx::smem_u32(smem + OFF_KV);
       const uint32_t p_addr = ptx::smem_u32(smem + OFF_P);
@@ -240,10 +241,10 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bflo
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             uint4 w;
-            w.x = ptx::pack_bf16x2(p[8 * u + 0], p[8 * u + 1]);
-            w.y = ptx::pack_bf16x2(p[8 * u + 2], p[8 * u + 3]);
-            w.z = ptx::pack_bf16x2(p[8 * u + 4], p[8 * u + 5]);
-            w.w = ptx::pack_bf16x2(p[8 * u + 6], p[8 * u + 7]);
+            w.x = ptx::pack16<BF16>(p[8 * u + 0], p[8 * u + 1]);
+            w.y = ptx::pack16<BF16>(p[8 * u + 2], p[8 * u + 3]);
+            w.z = ptx::pack16<BF16>(p[8 * u + 4], p[8 * u + 5]);
+            w.w = ptx::pack16<BF16>(p[8 * u + 6], p[8 * u + 7]);
             const int unit = ((c & 1) * 4 + u) ^ rx;
             *reinterpret_cast<uint4*>(chunk + unit * 16) = w;
           }
@@ -273,10 +274,10 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bflo
 #pragma unroll
         for (int u = 0; u < HD / 8; ++u) {
           uint4 w;
-          w.x = ptx::pack_bf16x2(o[8 * u + 0], o[8 * u + 1]);
-          w.y = ptx::pack_bf16x2(o[8 * u + 2], o[8 * u + 3]);
-          w.z = ptx::pack_bf16x2(o[8 * u + 4], o[8 * u + 5]);
-          w.w = ptx::pack_bf16x2(o[8 * u + 6], o[8 * u + 7]);
+          w.x = ptx::pack16<BF16>(o[8 * u + 0], o[8 * u + 1]);
+          w.y = ptx::pack16<BF16>(o[8 * u + 2], o[8 * u + 3]);
+          w.z = ptx::pack16<BF16>(o[8 * u + 4], o[8 * u + 5]);
+          w.w = ptx::pack16<BF16>(o[8 * u + 6], o[8 * u + 7]);
           dst[u] = w;
         }
       }

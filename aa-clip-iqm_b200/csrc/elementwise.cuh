@@ -20,7 +20,8 @@ __device__ __forceinline__ float warp_sum(float v) {
 // model/transformer.py:359-365):  images fp32 NCHW [B,3,S,S]  ->  A bf16 [B*G*G, KP]  with
 // k = c*ps*ps + ky*ps + kx (the flattening order of conv1.weight[1024,3,14,14]); columns >= 3*ps*ps stay 0.
 // grid = (G, B), block = 256: one CTA per row of patches; reads are fully coalesced image rows.
-__global__ void patch_gather_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ A, int S, int G,
+template <bool BF16>
+__global__ void patch_gather_kernel(const float* __restrict__ img, uint16_t* __restrict__ A, int S, int G,
                                     int ps, int KP) {
   const int py = blockIdx.x, b = blockIdx.y;
   const int W = G * ps;  // pixels actually covered by patches (== S when S % ps == 0)
@@ -30,14 +31,14 @@ __global__ void patch_gather_kernel(const float* __restrict__ img, __nv_bfloat16
     for (int x = threadIdx.x; x < W; x += blockDim.x) {
       const int px = x / ps, kx = x - px * ps;
       const size_t row = (static_cast<size_t>(b) * G + py) * G + px;
-      A[row * KP + (c * ps + ky) * ps + kx] = __float2bfloat16_rn(src[x]);
+      A[row * KP + (c * ps + ky) * ps + kx] = ptx::cvt16<BF16>(src[x]);
     }
   }
   // zero the K padding (the workspace is caller-owned and may hold anything)
   const int k_raw = 3 * ps * ps, pad = KP - k_raw;
   for (int i = threadIdx.x; i < G * pad; i += blockDim.x) {
     const int px = i / pad, k = k_raw + (i - px * pad);
-    A[((static_cast<size_t>(b) * G + py) * G + px) * KP + k] = __float2bfloat16_rn(0.f);
+    A[((static_cast<size_t>(b) * G + py) * G + px) * KP + k] = 0;
   }
 }
 
@@ -53,9 +54,9 @@ __global__ void cls_row_kernel(float* __restrict__ x, const float* __restrict__ 
 // ln_1, ln_2, ln_post, ln_final). Two-pass in registers: mean, then sum of squared deviations.
 // skipP > 0: output row r = b*skipP + p reads input row b*(skipP+1) + 1 + p (drops the CLS row: x[1:], adapter.py:172).
 // NORMALIZE=false degrades to a plain fp32 -> bf16 cast (operand staging for the adapter GEMM).
-template <int D, bool NORMALIZE>
+template <int D, bool NORMALIZE, bool BF16>
 __global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
-                                 const float* __restrict__ beta, __nv_bfloat16* __restrict__ out_bf16,
+                                 const float* __restrict__ beta, uint16_t* __restrict__ out_bf16,
                                  float* __restrict__ out_f32, int rows, int skipP, float eps) {
   constexpr int V = D / 128;  // float4 per lane
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -97,7 +98,7 @@ __global__ void layernorm_kernel(const float* __restrict__ x, const float* __res
     uint2* o = reinterpret_cast<uint2*>(out_bf16 + static_cast<size_t>(warp) * D);
 #pragma unroll
     for (int j = 0; j < V; ++j)
-      o[lane + 32 * j] = make_uint2(ptx::pack_bf16x2(v[j].x, v[j].y), ptx::pack_bf16x2(v[j].z, v[j].w));
+      o[lane + 32 * j] = make_uint2(ptx::pack16<BF16>(v[j].x, v[j].y), ptx::pack16<BF16>(v[j].z, v[j].w));
   }
   if (out_f32 != nullptr) {
     float4* o = reinterpret_cast<float4*>(out_f32 + static_cast<size_t>(warp) * D);

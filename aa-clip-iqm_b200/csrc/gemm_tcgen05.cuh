@@ -1,7 +1,7 @@
 // Persistent, warp-specialised tcgen05 GEMM for sm_100a:  C[M,N] = A[M,K] * W[N,K]^T  (+ fused epilogue)
 //
-//   A : bf16 row-major [M,K] (activations, token-major)         -- TMA, SWIZZLE_128B, box 64(K) x 128(M)
-//   W : bf16 row-major [N,K] (nn.Linear weight layout, K-major) -- TMA, SWIZZLE_128B, box 64(K) x 256(N)
+//   A : fp16|bf16 row-major [M,K] (activations, token-major)         -- TMA, SWIZZLE_128B, box 64(K) x 128(M)
+//   W : fp16|bf16 row-major [N,K] (nn.Linear weight layout, K-major) -- TMA, SWIZZLE_128B, box 64(K) x 256(N)
 //   D : fp32 accumulator in TMEM, 128 lanes x 256 columns, double-buffered (512 columns)
 //
 // Roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one lane) + TMEM owner,
@@ -20,7 +20,7 @@
 namespace aaclip {
 
 enum EpiMode : int {
-  EPI_BIAS_BF16 = 0,       // out_bf16 = acc + bias
+  EPI_BIAS_BF16 = 0,       // out_16 = acc + bias   ("BF16" in these names = the 16-bit operand dtype)
   EPI_BIAS_GELU_BF16 = 1,  // out_bf16 = gelu_erf(acc + bias)          (nn.GELU, model/model.py:84)
   EPI_BIAS_QGELU_BF16 = 2, // out_bf16 = x*sigmoid(1.702x), x=acc+bias (QuickGELU, model/transformer.py:46-49)
   EPI_BIAS_RESID_F32 = 3,  // out_f32 += acc + bias ; optional bf16 copy of the new value
@@ -33,7 +33,7 @@ enum EpiMode : int {
 struct GemmEpi {
   const float* bias = nullptr;        // [N]
   float* out_f32 = nullptr;           // [*, ldo]
-  __nv_bfloat16* out_bf16 = nullptr;  // [*, ldo]
+  uint16_t* out_16 = nullptr;         // [*, ldo] fp16 or bf16 (the operand dtype)
   const float* pos = nullptr;         // EPI_PATCH_F32: positional embedding [(P+1), N]
   int ldo = 0;                        // leading dimension of the outputs, in elements
   int patches = 0;                    // EPI_PATCH_F32: P
@@ -53,7 +53,7 @@ constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barrier
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 __device__ __forceinline__ float quick_gelu(float x) { return x / (1.0f + __expf(-1.702f * x)); }
 
-template <int EPI>
+template <int EPI, bool BF16>
 __device__ __forceinline__ void epilogue_store(const uint32_t (&r)[32], int row, int n0, int M, const GemmEpi& e) {
   if (row >= M) return;
   float v[32];
@@ -83,14 +83,14 @@ __device__ __forceinline__ void epilogue_store(const uint32_t (&r)[32], int row,
   }
 
   if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_QGELU_BF16) {
-    uint4* o = reinterpret_cast<uint4*>(e.out_bf16 + static_cast<size_t>(row) * e.ldo + n0);
+    uint4* o = reinterpret_cast<uint4*>(e.out_16 + static_cast<size_t>(row) * e.ldo + n0);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       uint4 u;
-      u.x = ptx::pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
-      u.y = ptx::pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
-      u.z = ptx::pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
-      u.w = ptx::pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+      u.x = ptx::pack16<BF16>(v[8 * i + 0], v[8 * i + 1]);
+      u.y = ptx::pack16<BF16>(v[8 * i + 2], v[8 * i + 3]);
+      u.z = ptx::pack16<BF16>(v[8 * i + 4], v[8 * i + 5]);
+      u.w = ptx::pack16<BF16>(v[8 * i + 6], v[8 * i + 7]);
       o[i] = u;
     }
   } else if constexpr (EPI == EPI_BIAS_RESID_F32) {
@@ -102,15 +102,15 @@ __device__ __forceinline__ void epilogue_store(const uint32_t (&r)[32], int row,
       o[i] = x;
       v[4 * i + 0] = x.x; v[4 * i + 1] = x.y; v[4 * i + 2] = x.z; v[4 * i + 3] = x.w;
     }
-    if (e.out_bf16 != nullptr) {
-      uint4* ob = reinterpret_cast<uint4*>(e.out_bf16 + static_cast<size_t>(row) * e.ldo + n0);
+    if (e.out_16 != nullptr) {
+      uint4* ob = reinterpret_cast<uint4*>(e.out_16 + static_cast<size_t>(row) * e.ldo + n0);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         uint4 u;
-        u.x = ptx::pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
-        u.y = ptx::pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
-        u.z = ptx::pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
-        u.w = ptx::pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+        u.x = ptx::pack16<BF16>(v[8 * i + 0], v[8 * i + 1]);
+        u.y = ptx::pack16<BF16>(v[8 * i + 2], v[8 * i + 3]);
+        u.z = ptx::pack16<BF16>(v[8 * i + 4], v[8 * i + 5]);
+        u.w = ptx::pack16<BF16>(v[8 * i + 6], v[8 * i + 7]);
         ob[i] = u;
       }
     }
@@ -132,7 +132,7 @@ __device__ __forceinline__ void epilogue_store(const uint32_t (&r)[32], int row,
   }
 }
 
-template <int EPI>
+template <int EPI, bool BF16>
 __global__ void __launch_bounds__(gemm_cfg::THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, int M,
                     int N, int K, GemmEpi epi) {
@@ -195,7 +195,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   } else if (warp == 1) {
     // ===================== MMA issuer (single thread) =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, BN, 0);
+      constexpr uint32_t idesc = ptx::make_idesc_16(BM, BN, 0, BF16);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -246,7 +246,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
         }
-        epilogue_store<EPI>(r, row, n_blk * BN + half * 128 + c * 32, M, epi);
+        epilogue_store<EPI, BF16>(r, row, n_blk * BN + half * 128 + c * 32, M, epi);
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }

@@ -136,11 +136,12 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
   return d;
 }
 
-// Instruction descriptor, kind::f16, bf16 x bf16 -> fp32. b_mn_major=1 when B is stored [K][N] (N contiguous).
-__host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N, uint32_t b_mn_major) {
-  return (1u << 4)                 // D format: F32
-         | (1u << 7)               // A format: BF16
-         | (1u << 10)              // B format: BF16
+// Instruction descriptor, kind::f16, (fp16 | bf16) x same -> fp32. b_mn_major=1 when B is stored [K][N]
+// (N contiguous). Operand format field: 0 = F16, 1 = BF16.
+__host__ __device__ constexpr uint32_t make_idesc_16(uint32_t M, uint32_t N, uint32_t b_mn_major, bool bf16) {
+  return (1u << 4)                           // D format: F32
+         | ((bf16 ? 1u : 0u) << 7)           // A format
+         | ((bf16 ? 1u : 0u) << 10)          // B format
          | (0u << 15)              // A major: K
          | (b_mn_major << 16)      // B major
          | ((N >> 3) << 17)        // N >> 3
@@ -164,9 +165,20 @@ __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&v);
+// two fp32 -> packed 16-bit pair (lo in bits [0,16)). fp16 saturates to +-65504 instead of overflowing to inf.
+template <bool BF16>
+__device__ __forceinline__ uint32_t pack16(float lo, float hi) {
+  uint32_t r;
+  if constexpr (BF16) {
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  } else {
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  }
+  return r;
+}
+template <bool BF16>
+__device__ __forceinline__ uint16_t cvt16(float v) {
+  return static_cast<uint16_t>(pack16<BF16>(v, 0.f) & 0xFFFFu);
 }
 
 }  // namespace ptx

@@ -35,59 +35,70 @@ def _ptr_array(tensors: Sequence[Optional[torch.Tensor]]):
 
 
 # ---------------------------------------------------------------------------------------- building blocks
-def pack_bf16(src: torch.Tensor, padded_cols: Optional[int] = None) -> torch.Tensor:
-    """fp32 [R,C] -> bf16 [R,Cp] zero padded (aaclip_pack_bf16)."""
+_TORCH_DT = {torch.float16: _lib.DT_F16, torch.bfloat16: _lib.DT_BF16}
+
+
+def _dt(t_or_dtype) -> int:
+    d = t_or_dtype.dtype if isinstance(t_or_dtype, torch.Tensor) else t_or_dtype
+    if d not in _TORCH_DT:
+        raise TypeError(f"16-bit operand dtype must be torch.float16 or torch.bfloat16, got {d}")
+    return _TORCH_DT[d]
+
+
+def pack16(src: torch.Tensor, dtype: torch.dtype = torch.float16, padded_cols: Optional[int] = None) -> torch.Tensor:
+    """fp32 [R,C] -> fp16|bf16 [R,Cp] zero padded, saturating (aaclip_pack16)."""
     _need_cuda(src)
     src = src.contiguous().float()
     R, C = src.shape
     Cp = C if padded_cols is None else padded_cols
-    dst = torch.empty((R, Cp), dtype=torch.bfloat16, device=src.device)
-    _lib.check(_lib.load().aaclip_pack_bf16(_ptr(src), _ptr(dst), R, C, Cp, _stream()), "aaclip_pack_bf16")
+    dst = torch.empty((R, Cp), dtype=dtype, device=src.device)
+    _lib.check(_lib.load().aaclip_pack16(_dt(dtype), _ptr(src), _ptr(dst), R, C, Cp, _stream()), "aaclip_pack16")
     return dst
 
 
-def gemm_bf16(a: torch.Tensor, w: torch.Tensor, epi: int, bias: Optional[torch.Tensor] = None,
-              out_f32: Optional[torch.Tensor] = None, out_bf16: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """C = A[M,K] @ W[N,K]^T with fused epilogue `epi` (aaclip_gemm_bf16). Returns the primary output."""
+def gemm16(a: torch.Tensor, w: torch.Tensor, epi: int, bias: Optional[torch.Tensor] = None,
+           out_f32: Optional[torch.Tensor] = None, out_16: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """C = A[M,K] @ W[N,K]^T with fused epilogue `epi` (aaclip_gemm16). Returns the primary output."""
     _need_cuda(a, w)
-    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.is_contiguous() and w.is_contiguous()
+    assert a.dtype == w.dtype and a.is_contiguous() and w.is_contiguous()
+    out_bf16 = out_16
     M, K = a.shape
     N = w.shape[0]
     assert w.shape[1] == K
     bf16_out = epi in (_lib.EPI_BIAS_BF16, _lib.EPI_BIAS_GELU_BF16, _lib.EPI_BIAS_QGELU_BF16)
     if bf16_out and out_bf16 is None:
-        out_bf16 = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
+        out_bf16 = torch.empty((M, N), dtype=a.dtype, device=a.device)
     if not bf16_out and out_f32 is None:
         out_f32 = torch.empty((M, N), dtype=torch.float32, device=a.device)
     _lib.check(
-        _lib.load().aaclip_gemm_bf16(_ptr(a), _ptr(w), M, N, K, epi, _ptr(bias), _ptr(out_f32), _ptr(out_bf16), N,
-                                     _stream()),
-        "aaclip_gemm_bf16")
+        _lib.load().aaclip_gemm16(_dt(a), _ptr(a), _ptr(w), M, N, K, epi, _ptr(bias), _ptr(out_f32), _ptr(out_bf16), N,
+                                  _stream()),
+        "aaclip_gemm16")
     return out_bf16 if bf16_out else out_f32
 
 
 def attention(qkv: torch.Tensor, causal: bool = False) -> torch.Tensor:
-    """qkv bf16 [B,N,3D] -> bf16 [B,N,D] (aaclip_attention)."""
+    """qkv fp16|bf16 [B,N,3D] -> same dtype [B,N,D] (aaclip_attention)."""
     _need_cuda(qkv)
-    assert qkv.dtype == torch.bfloat16 and qkv.is_contiguous() and qkv.dim() == 3
+    assert qkv.is_contiguous() and qkv.dim() == 3
     B, N, D3 = qkv.shape
     D = D3 // 3
-    out = torch.empty((B, N, D), dtype=torch.bfloat16, device=qkv.device)
-    _lib.check(_lib.load().aaclip_attention(_ptr(qkv), _ptr(out), B, N, D, int(causal), _stream()),
+    out = torch.empty((B, N, D), dtype=qkv.dtype, device=qkv.device)
+    _lib.check(_lib.load().aaclip_attention(_dt(qkv), _ptr(qkv), _ptr(out), B, N, D, int(causal), _stream()),
                "aaclip_attention")
     return out
 
 
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, skip_cls_P: int = 0,
-              want_bf16: bool = True, want_f32: bool = False) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
+              want_16: bool = True, want_f32: bool = False, dtype: torch.dtype = torch.float16) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
     """LayerNorm(eps=1e-5) over the last dim of fp32 x [rows, D] (aaclip_layernorm)."""
     _need_cuda(x, gamma, beta)
     assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 2
     rows_in, D = x.shape
     rows = rows_in if skip_cls_P == 0 else rows_in // (skip_cls_P + 1) * skip_cls_P
-    ob = torch.empty((rows, D), dtype=torch.bfloat16, device=x.device) if want_bf16 else None
+    ob = torch.empty((rows, D), dtype=dtype, device=x.device) if want_16 else None
     of = torch.empty((rows, D), dtype=torch.float32, device=x.device) if want_f32 else None
-    _lib.check(_lib.load().aaclip_layernorm(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(ob), _ptr(of), rows, D,
+    _lib.check(_lib.load().aaclip_layernorm(_dt(dtype), _ptr(x), _ptr(gamma), _ptr(beta), _ptr(ob), _ptr(of), rows, D,
                                             skip_cls_P, _stream()), "aaclip_layernorm")
     return ob, of
 
@@ -130,7 +141,7 @@ def score_maps(seg: Sequence[torch.Tensor], text: torch.Tensor, img_size: int, t
 # ---------------------------------------------------------------------------------------- the tower
 DEFAULT_CFG = dict(img_size=518, patch=14, width=1024, heads=16, layers=24, mlp_dim=4096, embed_dim=768,
                    adapt_until=6, levels=(6, 12, 18, 24), act=_lib.ACT_GELU_ERF, proj_relu=0, adapt_weight=0.1,
-                   max_batch=64)
+                   max_batch=64, operand_dtype=_lib.DT_F16)
 
 
 class AaclipEngine:
@@ -145,7 +156,7 @@ class AaclipEngine:
         self.cfg = full
         c = _lib.AaclipCfg()
         for k in ("img_size", "patch", "width", "heads", "layers", "mlp_dim", "embed_dim", "adapt_until", "act",
-                  "proj_relu", "max_batch"):
+                  "proj_relu", "max_batch", "operand_dtype"):
             setattr(c, k, int(full[k]))
         c.adapt_weight = float(full["adapt_weight"])
         levels = list(full["levels"])

@@ -38,7 +38,14 @@ extern "C" {
 #define AACLIP_ACT_GELU_ERF 0
 #define AACLIP_ACT_QUICK_GELU 1
 
-/* epilogue selectors of aaclip_gemm_bf16 (unit-test / building-block entry point) */
+/* 16-bit tensor-core operand type (fp32 accumulation in TMEM either way; same tensor throughput).
+ * F16 is the default: on the reference's fp32 oracle it keeps anomaly maps within 1e-2 abs, which bf16 operands
+ * (3 fewer mantissa bits) do not (DESIGN.md "Precision"). Stores saturate to +-65504 in F16 mode. */
+#define AACLIP_DT_F16 0
+#define AACLIP_DT_BF16 1
+
+/* epilogue selectors of aaclip_gemm16 (unit-test / building-block entry point); "BF16" in these names means
+ * "the 16-bit operand dtype" */
 #define AACLIP_EPI_BIAS_BF16 0
 #define AACLIP_EPI_BIAS_GELU_BF16 1
 #define AACLIP_EPI_BIAS_QGELU_BF16 2
@@ -64,6 +71,7 @@ typedef struct AaclipCfg {
   int32_t proj_relu;     /* SimpleProj(relu=...) : LeakyReLU after seg/det projections */
   float adapt_weight;    /* i_w = 0.1 */
   int32_t max_batch;     /* largest B accepted by aaclip_forward */
+  int32_t operand_dtype; /* AACLIP_DT_F16 (default) or AACLIP_DT_BF16 */
 } AaclipCfg;
 
 typedef struct AaclipHandle AaclipHandle;
@@ -130,22 +138,22 @@ int aaclip_last_launch_count(AaclipHandle* h);
 
 /* ---- building blocks, exported for the parity tests (each is exactly what aaclip_forward launches) ---- */
 
-/* C[M,N] = A[M,K] * W[N,K]^T with a fused epilogue (tcgen05/TMEM/TMA GEMM). A, W bf16 row-major.
- * N % 256 == 0, K % 64 == 0. out_f32 / out_bf16 as required by `epi`; ldo = leading dim of outputs. */
-int aaclip_gemm_bf16(const void* A_bf16, const void* W_bf16, int32_t M, int32_t N, int32_t K, int32_t epi,
-                     const float* bias, float* out_f32, void* out_bf16, int32_t ldo, void* stream);
+/* C[M,N] = A[M,K] * W[N,K]^T with a fused epilogue (tcgen05/TMEM/TMA GEMM). A, W: `dtype` row-major.
+ * N % 256 == 0, K % 64 == 0. out_f32 / out_16 as required by `epi`; ldo = leading dim of outputs. */
+int aaclip_gemm16(int32_t dtype, const void* A, const void* W, int32_t M, int32_t N, int32_t K, int32_t epi,
+                  const float* bias, float* out_f32, void* out_16, int32_t ldo, void* stream);
 
-/* Fused multi-head attention: qkv bf16 [B,N,3*D] -> out bf16 [B,N,D]; head dim 64; softmax scale 1/8. */
-int aaclip_attention(const void* qkv_bf16, void* out_bf16, int32_t B, int32_t N, int32_t D, int32_t causal,
+/* Fused multi-head attention: qkv `dtype` [B,N,3*D] -> out `dtype` [B,N,D]; head dim 64; softmax scale 1/8. */
+int aaclip_attention(int32_t dtype, const void* qkv, void* out, int32_t B, int32_t N, int32_t D, int32_t causal,
                      void* stream);
 
-/* LayerNorm(eps=1e-5) rows of fp32 x [rows_in, D] (D in {768,1024}); out_bf16 and/or out_f32 may be NULL.
+/* LayerNorm(eps=1e-5) rows of fp32 x [rows_in, D] (D in {768,1024}); out_16 and/or out_f32 may be NULL.
  * skip_cls_P > 0 drops the first row of every (P+1)-row group (x[1:] of each image). */
-int aaclip_layernorm(const float* x, const float* gamma, const float* beta, void* out_bf16, float* out_f32,
-                     int32_t rows_out, int32_t D, int32_t skip_cls_P, void* stream);
+int aaclip_layernorm(int32_t dtype, const float* x, const float* gamma, const float* beta, void* out_16,
+                     float* out_f32, int32_t rows_out, int32_t D, int32_t skip_cls_P, void* stream);
 
-/* fp32 [R,C] -> bf16 [R,Cp] (Cp >= C, zero padded): the weight / operand packing used by aaclip_set_weight. */
-int aaclip_pack_bf16(const float* src, void* dst_bf16, int64_t R, int64_t C, int64_t Cp, void* stream);
+/* fp32 [R,C] -> `dtype` [R,Cp] (Cp >= C, zero padded): the weight / operand packing used by aaclip_set_weight. */
+int aaclip_pack16(int32_t dtype, const float* src, void* dst_16, int64_t R, int64_t C, int64_t Cp, void* stream);
 
 #ifdef __cplusplus
 }

@@ -31,8 +31,8 @@ def test_library_exports_every_declared_symbol(built_lib):
 
 def test_cfg_struct_layout_matches_header():
     from aaclip_b200 import _lib
-    # 9 int32 + 4 levels + act + proj_relu + float + max_batch = 17 4-byte fields
-    assert ctypes.sizeof(_lib.AaclipCfg) == 17 * 4
+    # 9 int32 + 4 levels + act + proj_relu + float + max_batch + operand_dtype = 18 4-byte fields
+    assert ctypes.sizeof(_lib.AaclipCfg) == 18 * 4
 
 
 def test_argument_errors_are_reported_without_a_gpu(built_lib):

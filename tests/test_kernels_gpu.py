@@ -5,6 +5,9 @@ import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
 
+DTYPES = [torch.float16, torch.bfloat16]
+EPS = {torch.float16: 2 ** -11, torch.bfloat16: 2 ** -8}  # unit roundoff of one 16-bit store
+
 
 @pytest.fixture(scope="module")
 def eng():
@@ -13,51 +16,61 @@ def eng():
     return _lib, engine
 
 
-def _ab(M, N, K):
+def _ab(M, N, K, dtype):
     g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
-    a = (torch.randn(M, K, device="cuda", generator=g) * 0.5).bfloat16()
-    w = (torch.randn(N, K, device="cuda", generator=g) * K ** -0.5).bfloat16()
+    a = (torch.randn(M, K, device="cuda", generator=g) * 0.5).to(dtype)
+    w = (torch.randn(N, K, device="cuda", generator=g) * K ** -0.5).to(dtype)
     b = torch.randn(N, device="cuda", generator=g) * 0.1
     return a, w, b
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("M,N,K", [(1, 256, 64), (128, 256, 64), (129, 512, 192), (300, 768, 1024), (2740, 1024, 4096),
                                    (1369 * 3, 1024, 640)])
-def test_gemm_f32_epilogues(eng, M, N, K):
+def test_gemm_f32_epilogues(eng, M, N, K, dtype):
     _lib, engine = eng
-    a, w, b = _ab(M, N, K)
+    a, w, b = _ab(M, N, K, dtype)
     ref = a.float() @ w.float().t()
-    assert (engine.gemm_bf16(a, w, _lib.EPI_F32) - ref).abs().max().item() < 1e-3
-    assert (engine.gemm_bf16(a, w, _lib.EPI_BIAS_F32, bias=b) - (ref + b)).abs().max().item() < 1e-3
-    assert (engine.gemm_bf16(a, w, _lib.EPI_LEAKY_F32) - F.leaky_relu(ref, 0.01)).abs().max().item() < 1e-3
+    assert (engine.gemm16(a, w, _lib.EPI_F32) - ref).abs().max().item() < 1e-3
+    assert (engine.gemm16(a, w, _lib.EPI_BIAS_F32, bias=b) - (ref + b)).abs().max().item() < 1e-3
+    assert (engine.gemm16(a, w, _lib.EPI_LEAKY_F32) - F.leaky_relu(ref, 0.01)).abs().max().item() < 1e-3
     res = torch.randn(M, N, device="cuda")
-    out, cp = res.clone(), torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
-    engine.gemm_bf16(a, w, _lib.EPI_BIAS_RESID_F32, bias=b, out_f32=out, out_bf16=cp)
+    out, cp = res.clone(), torch.empty(M, N, device="cuda", dtype=dtype)
+    engine.gemm16(a, w, _lib.EPI_BIAS_RESID_F32, bias=b, out_f32=out, out_16=cp)
     assert (out - (res + ref + b)).abs().max().item() < 1e-3
-    assert (cp.float() - out).abs().max().item() <= out.abs().max().item() * 2 ** -8
+    assert (cp.float() - out).abs().max().item() <= out.abs().max().item() * EPS[dtype]
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("M,N,K", [(257, 3072, 1024), (2740, 4096, 1024)])
-def test_gemm_bf16_epilogues(eng, M, N, K):
+def test_gemm_16bit_epilogues(eng, M, N, K, dtype):
     _lib, engine = eng
-    a, w, b = _ab(M, N, K)
+    a, w, b = _ab(M, N, K, dtype)
     y = a.float() @ w.float().t() + b
-    tol = lambda r: r.abs().max().item() * 2 ** -8 + 1e-3  # one bf16 rounding of the result
-    assert (engine.gemm_bf16(a, w, _lib.EPI_BIAS_BF16, bias=b).float() - y).abs().max().item() < tol(y)
+    tol = lambda r: r.abs().max().item() * EPS[dtype] + 1e-3  # one 16-bit rounding of the result
+    assert (engine.gemm16(a, w, _lib.EPI_BIAS_BF16, bias=b).float() - y).abs().max().item() < tol(y)
     g = F.gelu(y)
-    assert (engine.gemm_bf16(a, w, _lib.EPI_BIAS_GELU_BF16, bias=b).float() - g).abs().max().item() < tol(g)
+    assert (engine.gemm16(a, w, _lib.EPI_BIAS_GELU_BF16, bias=b).float() - g).abs().max().item() < tol(g)
     q = y * torch.sigmoid(1.702 * y)
-    assert (engine.gemm_bf16(a, w, _lib.EPI_BIAS_QGELU_BF16, bias=b).float() - q).abs().max().item() < tol(q)
+    assert (engine.gemm16(a, w, _lib.EPI_BIAS_QGELU_BF16, bias=b).float() - q).abs().max().item() < tol(q)
+
+
+def test_fp16_stores_saturate_instead_of_overflowing(eng):
+    _lib, engine = eng
+    a = torch.full((128, 64), 200.0, device="cuda", dtype=torch.float16)
+    w = torch.full((256, 64), 200.0, device="cuda", dtype=torch.float16)
+    out = engine.gemm16(a, w, _lib.EPI_BIAS_BF16, bias=torch.zeros(256, device="cuda"))
+    assert torch.isfinite(out).all() and out.float().max().item() == 65504.0
 
 
 def test_gemm_rejects_bad_shapes(eng):
     _lib, engine = eng
-    a, w, b = _ab(64, 200, 64)
+    a, w, b = _ab(64, 200, 64, torch.float16)
     with pytest.raises(RuntimeError, match="unsupported shape"):
-        engine.gemm_bf16(a, w, _lib.EPI_F32)
-    a, w, b = _ab(64, 256, 64)
+        engine.gemm16(a, w, _lib.EPI_F32)
+    a, w, b = _ab(64, 256, 64, torch.float16)
     with pytest.raises(RuntimeError, match="needs a bias"):
-        engine.gemm_bf16(a, w, _lib.EPI_BIAS_F32)
+        engine.gemm16(a, w, _lib.EPI_BIAS_F32)
 
 
 def _attn_ref(qkv, causal):
@@ -72,17 +85,18 @@ def _attn_ref(qkv, causal):
     return (torch.softmax(s, dim=-1) @ v).transpose(1, 2).reshape(B, N, D)
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("B,N,D,causal", [(1, 1, 64, False), (1, 128, 64, False), (2, 129, 128, False),
                                           (1, 577, 1024, False), (2, 1370, 1024, False), (3, 77, 768, True),
                                           (1, 300, 128, True)])
-def test_attention(eng, B, N, D, causal):
+def test_attention(eng, B, N, D, causal, dtype):
     _lib, engine = eng
     g = torch.Generator(device="cuda").manual_seed(N + D)
-    qkv = (torch.randn(B, N, 3 * D, device="cuda", generator=g) * 1.5).bfloat16()
+    qkv = (torch.randn(B, N, 3 * D, device="cuda", generator=g) * 1.5).to(dtype)
     out = engine.attention(qkv, causal=causal).float()
     ref = _attn_ref(qkv, causal)
     assert torch.isfinite(out).all()
-    assert (out - ref).abs().max().item() < 2e-2
+    assert (out - ref).abs().max().item() < (2e-2 if dtype == torch.bfloat16 else 4e-3)
 
 
 def test_attention_extreme_logits(eng):
@@ -91,27 +105,28 @@ def test_attention_extreme_logits(eng):
     g = torch.Generator(device="cuda").manual_seed(3)
     qkv = torch.randn(1, 700, 3 * 64, device="cuda", generator=g)
     qkv[:, :, :128] *= 6.0  # |q.k|/8 up to ~100s
-    qkv = qkv.bfloat16()
+    qkv = qkv.half()
     out = engine.attention(qkv).float()
     assert torch.isfinite(out).all()
-    assert (out - _attn_ref(qkv, False)).abs().max().item() < 3e-2
+    assert (out - _attn_ref(qkv, False)).abs().max().item() < 1e-2
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("D", [768, 1024])
-def test_layernorm(eng, D):
+def test_layernorm(eng, D, dtype):
     _lib, engine = eng
     x = torch.randn(3 * 50, D, device="cuda") * 3 + 0.5
     g = torch.randn(D, device="cuda") * 0.1 + 1
     b = torch.randn(D, device="cuda") * 0.1
-    ob, of = engine.layernorm(x, g, b, want_bf16=True, want_f32=True)
+    ob, of = engine.layernorm(x, g, b, want_16=True, want_f32=True, dtype=dtype)
     ref = F.layer_norm(x, (D,), g, b, 1e-5)
     assert (of - ref).abs().max().item() < 1e-5
-    assert (ob.float() - ref).abs().max().item() < ref.abs().max().item() * 2 ** -8
-    _, of2 = engine.layernorm(x, g, b, skip_cls_P=49, want_bf16=False, want_f32=True)
+    assert (ob.float() - ref).abs().max().item() < ref.abs().max().item() * EPS[dtype]
+    _, of2 = engine.layernorm(x, g, b, skip_cls_P=49, want_16=False, want_f32=True)
     assert torch.equal(of2, of.view(3, 50, D)[:, 1:].reshape(-1, D))
 
 
-def test_score_maps_against_torch(eng):
+def test_score_maps_against_oracle(eng):
     _lib, engine = eng
     B, G, E, S = 2, 37, 768, 518
     seg = [F.normalize(torch.randn(B, G * G, E, device="cuda"), dim=-1) for _ in range(4)]
@@ -128,3 +143,8 @@ def test_score_maps_against_torch(eng):
     assert (tr.cpu() - ref).abs().max().item() < 1e-5
     with pytest.raises(RuntimeError, match="exactly one level"):
         engine.score_maps(seg, text, S, test=False)
+    # ragged / tiny grids and odd sizes
+    seg2 = [F.normalize(torch.randn(1, 16 * 16, E, device="cuda"), dim=-1)]
+    m, _ = engine.score_maps(seg2, text, 225, test=True, ksize=9, sigma=1.5)
+    ref = orc.anomaly_maps([seg2[0].cpu()], text.cpu(), 225, "Medical")
+    assert (m.cpu() - ref).abs().max().item() < 1e-4
