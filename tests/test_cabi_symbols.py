@@ -15,7 +15,7 @@ def declared_symbols():
 def test_header_declares_the_documented_entry_points():
     syms = declared_symbols()
     for s in ("aaclip_create", "aaclip_destroy", "aaclip_set_weight", "aaclip_forward", "aaclip_score_maps",
-              "aaclip_workspace_bytes", "aaclip_last_error", "aaclip_gemm_bf16", "aaclip_attention"):
+              "aaclip_workspace_bytes", "aaclip_last_error", "aaclip_gemm16", "aaclip_attention"):
         assert s in syms
 
 
