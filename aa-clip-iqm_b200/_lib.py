@@ -38,6 +38,8 @@ EPI_BIAS_F32 = 7
 DT_F16 = 0
 DT_BF16 = 1
 
+PROF_CLASSES = ("gemm", "attention", "layernorm", "other")
+
 ACT_GELU_ERF = 0
 ACT_QUICK_GELU = 1
 
@@ -124,6 +126,10 @@ def _declare(lib):
                                       vp, vp]
     lib.aaclip_last_launch_count.restype = i32
     lib.aaclip_last_launch_count.argtypes = [vp]
+    lib.aaclip_profile_enable.restype = i32
+    lib.aaclip_profile_enable.argtypes = [vp, i32]
+    lib.aaclip_profile_read.restype = i32
+    lib.aaclip_profile_read.argtypes = [vp, ctypes.POINTER(f32), ctypes.POINTER(i32), ctypes.POINTER(ctypes.c_double)]
     lib.aaclip_gemm16.restype = i32
     lib.aaclip_gemm16.argtypes = [i32, vp, vp, i32, i32, i32, i32, vp, vp, vp, i32, vp]
     lib.aaclip_attention.restype = i32
@@ -137,7 +143,7 @@ def _declare(lib):
 EXPORTED_SYMBOLS = [
     "aaclip_version", "aaclip_last_error", "aaclip_create", "aaclip_destroy", "aaclip_set_weight",
     "aaclip_missing_weights", "aaclip_workspace_bytes", "aaclip_forward", "aaclip_score_workspace_bytes",
-    "aaclip_score_maps", "aaclip_last_launch_count", "aaclip_gemm16", "aaclip_attention", "aaclip_layernorm",
+    "aaclip_score_maps", "aaclip_last_launch_count", "aaclip_profile_enable", "aaclip_profile_read", "aaclip_gemm16", "aaclip_attention", "aaclip_layernorm",
     "aaclip_pack16",
 ]
 

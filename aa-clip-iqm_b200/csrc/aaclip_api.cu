@@ -248,6 +248,32 @@ struct AaclipHandle {
   uint16_t* w_det;                   // [E,W]
   std::vector<std::string> missing;
   int last_launches = 0;
+  // optional per-kernel-class device timing (aaclip_profile_*)
+  struct ProfRec { int cls; double flops; cudaEvent_t a, b; };
+  bool prof_on = false;
+  std::vector<ProfRec> prof;
+};
+
+// Records a CUDA-event pair around one launch on the launch stream when profiling is enabled.
+struct ProfScope {
+  AaclipHandle* h;
+  cudaStream_t st;
+  size_t idx = 0;
+  bool on;
+  ProfScope(AaclipHandle* h_, int cls, double flops, cudaStream_t st_) : h(h_), st(st_), on(h_->prof_on) {
+    if (!on) return;
+    AaclipHandle::ProfRec r;
+    r.cls = cls;
+    r.flops = flops;
+    cudaEventCreate(&r.a);
+    cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, st);
+    h->prof.push_back(r);
+    idx = h->prof.size() - 1;
+  }
+  ~ProfScope() {
+    if (on) cudaEventRecord(h->prof[idx].b, st);
+  }
 };
 
 namespace {
@@ -380,6 +406,7 @@ int aaclip_create(const AaclipCfg* cfg, AaclipHandle** out) {
 void aaclip_destroy(AaclipHandle* h) {
   if (h == nullptr) return;
   if (h->arena) cudaFree(h->arena);
+  for (auto& r : h->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   delete h;
 }
 
@@ -508,71 +535,96 @@ int aaclip_forward(AaclipHandle* h, const float* images, int32_t B, void* worksp
   int rc;
   const bool bf = h->bf16;
 
+  // every launch goes through one of these wrappers: launch counting + optional per-class event timing
+  auto gemm = [&](int epi, const void* A, const void* Wt, int m, int n, int k, const GemmEpi& e) -> int {
+    ProfScope ps(h, AACLIP_PROF_GEMM, 2.0 * m * n * k, st);
+    ++launches;
+    return launch_gemm(epi, bf, A, Wt, m, n, k, e, st);
+  };
+  auto lnorm = [&](const float* in, const float* g, const float* bta, void* o16, float* o32, int rows, int skipP) -> int {
+    ProfScope ps(h, AACLIP_PROF_LAYERNORM, 0.0, st);
+    ++launches;
+    return launch_layernorm(bf, in, g, bta, o16, o32, rows, W, skipP, true, st);
+  };
+  auto l2norm = [&](float* t, int rows) -> int {
+    ProfScope ps(h, AACLIP_PROF_OTHER, 0.0, st);
+    ++launches;
+    const int grid = (rows + 7) / 8;
+    if (E == 768) l2norm_rows_kernel<768><<<grid, 256, 0, st>>>(t, rows);
+    else l2norm_rows_kernel<1024><<<grid, 256, 0, st>>>(t, rows);
+    LAUNCH_CHECK("l2norm_rows_kernel");
+    return AACLIP_OK;
+  };
+
   // ---- patch embedding + CLS + positional embedding + ln_pre (model/adapter.py:139-156)
-  if (bf) patch_gather_kernel<true><<<dim3(h->G, B), 256, 0, st>>>(images, patchA, c.img_size, h->G, c.patch, h->KP);
-  else patch_gather_kernel<false><<<dim3(h->G, B), 256, 0, st>>>(images, patchA, c.img_size, h->G, c.patch, h->KP);
-  LAUNCH_CHECK("patch_gather_kernel"); ++launches;
+  {
+    ProfScope ps(h, AACLIP_PROF_OTHER, 0.0, st);
+    if (bf) patch_gather_kernel<true><<<dim3(h->G, B), 256, 0, st>>>(images, patchA, c.img_size, h->G, c.patch, h->KP);
+    else patch_gather_kernel<false><<<dim3(h->G, B), 256, 0, st>>>(images, patchA, c.img_size, h->G, c.patch, h->KP);
+    LAUNCH_CHECK("patch_gather_kernel"); ++launches;
+  }
   {
     GemmEpi e; e.out_f32 = x; e.ldo = W; e.pos = h->pos; e.patches = P;
-    if ((rc = launch_gemm(EPI_PATCH_F32, bf, patchA, h->w_conv, MP, W, h->KP, e, st))) return rc;
-    ++launches;
+    if ((rc = gemm(EPI_PATCH_F32, patchA, h->w_conv, MP, W, h->KP, e))) return rc;
   }
-  cls_row_kernel<<<B, 256, 0, st>>>(x, h->cls, h->pos, N, W);
-  LAUNCH_CHECK("cls_row_kernel"); ++launches;
-  if ((rc = launch_layernorm(bf, x, h->lnpre_g, h->lnpre_b, nullptr, x, M, W, 0, true, st))) return rc;
-  ++launches;
+  {
+    ProfScope ps(h, AACLIP_PROF_OTHER, 0.0, st);
+    cls_row_kernel<<<B, 256, 0, st>>>(x, h->cls, h->pos, N, W);
+    LAUNCH_CHECK("cls_row_kernel"); ++launches;
+  }
+  if ((rc = lnorm(x, h->lnpre_g, h->lnpre_b, nullptr, x, M, 0))) return rc;
 
   // ---- residual attention blocks (model/transformer.py:239-258) + adapters (model/adapter.py:161-172)
   int level_idx = 0;
   for (int i = 0; i < c.layers; ++i) {
     const BlockW& b = h->blk[i];
-    if ((rc = launch_layernorm(bf, x, b.ln1_g, b.ln1_b, xn, nullptr, M, W, 0, true, st))) return rc;
+    if ((rc = lnorm(x, b.ln1_g, b.ln1_b, xn, nullptr, M, 0))) return rc;
     { GemmEpi e; e.bias = b.b_qkv; e.out_16 = qkv; e.ldo = 3 * W;
-      if ((rc = launch_gemm(EPI_BIAS_BF16, bf, xn, b.w_qkv, M, 3 * W, W, e, st))) return rc; }
-    if ((rc = launch_attention(bf, qkv, att, B, N, W, 0, st))) return rc;
+      if ((rc = gemm(EPI_BIAS_BF16, xn, b.w_qkv, M, 3 * W, W, e))) return rc; }
+    {
+      ProfScope ps(h, AACLIP_PROF_ATTENTION, 4.0 * B * (W / 64) * (double)N * N * 64, st);
+      ++launches;
+      if ((rc = launch_attention(bf, qkv, att, B, N, W, 0, st))) return rc;
+    }
     { GemmEpi e; e.bias = b.b_out; e.out_f32 = x; e.ldo = W;
-      if ((rc = launch_gemm(EPI_BIAS_RESID_F32, bf, att, b.w_out, M, W, W, e, st))) return rc; }
-    if ((rc = launch_layernorm(bf, x, b.ln2_g, b.ln2_b, xn, nullptr, M, W, 0, true, st))) return rc;
+      if ((rc = gemm(EPI_BIAS_RESID_F32, att, b.w_out, M, W, W, e))) return rc; }
+    if ((rc = lnorm(x, b.ln2_g, b.ln2_b, xn, nullptr, M, 0))) return rc;
     { GemmEpi e; e.bias = b.b_fc; e.out_16 = hid; e.ldo = F;
-      if ((rc = launch_gemm(c.act == AACLIP_ACT_QUICK_GELU ? EPI_BIAS_QGELU_BF16 : EPI_BIAS_GELU_BF16, bf, xn, b.w_fc, M, F, W, e, st))) return rc; }
+      if ((rc = gemm(c.act == AACLIP_ACT_QUICK_GELU ? EPI_BIAS_QGELU_BF16 : EPI_BIAS_GELU_BF16, xn, b.w_fc, M, F, W, e))) return rc; }
     const bool adapt = i < c.adapt_until;
     { GemmEpi e; e.bias = b.b_proj; e.out_f32 = x; e.ldo = W; e.out_16 = adapt ? xn : nullptr;
-      if ((rc = launch_gemm(EPI_BIAS_RESID_F32, bf, hid, b.w_proj, M, W, F, e, st))) return rc; }
-    launches += 7;
+      if ((rc = gemm(EPI_BIAS_RESID_F32, hid, b.w_proj, M, W, F, e))) return rc; }
     if (adapt) {
       { GemmEpi e; e.out_f32 = abuf; e.ldo = W;
-        if ((rc = launch_gemm(EPI_LEAKY_F32, bf, xn, h->w_adapter[i], M, W, W, e, st))) return rc; }
+        if ((rc = gemm(EPI_LEAKY_F32, xn, h->w_adapter[i], M, W, W, e))) return rc; }
+      ProfScope ps(h, AACLIP_PROF_OTHER, 0.0, st);
       const int grid = (M + 7) / 8;
       if (W == 1024) adapter_blend_kernel<1024><<<grid, 256, 0, st>>>(x, abuf, M, c.adapt_weight, 1.0f - c.adapt_weight);
       else adapter_blend_kernel<768><<<grid, 256, 0, st>>>(x, abuf, M, c.adapt_weight, 1.0f - c.adapt_weight);
       LAUNCH_CHECK("adapter_blend_kernel");
-      launches += 2;
+      ++launches;
     }
     if (level_idx < c.n_levels && c.levels[level_idx] == i + 1) {
       float* tok_f32 = (tokens_out != nullptr) ? tokens_out[level_idx] : nullptr;
-      if ((rc = launch_layernorm(bf, x, h->lnpost_g, h->lnpost_b, tok, tok_f32, MP, W, P, true, st))) return rc;
+      if ((rc = lnorm(x, h->lnpost_g, h->lnpost_b, tok, tok_f32, MP, P))) return rc;
       const int proj_epi = c.proj_relu ? EPI_LEAKY_F32 : EPI_F32;
       { GemmEpi e; e.out_f32 = seg_out[level_idx]; e.ldo = E;
-        if ((rc = launch_gemm(proj_epi, bf, tok, h->w_seg[level_idx], MP, E, W, e, st))) return rc; }
-      const int grid = (MP + 7) / 8;
-      if (E == 768) l2norm_rows_kernel<768><<<grid, 256, 0, st>>>(seg_out[level_idx], MP);
-      else l2norm_rows_kernel<1024><<<grid, 256, 0, st>>>(seg_out[level_idx], MP);
-      LAUNCH_CHECK("l2norm_rows_kernel");
-      launches += 3;
+        if ((rc = gemm(proj_epi, tok, h->w_seg[level_idx], MP, E, W, e))) return rc; }
+      if ((rc = l2norm(seg_out[level_idx], MP))) return rc;
       if (level_idx == c.n_levels - 1) {
         { GemmEpi e; e.out_f32 = detbuf; e.ldo = E;
-          if ((rc = launch_gemm(proj_epi, bf, tok, h->w_det, MP, E, W, e, st))) return rc; }
-        if (E == 768) l2norm_rows_kernel<768><<<grid, 256, 0, st>>>(detbuf, MP);
-        else l2norm_rows_kernel<1024><<<grid, 256, 0, st>>>(detbuf, MP);
-        LAUNCH_CHECK("l2norm_rows_kernel");
+          if ((rc = gemm(proj_epi, tok, h->w_det, MP, E, W, e))) return rc; }
+        if ((rc = l2norm(detbuf, MP))) return rc;
+        ProfScope ps(h, AACLIP_PROF_OTHER, 0.0, st);
         mean_over_patches_kernel<<<dim3((E + 127) / 128, B), 128, 0, st>>>(detbuf, det_out, P, E);
         LAUNCH_CHECK("mean_over_patches_kernel");
-        launches += 3;
+        ++launches;
       }
       ++level_idx;
     }
   }
   if (cls_out != nullptr) {
+    ProfScope ps(h, AACLIP_PROF_OTHER, 0.0, st);
     gather_cls_kernel<<<B, 256, 0, st>>>(x, cls_out, N, W);
     LAUNCH_CHECK("gather_cls_kernel"); ++launches;
   }
@@ -581,6 +633,31 @@ int aaclip_forward(AaclipHandle* h, const float* images, int32_t B, void* worksp
 }
 
 int aaclip_last_launch_count(AaclipHandle* h) { return h ? h->last_launches : -1; }
+
+int aaclip_profile_enable(AaclipHandle* h, int32_t enable) {
+  if (!h) return fail(AACLIP_EINVAL, "aaclip_profile_enable: null handle");
+  for (auto& r : h->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  h->prof.clear();
+  h->prof_on = enable != 0;
+  return AACLIP_OK;
+}
+
+int aaclip_profile_read(AaclipHandle* h, float* ms, int32_t* launches, double* flops) {
+  if (!h || !ms || !launches || !flops) return fail(AACLIP_EINVAL, "aaclip_profile_read: null argument");
+  for (int i = 0; i < AACLIP_PROF_CLASSES; ++i) { ms[i] = 0.f; launches[i] = 0; flops[i] = 0.0; }
+  for (auto& r : h->prof) {
+    CUDA_TRY(cudaEventSynchronize(r.b));
+    float t = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&t, r.a, r.b));
+    ms[r.cls] += t;
+    launches[r.cls] += 1;
+    flops[r.cls] += r.flops;
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  h->prof.clear();
+  return AACLIP_OK;
+}
 
 size_t aaclip_score_workspace_bytes(int32_t B, int32_t n_levels, int32_t P) {
   if (B <= 0 || n_levels <= 0 || P <= 0) return 0;

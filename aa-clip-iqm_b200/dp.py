@@ -1,0 +1,73 @@
+"""Data-parallel sharding of the image batch: one process per GPU, weights replicated, images are
+independent units, and the only collective is the gather of per-image scores and maps to the metric sink
+(rank 0), where the reference's metrics_eval (forward_utils.py:233-308) runs its global min-max on all images.
+
+The reference has no distributed code at all (device hard-wired to cuda:0, test_last.py:206); this module is the
+B200-native addition. It is backend-agnostic host logic: NCCL on the GPU box, gloo in the CPU tests.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_items: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous split of n_items over `world` ranks; the first (n_items % world) ranks get one extra item."""
+    if world <= 0 or not (0 <= rank < world) or n_items < 0:
+        raise ValueError(f"bad shard request n={n_items} rank={rank} world={world}")
+    base, rem = divmod(n_items, world)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def shard_sizes(n_items: int, world: int) -> List[int]:
+    return [shard_range(n_items, r, world)[1] - shard_range(n_items, r, world)[0] for r in range(world)]
+
+
+def gather_predictions(maps: torch.Tensor, scores: torch.Tensor, n_total: Optional[int] = None, dst: int = 0,
+                       group=None) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
+    """Gather per-rank maps [b_r,S,S] and scores [b_r] to `dst` in global image order.
+
+    Ranks may hold different b_r (ragged last shard). Returns (maps [n,S,S], scores [n]) on dst, (None, None)
+    elsewhere. Without an initialised process group (single process) it is the identity.
+    """
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return maps, scores
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    if n_total is None:
+        cnt = torch.tensor([maps.shape[0]], device=maps.device, dtype=torch.int64)
+        dist.all_reduce(cnt, group=group)
+        n_total = int(cnt.item())
+    sizes = shard_sizes(n_total, world)
+    if maps.shape[0] != sizes[rank] or scores.shape[0] != sizes[rank]:
+        raise ValueError(f"rank {rank} holds {maps.shape[0]} images, expected {sizes[rank]} of {n_total}")
+    S = maps.shape[1:]
+    if len(set(sizes)) == 1:
+        # equal shards: one gather each for maps and scores
+        if rank == dst:
+            out_m = torch.empty((n_total, *S), dtype=maps.dtype, device=maps.device)
+            out_s = torch.empty((n_total,), dtype=scores.dtype, device=scores.device)
+            dist.gather(maps.contiguous(), list(out_m.chunk(world)), dst=dst, group=group)
+            dist.gather(scores.contiguous(), list(out_s.chunk(world)), dst=dst, group=group)
+            return out_m, out_s
+        dist.gather(maps.contiguous(), None, dst=dst, group=group)
+        dist.gather(scores.contiguous(), None, dst=dst, group=group)
+        return None, None
+    # ragged shards: pad to the largest, gather, trim on the sink
+    mx = max(sizes)
+    pm = torch.zeros((mx, *S), dtype=maps.dtype, device=maps.device)
+    ps = torch.zeros((mx,), dtype=scores.dtype, device=scores.device)
+    pm[: maps.shape[0]] = maps
+    ps[: scores.shape[0]] = scores
+    if rank == dst:
+        gm = [torch.empty_like(pm) for _ in range(world)]
+        gs = [torch.empty_like(ps) for _ in range(world)]
+        dist.gather(pm, gm, dst=dst, group=group)
+        dist.gather(ps, gs, dst=dst, group=group)
+        return (torch.cat([g[:n] for g, n in zip(gm, sizes)]), torch.cat([g[:n] for g, n in zip(gs, sizes)]))
+    dist.gather(pm, None, dst=dst, group=group)
+    dist.gather(ps, None, dst=dst, group=group)
+    return None, None

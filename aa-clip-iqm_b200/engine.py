@@ -236,6 +236,19 @@ class AaclipEngine:
                                          _ptr(det), tok_arr, _ptr(cls), _stream()), "aaclip_forward")
         return seg, det, tokens, cls
 
+    # -- per-kernel-class device timing (bench.py roofline)
+    def profile_enable(self, on: bool = True):
+        _lib.check(self._lib.aaclip_profile_enable(self._h, int(on)), "aaclip_profile_enable")
+
+    def profile_read(self) -> Dict[str, Dict[str, float]]:
+        n = len(_lib.PROF_CLASSES)
+        ms = (ctypes.c_float * n)()
+        cnt = (ctypes.c_int32 * n)()
+        fl = (ctypes.c_double * n)()
+        _lib.check(self._lib.aaclip_profile_read(self._h, ms, cnt, fl), "aaclip_profile_read")
+        return {name: dict(ms=float(ms[i]), launches=int(cnt[i]), flops=float(fl[i]))
+                for i, name in enumerate(_lib.PROF_CLASSES)}
+
     @property
     def last_launch_count(self) -> int:
         return self._lib.aaclip_last_launch_count(self._h)

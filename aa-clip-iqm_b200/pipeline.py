@@ -1,0 +1,64 @@
+"""Batch-level public API of the hot path: images in, anomaly maps + image scores out.
+
+Mirrors one iteration of the reference's evaluation loop, test_last.get_predictions (test_last.py:70-151, no-IQM
+branch): ``image.to(device)`` -> ``model(image)`` -> ``det @ text`` -> 4 x ``calculate_similarity_map(test=True)`` ->
+level sum -> ``.cpu().numpy()``. Here the device part is two C-ABI calls (aaclip_forward, aaclip_score_maps) and the
+host<->device copies go through pinned staging buffers on the current stream.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import engine as _engine
+
+DOMAIN_BLUR = {"Industrial": (7, 1.0), "Medical": (9, 1.5)}  # forward_utils.py:205-206
+
+
+class AnomalyPredictor:
+    """Adapted ViT-L-14-336 tower + patch-text scoring on one GPU."""
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], text: torch.Tensor, img_size: int = 518,
+                 device: str | torch.device = "cuda", domain: str = "Industrial", max_batch: int = 32,
+                 relu: bool = False, **engine_cfg):
+        if domain not in DOMAIN_BLUR:
+            raise ValueError(f"domain must be one of {sorted(DOMAIN_BLUR)}")
+        self.device = torch.device(device)
+        self.img_size = img_size
+        self.domain = domain
+        self.max_batch = max_batch
+        self.engine = _engine.AaclipEngine(self.device, img_size=img_size, max_batch=max_batch,
+                                           proj_relu=int(relu), **engine_cfg)
+        self.engine.load_state_dict(state_dict)
+        if self.engine.missing:
+            raise RuntimeError(f"{self.engine.missing} weight tensors of the visual path are missing from the state dict")
+        self.text = text.to(self.device, torch.float32).contiguous()
+        self._stage_in: Optional[torch.Tensor] = None
+
+    # -- device-resident entry point (what bench.py's `value` times)
+    def predict_device(self, images: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """images [B,3,S,S] fp32 already on the GPU -> (maps [B,S,S], scores [B]) on the GPU."""
+        seg, det, _, _ = self.engine.forward(images)
+        k, s = DOMAIN_BLUR[self.domain]
+        return _engine.score_maps(seg, self.text, self.img_size, test=True, ksize=k, sigma=s, det=det)
+
+    @property
+    def launches_per_batch(self) -> int:
+        """Kernel launches of one predict_device call (tower + similarity + map + image-score kernels)."""
+        return self.engine.last_launch_count + 3
+
+    # -- host entry point (what bench.py's `e2e` times)
+    def predict_host(self, images_pinned: torch.Tensor, maps_out_pinned: torch.Tensor,
+                     scores_out_pinned: torch.Tensor) -> None:
+        """Pinned host images -> pinned host maps/scores; H2D, compute and D2H are enqueued on the current stream.
+        The caller synchronises (or records an event) before reading the outputs."""
+        B = images_pinned.shape[0]
+        if self._stage_in is None or self._stage_in.shape[0] < B:
+            self._stage_in = torch.empty((max(B, self.max_batch), 3, self.img_size, self.img_size), dtype=torch.float32,
+                                         device=self.device)
+        dev_in = self._stage_in[:B]
+        dev_in.copy_(images_pinned, non_blocking=True)
+        maps, scores = self.predict_device(dev_in)
+        maps_out_pinned.copy_(maps, non_blocking=True)
+        scores_out_pinned.copy_(scores, non_blocking=True)

@@ -136,6 +136,18 @@ int aaclip_score_maps(const float* const* seg, int32_t n_levels, const float* te
 /* Kernel launches enqueued by the last aaclip_forward on this handle (for bench.py's gpu_launches). */
 int aaclip_last_launch_count(AaclipHandle* h);
 
+/* Per-kernel-class device timing of aaclip_forward, for bench.py's roofline: while enabled, every launch is bracketed
+ * by a CUDA-event pair on the launch stream. aaclip_profile_read waits for the recorded events, returns the
+ * accumulated milliseconds / launch counts / algorithmic FLOPs (2*M*N*K per GEMM, 4*B*H*N*N*64 per attention) per
+ * class since the last enable/read, and clears the records. Arrays have AACLIP_PROF_CLASSES entries. */
+#define AACLIP_PROF_GEMM 0
+#define AACLIP_PROF_ATTENTION 1
+#define AACLIP_PROF_LAYERNORM 2
+#define AACLIP_PROF_OTHER 3
+#define AACLIP_PROF_CLASSES 4
+int aaclip_profile_enable(AaclipHandle* h, int32_t enable);
+int aaclip_profile_read(AaclipHandle* h, float* ms, int32_t* launches, double* flops);
+
 /* ---- building blocks, exported for the parity tests (each is exactly what aaclip_forward launches) ---- */
 
 /* C[M,N] = A[M,K] * W[N,K]^T with a fused epilogue (tcgen05/TMEM/TMA GEMM). A, W: `dtype` row-major.
