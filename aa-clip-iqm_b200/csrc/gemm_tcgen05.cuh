@@ -5,8 +5,8 @@
 //   D : fp32 accumulator in TMEM, 128 lanes x 256 columns, double-buffered (512 columns)
 //
 // Roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one lane) + TMEM owner,
-// warps 2..9 = epilogue (TMEM -> registers -> fused math -> global). The epilogue of tile i overlaps the
-// main loop of tile i+1 through the second TMEM accumulator stage.
+// warps 2..9 = epilogue (TMEM -> registers -> swizzled smem transpose -> fused math -> row-coalesced global
+// accesses). The epilogue of tile i overlaps the main loop of tile i+1 through the second TMEM accumulator stage.
 //
 // Replaces, on the reference's path: F.linear / addmm calls inside nn.MultiheadAttention
 // (model/transformer.py:200,237), the MLP (model/transformer.py:211-219), SimpleAdapter / SimpleProj
@@ -47,88 +47,52 @@ constexpr int STAGE_BYTES = A_BYTES + B_BYTES;   // 48 KiB
 constexpr int THREADS = 320;                     // 10 warps
 constexpr int EPI_WARPS = 8;
 constexpr int TMEM_COLS = 512;                   // 2 accumulator stages x 256 columns
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int EPI_STAGE_BYTES = 32 * 128;        // per epilogue warp: 32 rows x 32 fp32, swizzled
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 512 /*barriers*/ + EPI_WARPS * EPI_STAGE_BYTES + 1024 /*align*/;
 }  // namespace gemm_cfg
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 __device__ __forceinline__ float quick_gelu(float x) { return x / (1.0f + __expf(-1.702f * x)); }
 
+// Fused epilogue on one float4 = accumulator values of (row, columns n..n+3), executed in the "coalesced
+// domain": after the smem transpose a quarter-warp owns 128 contiguous bytes of one output row.
 template <int EPI, bool BF16>
-__device__ __forceinline__ void epilogue_store(const uint32_t (&r)[32], int row, int n0, int M, const GemmEpi& e) {
-  if (row >= M) return;
-  float v[32];
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-
+__device__ __forceinline__ void epilogue_apply(float4 v, int row, int n, const GemmEpi& e) {
   if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_QGELU_BF16 ||
                 EPI == EPI_BIAS_RESID_F32 || EPI == EPI_BIAS_F32) {
-    const float4* b4 = reinterpret_cast<const float4*>(e.bias + n0);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float4 b = __ldg(b4 + i);
-      v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
-    }
+    const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + n));
+    v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
   }
   if constexpr (EPI == EPI_BIAS_GELU_BF16) {
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+    v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
   }
   if constexpr (EPI == EPI_BIAS_QGELU_BF16) {
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = quick_gelu(v[i]);
+    v.x = quick_gelu(v.x); v.y = quick_gelu(v.y); v.z = quick_gelu(v.z); v.w = quick_gelu(v.w);
   }
   if constexpr (EPI == EPI_LEAKY_F32) {
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = v[i] > 0.f ? v[i] : 0.01f * v[i];
+    v.x = v.x > 0.f ? v.x : 0.01f * v.x; v.y = v.y > 0.f ? v.y : 0.01f * v.y;
+    v.z = v.z > 0.f ? v.z : 0.01f * v.z; v.w = v.w > 0.f ? v.w : 0.01f * v.w;
   }
-
   if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_QGELU_BF16) {
-    uint4* o = reinterpret_cast<uint4*>(e.out_16 + static_cast<size_t>(row) * e.ldo + n0);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      uint4 u;
-      u.x = ptx::pack16<BF16>(v[8 * i + 0], v[8 * i + 1]);
-      u.y = ptx::pack16<BF16>(v[8 * i + 2], v[8 * i + 3]);
-      u.z = ptx::pack16<BF16>(v[8 * i + 4], v[8 * i + 5]);
-      u.w = ptx::pack16<BF16>(v[8 * i + 6], v[8 * i + 7]);
-      o[i] = u;
-    }
+    *reinterpret_cast<uint2*>(e.out_16 + static_cast<size_t>(row) * e.ldo + n) =
+        make_uint2(ptx::pack16<BF16>(v.x, v.y), ptx::pack16<BF16>(v.z, v.w));
   } else if constexpr (EPI == EPI_BIAS_RESID_F32) {
-    float4* o = reinterpret_cast<float4*>(e.out_f32 + static_cast<size_t>(row) * e.ldo + n0);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float4 x = o[i];
-      x.x += v[4 * i + 0]; x.y += v[4 * i + 1]; x.z += v[4 * i + 2]; x.w += v[4 * i + 3];
-      o[i] = x;
-      v[4 * i + 0] = x.x; v[4 * i + 1] = x.y; v[4 * i + 2] = x.z; v[4 * i + 3] = x.w;
-    }
-    if (e.out_16 != nullptr) {
-      uint4* ob = reinterpret_cast<uint4*>(e.out_16 + static_cast<size_t>(row) * e.ldo + n0);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        uint4 u;
-        u.x = ptx::pack16<BF16>(v[8 * i + 0], v[8 * i + 1]);
-        u.y = ptx::pack16<BF16>(v[8 * i + 2], v[8 * i + 3]);
-        u.z = ptx::pack16<BF16>(v[8 * i + 4], v[8 * i + 5]);
-        u.w = ptx::pack16<BF16>(v[8 * i + 6], v[8 * i + 7]);
-        ob[i] = u;
-      }
-    }
+    float4* o = reinterpret_cast<float4*>(e.out_f32 + static_cast<size_t>(row) * e.ldo + n);
+    float4 x = *o;
+    x.x += v.x; x.y += v.y; x.z += v.z; x.w += v.w;
+    *o = x;
+    if (e.out_16 != nullptr)
+      *reinterpret_cast<uint2*>(e.out_16 + static_cast<size_t>(row) * e.ldo + n) =
+          make_uint2(ptx::pack16<BF16>(x.x, x.y), ptx::pack16<BF16>(x.z, x.w));
   } else {
     size_t orow = static_cast<size_t>(row);
     if constexpr (EPI == EPI_PATCH_F32) {
       const int b = row / e.patches, p = row - b * e.patches;
       orow = static_cast<size_t>(b) * (e.patches + 1) + 1 + p;
-      const float4* pe = reinterpret_cast<const float4*>(e.pos + static_cast<size_t>(p + 1) * e.ldo + n0);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float4 q = __ldg(pe + i);
-        v[4 * i + 0] += q.x; v[4 * i + 1] += q.y; v[4 * i + 2] += q.z; v[4 * i + 3] += q.w;
-      }
+      const float4 q = __ldg(reinterpret_cast<const float4*>(e.pos + static_cast<size_t>(p + 1) * e.ldo + n));
+      v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
     }
-    float4* o = reinterpret_cast<float4*>(e.out_f32 + orow * e.ldo + n0);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] = make_float4(v[4 * i + 0], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    *reinterpret_cast<float4*>(e.out_f32 + orow * e.ldo + n) = v;
   }
 }
 
@@ -227,14 +191,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int e = warp - 2;
     const int q = warp & 3;        // TMEM lane quarter this warp may access
     const int half = e >> 2;       // which 128 of the 256 accumulator columns
+    uint8_t* stage = smem + STAGES * STAGE_BYTES + 512 + e * EPI_STAGE_BYTES;  // this warp's transpose buffer
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
       ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
       ptx::tc_fence_after();
-      const int row = m_blk * BM + q * 32 + lane;
+      const int row0 = m_blk * BM + q * 32;   // first of this warp's 32 rows
       const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + half * 128;
+      const int sub = lane >> 3, unit = lane & 7;   // coalesced domain: 4 rows x (8 lanes x 16 B) per instruction
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         uint32_t r[32];
@@ -246,7 +212,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
         }
-        epilogue_store<EPI, BF16>(r, row, n_blk * BN + half * 128 + c * 32, M, epi);
+        // thread-owns-row -> staging tile [32 rows][128 B], 16-B units XOR-swizzled by (row & 7): conflict-free
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          *reinterpret_cast<uint4*>(stage + lane * 128 + ((u ^ (lane & 7)) << 4)) =
+              make_uint4(r[4 * u], r[4 * u + 1], r[4 * u + 2], r[4 * u + 3]);
+        __syncwarp();
+        const int n = n_blk * BN + half * 128 + c * 32 + unit * 4;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int rr = j * 4 + sub;
+          const float4 v = *reinterpret_cast<const float4*>(stage + rr * 128 + ((unit ^ (rr & 7)) << 4));
+          if (row0 + rr < M) epilogue_apply<EPI, BF16>(v, row0 + rr, n, epi);
+        }
+        __syncwarp();
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
