@@ -51,13 +51,29 @@ constexpr int EPI_STAGE_BYTES = 32 * 128;        // per epilogue warp: 32 rows x
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 512 /*barriers*/ + EPI_WARPS * EPI_STAGE_BYTES + 1024 /*align*/;
 }  // namespace gemm_cfg
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// erf-GELU, x * Phi(x), with erf from Abramowitz & Stegun 7.1.26 (|abs err| <= 1.5e-7, far below the 16-bit store):
+//   erf(z) = 1 - (a1 t + ... + a5 t^5) exp(-z^2),  t = 1/(1 + p z),  z >= 0.
+// ~14 instructions (2 MUFU) instead of ~30 for erff(): the c_fc epilogue must stay below the 8192-cycle MMA time of
+// its tile with 128 activations per epilogue thread.
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
+  poly = fmaf(poly, t, 0.5f * 1.421413741f);
+  poly = fmaf(poly, t, 0.5f * -0.284496736f);
+  poly = fmaf(poly, t, 0.5f * 0.254829592f);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * z * z));
+  const float q = poly * t * e;              // = (1 - erf(z)) / 2 = Phi(-|x|)
+  return x * (x >= 0.f ? 1.0f - q : q);
+}
 __device__ __forceinline__ float quick_gelu(float x) { return x / (1.0f + __expf(-1.702f * x)); }
 
 // Fused epilogue on one float4 = accumulator values of (row, columns n..n+3), executed in the "coalesced
 // domain": after the smem transpose a quarter-warp owns 128 contiguous bytes of one output row.
 template <int EPI, bool BF16>
-__device__ __forceinline__ void epilogue_apply(float4 v, int row, int n, const GemmEpi& e) {
+__device__ __forceinline__ void epilogue_apply(float4 v, int row, int n, const GemmEpi& e,
+                                               float4 resid = make_float4(0.f, 0.f, 0.f, 0.f)) {
   if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_QGELU_BF16 ||
                 EPI == EPI_BIAS_RESID_F32 || EPI == EPI_BIAS_F32) {
     const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + n));
@@ -78,7 +94,7 @@ __device__ __forceinline__ void epilogue_apply(float4 v, int row, int n, const G
         make_uint2(ptx::pack16<BF16>(v.x, v.y), ptx::pack16<BF16>(v.z, v.w));
   } else if constexpr (EPI == EPI_BIAS_RESID_F32) {
     float4* o = reinterpret_cast<float4*>(e.out_f32 + static_cast<size_t>(row) * e.ldo + n);
-    float4 x = *o;
+    float4 x = resid;   // loaded by the caller, 8 rows in flight, before the TMEM load
     x.x += v.x; x.y += v.y; x.z += v.z; x.w += v.w;
     *o = x;
     if (e.out_16 != nullptr)
@@ -203,6 +219,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const int sub = lane >> 3, unit = lane & 7;   // coalesced domain: 4 rows x (8 lanes x 16 B) per instruction
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
+        const int n = n_blk * BN + half * 128 + c * 32 + unit * 4;
+        float4 resid[8];
+        if constexpr (EPI == EPI_BIAS_RESID_F32) {
+          // residual rows for this chunk: 8 independent coalesced loads issued before the TMEM load / transpose
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int rr = row0 + j * 4 + sub;
+            resid[j] = (rr < M) ? *reinterpret_cast<const float4*>(epi.out_f32 + static_cast<size_t>(rr) * epi.ldo + n)
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
         uint32_t r[32];
         ptx::tmem_ld_32x32b_x32(t_base + c * 32, r);
         ptx::tmem_ld_wait();
@@ -218,12 +245,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           *reinterpret_cast<uint4*>(stage + lane * 128 + ((u ^ (lane & 7)) << 4)) =
               make_uint4(r[4 * u], r[4 * u + 1], r[4 * u + 2], r[4 * u + 3]);
         __syncwarp();
-        const int n = n_blk * BN + half * 128 + c * 32 + unit * 4;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int rr = j * 4 + sub;
           const float4 v = *reinterpret_cast<const float4*>(stage + rr * 128 + ((unit ^ (rr & 7)) << 4));
-          if (row0 + rr < M) epilogue_apply<EPI, BF16>(v, row0 + rr, n, epi);
+          if (row0 + rr < M) {
+            if constexpr (EPI == EPI_BIAS_RESID_F32) epilogue_apply<EPI, BF16>(v, row0 + rr, n, epi, resid[j]);
+            else epilogue_apply<EPI, BF16>(v, row0 + rr, n, epi);
+          }
         }
         __syncwarp();
       }
