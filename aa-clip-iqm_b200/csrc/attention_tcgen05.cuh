@@ -4,20 +4,27 @@
 // F.multi_head_attention_forward): q*(1/8), bmm, softmax, bmm, plus the head-averaged weights that
 // AdaptedCLIP.forward discards (model/adapter.py:162). Nothing N x N ever reaches HBM here.
 //
-// Input : packed QKV bf16 [B, N, 3*D] (the QKV GEMM output, q | k | v along the last axis, head h at h*64)
-// Output: O bf16 [B, N, D] (heads concatenated) -- directly the A operand of the out-projection GEMM.
+// Input : packed QKV fp16|bf16 [B, N, 3*D] (the QKV GEMM output, q | k | v along the last axis, head h at h*64)
+// Output: O same dtype [B, N, D] (heads concatenated) -- directly the A operand of the out-projection GEMM.
 //
 // One CTA = (image b, head h, 256 query rows) = two 128-row Q tiles that share every K/V tile:
 //   warp 8      : TMA producer (Q once; K_j/V_j through a 3-stage ring)
-//   warp 9      : tcgen05.mma issuer (one lane) + TMEM owner
-//   warps 0..3  : softmax + O accumulation for Q tile 0 (thread = one query row; lane quarter = warp % 4)
+//   warp 9      : tcgen05.mma issuer (one lane) + TMEM owner   (warps 10, 11 idle: they complete the third
+//                 warpgroup so that setmaxnreg can hand its registers to the softmax warpgroups)
+//   warps 0..3  : softmax for Q tile 0 (thread = one query row; TMEM lane quarter = warp % 4)
 //   warps 4..7  : same for Q tile 1
-// TMEM (512 cols): S_t [128 x 128] fp32 at t*128, PV_t [128 x 64] fp32 at 256 + t*64.
-// Per K/V tile j and Q tile t:  S_t = Q_t K_j^T (SS MMA) -> softmax warps read S_t twice from TMEM (row max,
-// then exp2) and write P_t (bf16) into a 128B-swizzled K-major smem tile -> PV_t = P_t V_j (V is the MN-major
-// B operand, straight from the TMA tile) -> the owning threads fold PV_t into their fp32 O registers with the
-// usual online-softmax rescale. While one Q tile is in its softmax phase the tensor core runs the other tile's
-// S / PV MMAs (ping-pong), so MUFU and tensor pipes overlap.
+// TMEM (512 cols): S_t [128 x 128] fp32 at t*128; O_t [128 x 64] fp32 accumulator at 256 + t*64.
+//
+// Per K/V tile j and Q tile t:
+//   MMA   : S_t = Q_t K_j^T (SS, M128 N128 K64)                                         -> s_full[t]
+//   softmax: whole S row (128 fp32) TMEM -> registers in one go                         -> s_free[t]  (S_t(j+1) may
+//            now be issued: the next QK^T runs under this tile's exponentials)
+//            row max; LAZY rescale: the running max used for the exponentials only moves when the true max grew by
+//            more than 2^8 (then O_t in TMEM and the row sum are rescaled once); P = exp2(S*scale - m) <= 256
+//            packed to 16 bit into a 128B-swizzled K-major smem tile                    -> p_full[t]
+//   MMA   : O_t += P_t V_j (V = MN-major B operand straight from the TMA tile)          -> o_full[t]
+// O stays in TMEM for the whole K/V loop; the softmax threads read it once at the end, scale by 1/rowsum and store.
+// While one Q tile is in its exponential phase the tensor core works for the other tile (ping-pong).
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -28,21 +35,22 @@ namespace aaclip {
 
 namespace attn_cfg {
 constexpr int BQ = 128, QT = 2, BKV = 128, HD = 64, KV_STAGES = 3;
-constexpr int Q_BYTES = BQ * HD * 2;         // 16 KiB per Q tile
+constexpr int Q_BYTES = BQ * HD * 2;              // 16 KiB per Q tile
 constexpr int KV_STAGE_BYTES = 2 * BKV * HD * 2;  // K tile + V tile = 32 KiB
-constexpr int P_BYTES = BQ * BKV * 2;        // 32 KiB per Q tile
-constexpr int THREADS = 320;
+constexpr int P_BYTES = BQ * BKV * 2;             // 32 KiB per Q tile
+constexpr int THREADS = 384;                      // 3 warpgroups: softmax tile 0, softmax tile 1, {TMA, MMA, 2 idle}
 constexpr int TMEM_COLS = 512;
 constexpr int OFF_Q = 0;
 constexpr int OFF_KV = QT * Q_BYTES;
 constexpr int OFF_P = OFF_KV + KV_STAGES * KV_STAGE_BYTES;
 constexpr int OFF_BAR = OFF_P + QT * P_BYTES;
 constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+constexpr float RESCALE_THRESHOLD = 8.0f;         // log2 units: P never exceeds 2^8
 }  // namespace attn_cfg
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
-  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
 
@@ -56,9 +64,10 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, uint16_t*
   uint64_t* q_full = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint64_t* kv_full = q_full + 1;             // [KV_STAGES]
   uint64_t* kv_empty = kv_full + KV_STAGES;   // [KV_STAGES]
-  uint64_t* s_full = kv_empty + KV_STAGES;    // [QT]
-  uint64_t* p_full = s_full + QT;             // [QT]
-  uint64_t* o_full = p_full + QT;             // [QT]
+  uint64_t* s_full = kv_empty + KV_STAGES;    // [QT]  MMA -> softmax : S_t(j) complete
+  uint64_t* s_free = s_full + QT;             // [QT]  softmax -> MMA : S_t(j) is in registers
+  uint64_t* p_full = s_free + QT;             // [QT]  softmax -> MMA : P_t(j) in smem, O_t rescaled if needed
+  uint64_t* o_full = p_full + QT;             // [QT]  MMA -> softmax : O_t += P_t(j) V_j complete
   uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(o_full + QT);
 
   const int warp = threadIdx.x >> 5;
@@ -77,6 +86,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, uint16_t*
     }
     for (int t = 0; t < QT; ++t) {
       ptx::mbar_init(&s_full[t], 1);
+      ptx::mbar_init(&s_free[t], 4);
       ptx::mbar_init(&p_full[t], 4);
       ptx::mbar_init(&o_full[t], 1);
     }
@@ -91,7 +101,12 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, uint16_t*
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
 
-  if (warp == 8) {
+  // The softmax warpgroups need a whole S row in registers: warpgroup 2 (TMA, MMA, 2 idle warps) hands its
+  // registers over with setmaxnreg (issued inside each role's branch so ptxas allocates per role).
+  if (warp >= 10) {
+    ptx::reg_dec<40>();
+  } else if (warp == 8) {
+    ptx::reg_dec<40>();
     // ===================== TMA producer =====================
     if (lane == 0) {
       ptx::mbar_arrive_expect_tx(q_full, QT * Q_BYTES);
@@ -109,10 +124,11 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, uint16_t*
       }
     }
   } else if (warp == 9) {
+    ptx::reg_dec<40>();
     // ===================== MMA issuer (single thread) =====================
     if (lane == 0) {
       constexpr uint32_t idesc_s = ptx::make_idesc_16(BQ, BKV, 0, BF16);   // S = Q K^T : both operands K-major
-      constexpr uint32_t idesc_pv = ptx::make_idesc_16(BQ, HD, 1, BF16);   // PV = P V  : V is MN-major
+      constexpr uint32_t idesc_pv = ptx::make_idesc_16(BQ, HD, 1, BF16);   // O += P V  : V is MN-major
       const uint32_t q_addr = ptx::smem_u32(smem + OFF_Q);
       const uint32_t kv_addr = ptx::smem_u32(smem + OFF_KV);
       const uint32_t p_addr = ptx::smem_u32(smem + OFF_P);
@@ -125,7 +141,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, uint16_t*
           ptx::tc_mma_f16(tmem_base + t * BKV, a + 2 * k, bd + 2 * k, idesc_s, k != 0 ? 1u : 0u);
         ptx::tc_commit(&s_full[t]);
       };
-      auto issue_pv = [&](int t, int stage) {
+      auto issue_pv = [&](int t, int stage, uint32_t accumulate) {
         const uint32_t pa = p_addr + t * P_BYTES;
         const uint32_t va = kv_addr + stage * KV_STAGE_BYTES + BKV * HD * 2;
 #pragma unroll
@@ -134,7 +150,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, uint16_t*
           const uint64_t a = ptx::make_sw128_desc(pa + (k >> 2) * (BQ * 128) + (k & 3) * 32);
           // B (MN-major): 16 kv rows of 128 B per k-step.
           const uint64_t bd = ptx::make_sw128_desc(va + k * 16 * 128);
-          ptx::tc_mma_f16(tmem_base + 2 * BKV + t * HD, a, bd, idesc_pv, k != 0 ? 1u : 0u);
+          ptx::tc_mma_f16(tmem_base + 2 * BKV + t * HD, a, bd, idesc_pv, (accumulate | k) != 0 ? 1u : 0u);
         }
         ptx::tc_commit(&o_full[t]);
       };
@@ -150,25 +166,27 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, uint16_t*
         int nstage = stage + 1;
         uint32_t nphase = phase;
         if (nstage == KV_STAGES) { nstage = 0; nphase ^= 1; }
-        for (int t = 0; t < n_qt; ++t) {
-          ptx::mbar_wait(&p_full[t], j & 1);   // P_t(j) in smem, S_t and PV_t drained by the softmax warps
-          ptx::tc_fence_after();
-          if (j + 1 < n_kv_tiles) {
-            if (t == 0) {
-              ptx::mbar_wait(&kv_full[nstage], nphase);
-              ptx::tc_fence_after();
-            }
+        if (j + 1 < n_kv_tiles) {
+          ptx::mbar_wait(&kv_full[nstage], nphase);
+          for (int t = 0; t < n_qt; ++t) {
+            ptx::mbar_wait(&s_free[t], j & 1);   // S_t(j) has been copied to registers
+            ptx::tc_fence_after();
             issue_s(t, nstage);
           }
-          issue_pv(t, stage);
-          if (t == n_qt - 1) ptx::tc_commit(&kv_empty[stage]);
         }
+        for (int t = 0; t < n_qt; ++t) {
+          ptx::mbar_wait(&p_full[t], j & 1);     // P_t(j) in smem; O_t rescaled if the running max moved
+          ptx::tc_fence_after();
+          issue_pv(t, stage, j > 0 ? 1u : 0u);
+        }
+        ptx::tc_commit(&kv_empty[stage]);
         stage = nstage;
         phase = nphase;
       }
     }
   } else {
-    // ===================== softmax / accumulate warps =====================
+    ptx::reg_inc<216>();
+    // ===================== softmax warps =====================
     const int t = warp >> 2;
     const int q = warp & 3;
     if (t < n_qt) {
@@ -180,71 +198,92 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, uint16_t*
       uint8_t* p_row = smem + OFF_P + t * P_BYTES + r * 128;
       const int rx = r & 7;
 
-      float m = -1e30f, l = 0.f;
-      float o[HD];
-#pragma unroll
-      for (int i = 0; i < HD; ++i) o[i] = 0.f;
+      float m_used = -1e30f;   // the maximum the exponentials are taken against (log2 domain, scaled)
+      float l = 0.f;           // running row sum of P
 
       for (int j = 0; j < n_kv_tiles; ++j) {
         ptx::mbar_wait(&s_full[t], j & 1);
         ptx::tc_fence_after();
-        const int col0 = j * BKV;
-        int lim_all = n_tok - col0;                       // valid columns in this tile
-        if (causal) lim_all = min(lim_all, qrow - col0 + 1);
-
-        // ---- pass 1: row maximum
-        float mx = -INFINITY;
-#pragma unroll 1
-        for (int c = 0; c < BKV / 32; ++c) {
-          uint32_t v[32];
-          ptx::tmem_ld_32x32b_x32(s_tmem + c * 32, v);
+        uint32_t s[BKV];
+        {
+          uint32_t(&s0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[0]);
+          uint32_t(&s1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[32]);
+          uint32_t(&s2)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[64]);
+          uint32_t(&s3)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[96]);
+          ptx::tmem_ld_32x32b_x32(s_tmem + 0, s0);
+          ptx::tmem_ld_32x32b_x32(s_tmem + 32, s1);
+          ptx::tmem_ld_32x32b_x32(s_tmem + 64, s2);
+          ptx::tmem_ld_32x32b_x32(s_tmem + 96, s3);
           ptx::tmem_ld_wait();
-          const int lim = lim_all - c * 32;
-#pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (i < lim) ? __uint_as_float(v[i]) : -INFINITY);
         }
-        const float m_new = fmaxf(m, mx * scale_log2);
-        const float alpha = ex2_approx(m - m_new);
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&s_free[t]);
 
-        // ---- fold the previous tile's PV into O, then rescale to the new maximum
+        const int col0 = j * BKV;
+        int lim = n_tok - col0;                       // number of valid columns in this tile
+        if (causal) lim = min(lim, qrow - col0 + 1);
+        const bool full_tile = __all_sync(0xffffffffu, lim >= BKV);
+
+        // ---- row maximum
+        float mx = -INFINITY;
+        if (full_tile) {
+#pragma unroll
+          for (int i = 0; i < BKV; ++i) mx = fmaxf(mx, __uint_as_float(s[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < BKV; ++i) {
+            if (i >= lim) s[i] = 0xff800000u;   // -inf: exp2 gives 0, contributes nothing
+            mx = fmaxf(mx, __uint_as_float(s[i]));
+          }
+        }
+        const float m_tile = mx * scale_log2;
+
+        // ---- P(j-1) must have been consumed (and O_t be quiescent) before we touch P smem / O TMEM
         if (j > 0) {
           ptx::mbar_wait(&o_full[t], (j - 1) & 1);
           ptx::tc_fence_after();
-#pragma unroll
-          for (int c = 0; c < HD / 32; ++c) {
-            uint32_t v[32];
-            ptx::tmem_ld_32x32b_x32(o_tmem + c * 32, v);
-            ptx::tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[c * 32 + i] = (o[c * 32 + i] + __uint_as_float(v[i])) * alpha;
-          }
         }
-        l *= alpha;
-        m = m_new;
 
-        // ---- pass 2: P = exp2(S*scale - m) -> bf16 -> swizzled K-major smem tile
-        float rowsum = 0.f;
-#pragma unroll 1
-        for (int c = 0; c < BKV / 32; ++c) {
-          uint32_t v[32];
-          ptx::tmem_ld_32x32b_x32(s_tmem + c * 32, v);
-          ptx::tmem_ld_wait();
-          const int lim = lim_all - c * 32;
-          float p[32];
+        // ---- lazy rescale: only when the true maximum ran away from the one in use by more than 2^8
+        const bool need = m_tile > m_used + RESCALE_THRESHOLD;
+        if (__any_sync(0xffffffffu, need)) {
+          const float m_new = need ? m_tile : m_used;
+          const float alpha = ex2_approx(m_used - m_new);   // 1 for rows that keep their maximum
+          if (j > 0) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float e = ex2_approx(fmaf(__uint_as_float(v[i]), scale_log2, -m_new));
-            p[i] = (i < lim) ? e : 0.f;
-            rowsum += p[i];
+            for (int c = 0; c < HD / 16; ++c) {
+              uint32_t v[16];
+              ptx::tmem_ld_32x32b_x16(o_tmem + c * 16, v);
+              ptx::tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+              ptx::tmem_st_32x32b_x16(o_tmem + c * 16, v);
+            }
+            ptx::tmem_st_wait();
           }
+          l *= alpha;
+          m_used = m_new;
+        }
+
+        // ---- P = exp2(S*scale - m_used) -> 16 bit -> swizzled K-major smem tile; row sum in fp32
+        float rowsum = 0.f;
+#pragma unroll
+        for (int c = 0; c < BKV / 32; ++c) {
           uint8_t* chunk = p_row + (c >> 1) * (BQ * 128);
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
+            float p[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              p[i] = ex2_approx(fmaf(__uint_as_float(s[c * 32 + u * 8 + i]), scale_log2, -m_used));
+              rowsum += p[i];
+            }
             uint4 w;
-            w.x = ptx::pack16<BF16>(p[8 * u + 0], p[8 * u + 1]);
-            w.y = ptx::pack16<BF16>(p[8 * u + 2], p[8 * u + 3]);
-            w.z = ptx::pack16<BF16>(p[8 * u + 4], p[8 * u + 5]);
-            w.w = ptx::pack16<BF16>(p[8 * u + 6], p[8 * u + 7]);
+            w.x = ptx::pack16<BF16>(p[0], p[1]);
+            w.y = ptx::pack16<BF16>(p[2], p[3]);
+            w.z = ptx::pack16<BF16>(p[4], p[5]);
+            w.w = ptx::pack16<BF16>(p[6], p[7]);
             const int unit = ((c & 1) * 4 + u) ^ rx;
             *reinterpret_cast<uint4*>(chunk + unit * 16) = w;
           }
@@ -257,28 +296,27 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, uint16_t*
         if (lane == 0) ptx::mbar_arrive(&p_full[t]);
       }
 
-      // ---- last PV, normalise, store
+      // ---- all P V accumulated: normalise and store
       ptx::mbar_wait(&o_full[t], (n_kv_tiles - 1) & 1);
       ptx::tc_fence_after();
       const float inv_l = 1.0f / l;
+      uint16_t* dst_row = out + (static_cast<size_t>(b) * n_tok + qrow) * D + h * HD;
 #pragma unroll
       for (int c = 0; c < HD / 32; ++c) {
         uint32_t v[32];
         ptx::tmem_ld_32x32b_x32(o_tmem + c * 32, v);
         ptx::tmem_ld_wait();
+        if (qrow < n_tok) {
+          uint4* dst = reinterpret_cast<uint4*>(dst_row + c * 32);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o[c * 32 + i] = (o[c * 32 + i] + __uint_as_float(v[i])) * inv_l;
-      }
-      if (qrow < n_tok) {
-        uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<size_t>(b) * n_tok + qrow) * D + h * HD);
-#pragma unroll
-        for (int u = 0; u < HD / 8; ++u) {
-          uint4 w;
-          w.x = ptx::pack16<BF16>(o[8 * u + 0], o[8 * u + 1]);
-          w.y = ptx::pack16<BF16>(o[8 * u + 2], o[8 * u + 3]);
-          w.z = ptx::pack16<BF16>(o[8 * u + 4], o[8 * u + 5]);
-          w.w = ptx::pack16<BF16>(o[8 * u + 6], o[8 * u + 7]);
-          dst[u] = w;
+          for (int u = 0; u < 4; ++u) {
+            uint4 w;
+            w.x = ptx::pack16<BF16>(__uint_as_float(v[8 * u + 0]) * inv_l, __uint_as_float(v[8 * u + 1]) * inv_l);
+            w.y = ptx::pack16<BF16>(__uint_as_float(v[8 * u + 2]) * inv_l, __uint_as_float(v[8 * u + 3]) * inv_l);
+            w.z = ptx::pack16<BF16>(__uint_as_float(v[8 * u + 4]) * inv_l, __uint_as_float(v[8 * u + 5]) * inv_l);
+            w.w = ptx::pack16<BF16>(__uint_as_float(v[8 * u + 6]) * inv_l, __uint_as_float(v[8 * u + 7]) * inv_l);
+            dst[u] = w;
+          }
         }
       }
     }
