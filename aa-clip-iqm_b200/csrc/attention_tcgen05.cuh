@@ -48,6 +48,11 @@ constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
 constexpr float RESCALE_THRESHOLD = 8.0f;         // log2 units: P never exceeds 2^8
 }  // namespace attn_cfg
 
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));   // FMNMX3 on sm_100
+  return r;
+}
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -226,17 +231,22 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, uint16_t*
         const bool full_tile = __all_sync(0xffffffffu, lim >= BKV);
 
         // ---- row maximum
-        float mx = -INFINITY;
-        if (full_tile) {
+        if (!full_tile) {
 #pragma unroll
-          for (int i = 0; i < BKV; ++i) mx = fmaxf(mx, __uint_as_float(s[i]));
-        } else {
-#pragma unroll
-          for (int i = 0; i < BKV; ++i) {
+          for (int i = 0; i < BKV; ++i)
             if (i >= lim) s[i] = 0xff800000u;   // -inf: exp2 gives 0, contributes nothing
-            mx = fmaxf(mx, __uint_as_float(s[i]));
-          }
         }
+        // 8 independent FMNMX3 chains (a single 128-long dependent chain would cost ~500 cycles of latency)
+        float mxp[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          mxp[c] = max3(__uint_as_float(s[c * 16]), __uint_as_float(s[c * 16 + 1]), __uint_as_float(s[c * 16 + 2]));
+#pragma unroll
+          for (int i = 3; i < 15; i += 2)
+            mxp[c] = max3(mxp[c], __uint_as_float(s[c * 16 + i]), __uint_as_float(s[c * 16 + i + 1]));
+          mxp[c] = fmaxf(mxp[c], __uint_as_float(s[c * 16 + 15]));
+        }
+        const float mx = max3(max3(mxp[0], mxp[1], mxp[2]), max3(mxp[3], mxp[4], mxp[5]), fmaxf(mxp[6], mxp[7]));
         const float m_tile = mx * scale_log2;
 
         // ---- P(j-1) must have been consumed (and O_t be quiescent) before we touch P smem / O TMEM
@@ -267,7 +277,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, uint16_t*
         }
 
         // ---- P = exp2(S*scale - m_used) -> 16 bit -> swizzled K-major smem tile; row sum in fp32
-        float rowsum = 0.f;
+        float rs[4] = {0.f, 0.f, 0.f, 0.f};   // independent partial sums (no 128-long FADD chain)
 #pragma unroll
         for (int c = 0; c < BKV / 32; ++c) {
           uint8_t* chunk = p_row + (c >> 1) * (BQ * 128);
@@ -277,7 +287,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, uint16_t*
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               p[i] = ex2_approx(fmaf(__uint_as_float(s[c * 32 + u * 8 + i]), scale_log2, -m_used));
-              rowsum += p[i];
+              rs[i & 3] += p[i];
             }
             uint4 w;
             w.x = ptx::pack16<BF16>(p[0], p[1]);
@@ -288,7 +298,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, uint16_t*
             *reinterpret_cast<uint4*>(chunk + unit * 16) = w;
           }
         }
-        l += rowsum;
+        l += (rs[0] + rs[1]) + (rs[2] + rs[3]);
 
         ptx::tc_fence_before();
         ptx::fence_proxy_async_smem();
