@@ -8,25 +8,24 @@
 // Output: O same dtype [B, N, D] (heads concatenated) -- directly the A operand of the out-projection GEMM.
 //
 // One CTA = (image b, head h, 256 query rows) = two 128-row Q tiles that share every K/V tile:
-//   warp 8      : TMA producer (Q once; K_j and V_j through separate 2-deep rings)
+//   warp 8      : TMA producer (Q once; K_j and V_j through separate 3-deep rings)
 //   warp 9      : tcgen05.mma issuer (one lane) + TMEM owner   (warps 10, 11 idle: they complete the third
 //                 warpgroup so that setmaxnreg can hand its registers to the softmax warpgroups)
 //   warps 0..3  : softmax for Q tile 0 (thread = one query row; TMEM lane quarter = warp % 4)
 //   warps 4..7  : same for Q tile 1
-// TMEM (512 cols): S_t [128 x 128] fp32 at t*128; O_t [128 x 64] fp32 accumulator at 256 + t*64.
-// smem: Q 2x16K | K 2x16K | V 2x16K | P [tile][parity] 4x32K  = 224 KiB.
+// TMEM (512 cols): S_t [128x128] fp32 at t*128 | O_t [128x64] fp32 at 256+t*64 | P_t [128x128] 16-bit at 384+t*64.
 //
 // Per K/V tile j and Q tile t:
-//   MMA   : S_t = Q_t K_j^T (SS, M128 N128 K64)                                         -> s_full[t]
+//   MMA   : S_t = Q_t K_j^T (SS MMA, M128 N128 K64)                                     -> s_full[t]
 //   softmax: whole S row (128 fp32) TMEM -> registers in one go                         -> s_free[t]  (S_t(j+1) may
 //            now be issued: the next QK^T runs under this tile's exponentials)
 //            row max; LAZY rescale: the running max used for the exponentials only moves when the true max grew by
 //            more than 2^8 (then O_t in TMEM and the row sum are rescaled once); P = exp2(S*scale - m) <= 256
-//            packed to 16 bit into the 128B-swizzled K-major smem tile P[t][j&1]        -> p_full[t]
-//   MMA   : O_t += P_t V_j (V = MN-major B operand straight from the TMA tile)          -> o_full[t][j&1]
-// P is double-buffered so the softmax threads only depend on the P V product of two tiles ago; O stays in TMEM for
-// the whole K/V loop and is read once at the end (scaled by 1/rowsum). While one Q tile is in its exponential phase
-// the tensor core works for the other tile.
+//            packed to 16 bit and written back to TENSOR MEMORY (tcgen05.st)            -> p_full[t]
+//   MMA   : O_t += P_t V_j  (TS MMA: A = P_t from TMEM, B = V_j MN-major straight from the TMA tile) -> o_full[t]
+// P never touches shared memory: smem bandwidth (128 B/clk) is what bounds SS MMAs at this tile shape, and a
+// P round trip through smem would double the traffic. O stays in TMEM for the whole K/V loop and is read once at
+// the end (scaled by 1/rowsum). While one Q tile is in its exponential phase the tensor core works for the other.
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -36,16 +35,15 @@
 namespace aaclip {
 
 namespace attn_cfg {
-constexpr int BQ = 128, QT = 2, BKV = 128, HD = 64, KV_STAGES = 2;
+constexpr int BQ = 128, QT = 2, BKV = 128, HD = 64, KV_STAGES = 3;
 constexpr int TILE_BYTES = 128 * HD * 2;          // one Q / K / V tile: 128 rows x 128 B = 16 KiB
-constexpr int P_BYTES = BQ * BKV * 2;             // 32 KiB per P tile
 constexpr int THREADS = 384;                      // 3 warpgroups: softmax tile 0, softmax tile 1, {TMA, MMA, 2 idle}
 constexpr int TMEM_COLS = 512;
+constexpr int TM_S = 0, TM_O = 2 * BKV, TM_P = TM_O + 2 * HD;   // TMEM column map
 constexpr int OFF_Q = 0;
 constexpr int OFF_K = OFF_Q + QT * TILE_BYTES;
 constexpr int OFF_V = OFF_K + KV_STAGES * TILE_BYTES;
-constexpr int OFF_P = OFF_V + KV_STAGES * TILE_BYTES;
-constexpr int OFF_BAR = OFF_P + QT * 2 * P_BYTES;
+constexpr int OFF_BAR = OFF_V + KV_STAGES * TILE_BYTES;
 constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
 constexpr float RESCALE_THRESHOLD = 8.0f;         // log2 units: P never exceeds 2^8
 }  // namespace attn_cfg
@@ -69,15 +67,15 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, uint16_t*
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* q_full = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
-  uint64_t* k_full = q_full + 1;              // [2]  TMA -> MMA
-  uint64_t* k_empty = k_full + 2;             // [2]  MMA -> TMA : every S MMA reading K_j has retired
-  uint64_t* v_full = k_empty + 2;             // [2]
-  uint64_t* v_empty = v_full + 2;             // [2]  MMA -> TMA : every P V MMA reading V_j has retired
-  uint64_t* s_full = v_empty + 2;             // [QT] MMA -> softmax : S_t(j) complete
-  uint64_t* s_free = s_full + QT;             // [QT] softmax -> MMA : S_t(j) is in registers
-  uint64_t* p_full = s_free + QT;             // [QT] softmax -> MMA : P_t(j) in smem, O_t rescaled if needed
-  uint64_t* o_full = p_full + QT;             // [QT][2] MMA -> softmax : O_t += P_t(j) V_j complete (slot j&1)
-  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(o_full + QT * 2);
+  uint64_t* k_full = q_full + 1;                  // [KV_STAGES] TMA -> MMA
+  uint64_t* k_empty = k_full + KV_STAGES;         // [KV_STAGES] MMA -> TMA : every S MMA reading K_j has retired
+  uint64_t* v_full = k_empty + KV_STAGES;         // [KV_STAGES]
+  uint64_t* v_empty = v_full + KV_STAGES;         // [KV_STAGES] MMA -> TMA : every P V MMA reading V_j has retired
+  uint64_t* s_full = v_empty + KV_STAGES;         // [QT] MMA -> softmax : S_t(j) complete
+  uint64_t* s_free = s_full + QT;                 // [QT] softmax -> MMA : S_t(j) is in registers
+  uint64_t* p_full = s_free + QT;                 // [QT] softmax -> MMA : P_t(j) in TMEM, O_t rescaled if needed
+  uint64_t* o_full = p_full + QT;                 // [QT] MMA -> softmax : O_t += P_t(j) V_j complete
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(o_full + QT);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -89,7 +87,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, uint16_t*
   if (warp == 8 && lane == 0) {
     ptx::prefetch_tmap(&tmap_qkv);
     ptx::mbar_init(q_full, 1);
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < KV_STAGES; ++s) {
       ptx::mbar_init(&k_full[s], 1);
       ptx::mbar_init(&k_empty[s], 1);
       ptx::mbar_init(&v_full[s], 1);
@@ -99,8 +97,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, uint16_t*
       ptx::mbar_init(&s_full[t], 1);
       ptx::mbar_init(&s_free[t], 4);
       ptx::mbar_init(&p_full[t], 4);
-      ptx::mbar_init(&o_full[t * 2 + 0], 1);
-      ptx::mbar_init(&o_full[t * 2 + 1], 1);
+      ptx::mbar_init(&o_full[t], 1);
     }
     ptx::fence_mbar_init();
   }
@@ -124,15 +121,16 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, uint16_t*
       ptx::mbar_arrive_expect_tx(q_full, QT * TILE_BYTES);
       for (int t = 0; t < QT; ++t)
         ptx::tma_load_3d(smem + OFF_Q + t * TILE_BYTES, &tmap_qkv, q_full, h * HD, q_base + t * BQ, b);
+      int st = 0;
+      uint32_t ph = 0;
       for (int j = 0; j < n_kv_tiles; ++j) {
-        const int st = j & 1;
-        const uint32_t ph = (j >> 1) & 1;   // use count of this slot
         ptx::mbar_wait(&k_empty[st], ph ^ 1);
         ptx::mbar_arrive_expect_tx(&k_full[st], TILE_BYTES);
         ptx::tma_load_3d(smem + OFF_K + st * TILE_BYTES, &tmap_qkv, &k_full[st], D + h * HD, j * BKV, b);
         ptx::mbar_wait(&v_empty[st], ph ^ 1);
         ptx::mbar_arrive_expect_tx(&v_full[st], TILE_BYTES);
         ptx::tma_load_3d(smem + OFF_V + st * TILE_BYTES, &tmap_qkv, &v_full[st], 2 * D + h * HD, j * BKV, b);
+        if (++st == KV_STAGES) { st = 0; ph ^= 1; }
       }
     }
   } else if (warp == 9) {
@@ -144,28 +142,25 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, uint16_t*
       const uint32_t q_addr = ptx::smem_u32(smem + OFF_Q);
       const uint32_t k_addr = ptx::smem_u32(smem + OFF_K);
       const uint32_t v_addr = ptx::smem_u32(smem + OFF_V);
-      const uint32_t p_addr = ptx::smem_u32(smem + OFF_P);
 
-      auto issue_s = [&](int t, int j) {
+      auto issue_s = [&](int t, int stage) {
         const uint64_t a = ptx::make_sw128_desc(q_addr + t * TILE_BYTES);
-        const uint64_t bd = ptx::make_sw128_desc(k_addr + (j & 1) * TILE_BYTES);
+        const uint64_t bd = ptx::make_sw128_desc(k_addr + stage * TILE_BYTES);
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k)
-          ptx::tc_mma_f16(tmem_base + t * BKV, a + 2 * k, bd + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+          ptx::tc_mma_f16(tmem_base + TM_S + t * BKV, a + 2 * k, bd + 2 * k, idesc_s, k != 0 ? 1u : 0u);
         ptx::tc_commit(&s_full[t]);
       };
-      auto issue_pv = [&](int t, int j) {
-        const uint32_t pa = p_addr + (t * 2 + (j & 1)) * P_BYTES;
-        const uint32_t va = v_addr + (j & 1) * TILE_BYTES;
+      auto issue_pv = [&](int t, int stage, uint32_t accumulate) {
+        const uint32_t va = v_addr + stage * TILE_BYTES;
 #pragma unroll
         for (int k = 0; k < BKV / 16; ++k) {
-          // A: two 64-wide K chunks (16 KiB apart), 32 B per k-step inside a chunk.
-          const uint64_t a = ptx::make_sw128_desc(pa + (k >> 2) * (BQ * 128) + (k & 3) * 32);
-          // B (MN-major): 16 kv rows of 128 B per k-step.
+          // A: P_t in TMEM, 8 columns (16 packed K elements) per k-step.  B (MN-major): 16 kv rows of 128 B.
           const uint64_t bd = ptx::make_sw128_desc(va + k * 16 * 128);
-          ptx::tc_mma_f16(tmem_base + 2 * BKV + t * HD, a, bd, idesc_pv, (j | k) != 0 ? 1u : 0u);
+          ptx::tc_mma_f16_ts(tmem_base + TM_O + t * HD, tmem_base + TM_P + t * (BKV / 2) + k * 8, bd, idesc_pv,
+                             (accumulate | k) != 0 ? 1u : 0u);
         }
-        ptx::tc_commit(&o_full[t * 2 + (j & 1)]);
+        ptx::tc_commit(&o_full[t]);
       };
 
       ptx::mbar_wait(q_full, 0);
@@ -174,23 +169,30 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, uint16_t*
       for (int t = 0; t < n_qt; ++t) issue_s(t, 0);
       ptx::tc_commit(&k_empty[0]);
 
+      int st = 0;             // ring slot of K_j / V_j
+      uint32_t ph = 0;
       for (int j = 0; j < n_kv_tiles; ++j) {
+        int nst = st + 1;
+        uint32_t nph = ph;
+        if (nst == KV_STAGES) { nst = 0; nph ^= 1; }
         if (j + 1 < n_kv_tiles) {
-          ptx::mbar_wait(&k_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
+          ptx::mbar_wait(&k_full[nst], nph);
           for (int t = 0; t < n_qt; ++t) {
             ptx::mbar_wait(&s_free[t], j & 1);   // S_t(j) has been copied to registers
             ptx::tc_fence_after();
-            issue_s(t, j + 1);
+            issue_s(t, nst);
           }
-          ptx::tc_commit(&k_empty[(j + 1) & 1]);
+          ptx::tc_commit(&k_empty[nst]);
         }
-        ptx::mbar_wait(&v_full[j & 1], (j >> 1) & 1);
+        ptx::mbar_wait(&v_full[st], ph);
         for (int t = 0; t < n_qt; ++t) {
-          ptx::mbar_wait(&p_full[t], j & 1);     // P_t(j) in smem; O_t rescaled if the running max moved
+          ptx::mbar_wait(&p_full[t], j & 1);     // P_t(j) in TMEM; O_t rescaled if the running max moved
           ptx::tc_fence_after();
-          issue_pv(t, j);
+          issue_pv(t, st, j > 0 ? 1u : 0u);
         }
-        ptx::tc_commit(&v_empty[j & 1]);
+        ptx::tc_commit(&v_empty[st]);
+        st = nst;
+        ph = nph;
       }
     }
   } else {
@@ -202,10 +204,9 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, uint16_t*
       const int r = q * 32 + lane;              // row inside the Q tile == TMEM lane
       const int qrow = q_base + t * BQ + r;     // token index of this query
       const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
-      const uint32_t s_tmem = tmem_base + lane_off + t * BKV;
-      const uint32_t o_tmem = tmem_base + lane_off + 2 * BKV + t * HD;
-      uint8_t* p_tile = smem + OFF_P + t * 2 * P_BYTES + r * 128;
-      const int rx = r & 7;
+      const uint32_t s_tmem = tmem_base + lane_off + TM_S + t * BKV;
+      const uint32_t o_tmem = tmem_base + lane_off + TM_O + t * HD;
+      const uint32_t p_tmem = tmem_base + lane_off + TM_P + t * (BKV / 2);
 
       float m_used = -1e30f;   // the maximum the exponentials are taken against (log2 domain, scaled)
       float l = 0.f;           // running row sum of P
@@ -252,15 +253,18 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, uint16_t*
         const float mx = max3(max3(mxp[0], mxp[1], mxp[2]), max3(mxp[3], mxp[4], mxp[5]), fmaxf(mxp[6], mxp[7]));
         const float m_tile = mx * scale_log2;
 
+        // ---- P_t (TMEM) and O_t are still being read / accumulated by the P V product of the previous tile
+        if (j > 0) {
+          ptx::mbar_wait(&o_full[t], (j - 1) & 1);
+          ptx::tc_fence_after();
+        }
+
         // ---- lazy rescale: only when the true maximum ran away from the one in use by more than 2^8
         const bool need = m_tile > m_used + RESCALE_THRESHOLD;
         if (__any_sync(0xffffffffu, need)) {
           const float m_new = need ? m_tile : m_used;
           const float alpha = ex2_approx(m_used - m_new);   // 1 for rows that keep their maximum
           if (j > 0) {
-            // O_t must be quiescent: wait for the P V product of the previous tile
-            ptx::mbar_wait(&o_full[t * 2 + ((j - 1) & 1)], ((j - 1) >> 1) & 1);
-            ptx::tc_fence_after();
 #pragma unroll
             for (int c = 0; c < HD / 16; ++c) {
               uint32_t v[16];
@@ -270,51 +274,36 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, uint16_t*
               for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
               ptx::tmem_st_32x32b_x16(o_tmem + c * 16, v);
             }
-            ptx::tmem_st_wait();
           }
           l *= alpha;
           m_used = m_new;
         }
 
-        // ---- the P buffer of parity j&1 was last read by the P V product of tile j-2
-        if (j >= 2) {
-          ptx::mbar_wait(&o_full[t * 2 + (j & 1)], ((j >> 1) - 1) & 1);
-        }
-
-        // ---- P = exp2(S*scale - m_used) -> 16 bit -> swizzled K-major smem tile; row sum in fp32
-        uint8_t* p_row = p_tile + (j & 1) * P_BYTES;
+        // ---- P = exp2(S*scale - m_used) -> packed 16-bit pairs -> tensor memory; row sum in fp32
         float rs[4] = {0.f, 0.f, 0.f, 0.f};   // independent partial sums (no 128-long FADD chain)
 #pragma unroll
-        for (int c = 0; c < BKV / 32; ++c) {
-          uint8_t* chunk = p_row + (c >> 1) * (BQ * 128);
+        for (int c = 0; c < 2; ++c) {          // 64 P values -> 32 packed columns per store
+          uint32_t w[32];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            float p[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              p[i] = ex2_approx(fmaf(__uint_as_float(s[c * 32 + u * 8 + i]), scale_log2, -m_used));
-              rs[i & 3] += p[i];
-            }
-            uint4 w;
-            w.x = ptx::pack16<BF16>(p[0], p[1]);
-            w.y = ptx::pack16<BF16>(p[2], p[3]);
-            w.z = ptx::pack16<BF16>(p[4], p[5]);
-            w.w = ptx::pack16<BF16>(p[6], p[7]);
-            const int unit = ((c & 1) * 4 + u) ^ rx;
-            *reinterpret_cast<uint4*>(chunk + unit * 16) = w;
+          for (int i = 0; i < 32; ++i) {
+            const float p0 = ex2_approx(fmaf(__uint_as_float(s[c * 64 + 2 * i]), scale_log2, -m_used));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(s[c * 64 + 2 * i + 1]), scale_log2, -m_used));
+            rs[(2 * i) & 3] += p0;
+            rs[(2 * i + 1) & 3] += p1;
+            w[i] = ptx::pack16<BF16>(p0, p1);
           }
+          ptx::tmem_st_32x32b_x32(p_tmem + c * 32, w);
         }
         l += (rs[0] + rs[1]) + (rs[2] + rs[3]);
 
+        ptx::tmem_st_wait();
         ptx::tc_fence_before();
-        ptx::fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&p_full[t]);
       }
 
       // ---- all P V accumulated: normalise and store
-      const int jl = n_kv_tiles - 1;
-      ptx::mbar_wait(&o_full[t * 2 + (jl & 1)], (jl >> 1) & 1);
+      ptx::mbar_wait(&o_full[t], (n_kv_tiles - 1) & 1);
       ptx::tc_fence_after();
       const float inv_l = 1.0f / l;
       uint16_t* dst_row = out + (static_cast<size_t>(b) * n_tok + qrow) * D + h * HD;
