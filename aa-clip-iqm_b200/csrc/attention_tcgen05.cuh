@@ -208,7 +208,6 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, uint16_t*
       const uint32_t o_tmem = tmem_base + lane_off + TM_O + t * HD;
       const uint32_t p_tmem = tmem_base + lane_off + TM_P + t * (BKV / 2);
 
-      const bool pingpong = (n_qt == 2);
       float m_used = -1e30f;   // the maximum the exponentials are taken against (log2 domain, scaled)
       float l = 0.f;           // running row sum of P
 
@@ -280,14 +279,6 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, uint16_t*
           m_used = m_new;
         }
 
-        // ---- MUFU hand-off between the two softmax warpgroups: the exponential phases of tile 0 and tile 1
-        // strictly alternate (named barriers 1/2), so one tile's S load / row max / waits always run under the
-        // other tile's exponentials instead of both idling the MUFU at the same time.
-        if (pingpong) {
-          if (t == 0) { if (j > 0) asm volatile("bar.sync 1, 256;" ::: "memory"); }
-          else asm volatile("bar.sync 2, 256;" ::: "memory");
-        }
-
         // ---- P = exp2(S*scale - m_used) -> packed 16-bit pairs -> tensor memory; row sum in fp32
         float rs[4] = {0.f, 0.f, 0.f, 0.f};   // independent partial sums (no 128-long FADD chain)
 #pragma unroll
@@ -304,10 +295,6 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, uint16_t*
           ptx::tmem_st_32x32b_x32(p_tmem + c * 32, w);
         }
         l += (rs[0] + rs[1]) + (rs[2] + rs[3]);
-        if (pingpong) {
-          if (t == 0) asm volatile("bar.arrive 2, 256;" ::: "memory");
-          else if (j + 1 < n_kv_tiles) asm volatile("bar.arrive 1, 256;" ::: "memory");
-        }
 
         ptx::tmem_st_wait();
         ptx::tc_fence_before();
