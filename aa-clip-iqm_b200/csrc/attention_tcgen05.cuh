@@ -9,8 +9,11 @@
 //
 // One CTA = (image b, head h, 256 query rows) = two 128-row Q tiles that share every K/V tile:
 //   warp 8      : TMA producer (Q once; K_j and V_j through separate 3-deep rings)
-//   warp 9      : tcgen05.mma issuer (one lane) + TMEM owner   (warps 10, 11 idle: they complete the third
-//                 warpgroup so that setmaxnreg can hand its registers to the softmax warpgroups)
+//   warp 9 / 10 : tcgen05.mma issuer (one lane each) for Q tile 0 / 1; warp 9 also owns the TMEM allocation.
+//                 One issuer per Q tile keeps the two softmax pipelines independent: with a single in-order
+//                 issuer a late s_free of one tile delayed the other tile's P V product (ncu: 18 % of the softmax
+//                 warps' samples sat on o_full). Warp 11 is idle: it completes the third warpgroup so that
+//                 setmaxnreg can hand its registers to the softmax warpgroups.
 //   warps 0..3  : softmax for Q tile 0 (thread = one query row; TMEM lane quarter = warp % 4)
 //   warps 4..7  : same for Q tile 1
 // TMEM (512 cols): S_t [128x128] fp32 at t*128 | O_t [128x64] fp32 at 256+t*64 | P_t [128x128] 16-bit at 384+t*64.
@@ -46,6 +49,10 @@ constexpr int OFF_V = OFF_K + KV_STAGES * TILE_BYTES;
 constexpr int OFF_BAR = OFF_V + KV_STAGES * TILE_BYTES;
 constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
 constexpr float RESCALE_THRESHOLD = 8.0f;         // log2 units: P never exceeds 2^8
+#ifndef AACLIP_ATTN_STAGGER
+#define AACLIP_ATTN_STAGGER 1
+#endif
+constexpr bool STAGGER = AACLIP_ATTN_STAGGER != 0;
 }  // namespace attn_cfg
 
 __device__ __forceinline__ float max3(float a, float b, float c) {
@@ -75,7 +82,8 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, uint16_t*
   uint64_t* s_free = s_full + QT;                 // [QT] softmax -> MMA : S_t(j) is in registers
   uint64_t* p_full = s_free + QT;                 // [QT] softmax -> MMA : P_t(j) in TMEM, O_t rescaled if needed
   uint64_t* o_full = p_full + QT;                 // [QT] MMA -> softmax : O_t += P_t(j) V_j complete
-  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(o_full + QT);
+  uint64_t* stagger = o_full + QT;                // softmax WG0 -> WG1, once: start half an exponential phase later
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(stagger + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -89,9 +97,9 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, uint16_t*
     ptx::mbar_init(q_full, 1);
     for (int s = 0; s < KV_STAGES; ++s) {
       ptx::mbar_init(&k_full[s], 1);
-      ptx::mbar_init(&k_empty[s], 1);
+      ptx::mbar_init(&k_empty[s], 2);   // one tcgen05.commit per MMA issuer (twice from issuer 0 if n_qt == 1)
       ptx::mbar_init(&v_full[s], 1);
-      ptx::mbar_init(&v_empty[s], 1);
+      ptx::mbar_init(&v_empty[s], 2);
     }
     for (int t = 0; t < QT; ++t) {
       ptx::mbar_init(&s_full[t], 1);
@@ -99,6 +107,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, uint16_t*
       ptx::mbar_init(&p_full[t], 4);
       ptx::mbar_init(&o_full[t], 1);
     }
+    ptx::mbar_init(stagger, 4);
     ptx::fence_mbar_init();
   }
   if (warp == 9) {
@@ -112,7 +121,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, uint16_t*
 
   // The softmax warpgroups need a whole S row in registers: warpgroup 2 (TMA, MMA, 2 idle warps) hands its
   // registers over with setmaxnreg (issued inside each role's branch so ptxas allocates per role).
-  if (warp >= 10) {
+  if (warp == 11) {
     ptx::reg_dec<40>();
   } else if (warp == 8) {
     ptx::reg_dec<40>();
@@ -133,25 +142,29 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, uint16_t*
         if (++st == KV_STAGES) { st = 0; ph ^= 1; }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == 9 || warp == 10) {
     ptx::reg_dec<40>();
-    // ===================== MMA issuer (single thread) =====================
-    if (lane == 0) {
+    // ===================== MMA issuers (one thread per Q tile) =====================
+    const int t = warp - 9;
+    if (lane == 0 && t < n_qt) {
       constexpr uint32_t idesc_s = ptx::make_idesc_16(BQ, BKV, 0, BF16);   // S = Q K^T : both operands K-major
       constexpr uint32_t idesc_pv = ptx::make_idesc_16(BQ, HD, 1, BF16);   // O += P V  : V is MN-major
-      const uint32_t q_addr = ptx::smem_u32(smem + OFF_Q);
+      const uint32_t q_addr = ptx::smem_u32(smem + OFF_Q) + t * TILE_BYTES;
       const uint32_t k_addr = ptx::smem_u32(smem + OFF_K);
       const uint32_t v_addr = ptx::smem_u32(smem + OFF_V);
+      const bool alone = (n_qt == 1);   // then this thread supplies both arrivals of k_empty / v_empty
 
-      auto issue_s = [&](int t, int stage) {
-        const uint64_t a = ptx::make_sw128_desc(q_addr + t * TILE_BYTES);
+      auto issue_s = [&](int stage) {
+        const uint64_t a = ptx::make_sw128_desc(q_addr);
         const uint64_t bd = ptx::make_sw128_desc(k_addr + stage * TILE_BYTES);
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k)
           ptx::tc_mma_f16(tmem_base + TM_S + t * BKV, a + 2 * k, bd + 2 * k, idesc_s, k != 0 ? 1u : 0u);
         ptx::tc_commit(&s_full[t]);
+        ptx::tc_commit(&k_empty[stage]);
+        if (alone) ptx::tc_commit(&k_empty[stage]);
       };
-      auto issue_pv = [&](int t, int stage, uint32_t accumulate) {
+      auto issue_pv = [&](int stage, uint32_t accumulate) {
         const uint32_t va = v_addr + stage * TILE_BYTES;
 #pragma unroll
         for (int k = 0; k < BKV / 16; ++k) {
@@ -161,13 +174,14 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, uint16_t*
                              (accumulate | k) != 0 ? 1u : 0u);
         }
         ptx::tc_commit(&o_full[t]);
+        ptx::tc_commit(&v_empty[stage]);
+        if (alone) ptx::tc_commit(&v_empty[stage]);
       };
 
       ptx::mbar_wait(q_full, 0);
       ptx::mbar_wait(&k_full[0], 0);
       ptx::tc_fence_after();
-      for (int t = 0; t < n_qt; ++t) issue_s(t, 0);
-      ptx::tc_commit(&k_empty[0]);
+      issue_s(0);
 
       int st = 0;             // ring slot of K_j / V_j
       uint32_t ph = 0;
@@ -177,20 +191,14 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, uint16_t*
         if (nst == KV_STAGES) { nst = 0; nph ^= 1; }
         if (j + 1 < n_kv_tiles) {
           ptx::mbar_wait(&k_full[nst], nph);
-          for (int t = 0; t < n_qt; ++t) {
-            ptx::mbar_wait(&s_free[t], j & 1);   // S_t(j) has been copied to registers
-            ptx::tc_fence_after();
-            issue_s(t, nst);
-          }
-          ptx::tc_commit(&k_empty[nst]);
+          ptx::mbar_wait(&s_free[t], j & 1);     // S_t(j) has been copied to registers
+          ptx::tc_fence_after();
+          issue_s(nst);                          // runs under this tile's exponentials
         }
         ptx::mbar_wait(&v_full[st], ph);
-        for (int t = 0; t < n_qt; ++t) {
-          ptx::mbar_wait(&p_full[t], j & 1);     // P_t(j) in TMEM; O_t rescaled if the running max moved
-          ptx::tc_fence_after();
-          issue_pv(t, st, j > 0 ? 1u : 0u);
-        }
-        ptx::tc_commit(&v_empty[st]);
+        ptx::mbar_wait(&p_full[t], j & 1);       // P_t(j) in TMEM; O_t rescaled if the running max moved
+        ptx::tc_fence_after();
+        issue_pv(st, j > 0 ? 1u : 0u);
         st = nst;
         ph = nph;
       }
@@ -210,6 +218,11 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, uint16_t*
 
       float m_used = -1e30f;   // the maximum the exponentials are taken against (log2 domain, scaled)
       float l = 0.f;           // running row sum of P
+
+      // Two warps share each SM sub-partition's MUFU (4 ex2/clk): if both Q tiles run in lock-step, the MUFU idles
+      // while both are in their load/max/wait phases and is oversubscribed while both exponentiate. Q tile 1 starts
+      // half an exponential phase late, so one tile's exponentials cover the other's non-MUFU phases.
+      if (STAGGER && t == 1) ptx::mbar_wait(stagger, 0);
 
       for (int j = 0; j < n_kv_tiles; ++j) {
         ptx::mbar_wait(&s_full[t], j & 1);
@@ -293,6 +306,10 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, uint16_t*
             w[i] = ptx::pack16<BF16>(p0, p1);
           }
           ptx::tmem_st_32x32b_x32(p_tmem + c * 32, w);
+          if (STAGGER && t == 0 && j == 0 && c == 0) {
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(stagger);
+          }
         }
         l += (rs[0] + rs[1]) + (rs[2] + rs[3]);
 
