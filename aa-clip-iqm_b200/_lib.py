@@ -15,7 +15,8 @@ from pathlib import Path
 PKG_DIR = Path(__file__).resolve().parent
 REPO_ROOT = PKG_DIR.parent
 CSRC = PKG_DIR / "csrc"
-LIB_PATH = PKG_DIR / "libaaclip_b200.so"
+# AACLIP_LIB_PATH: developer knob for kernel-variant sweeps (tools/); the product default is the in-tree library
+LIB_PATH = Path(os.environ.get("AACLIP_LIB_PATH") or (PKG_DIR / "libaaclip_b200.so"))
 HEADER = REPO_ROOT / "include" / "aaclip.h"
 
 NVCC_FLAGS = [
@@ -66,6 +67,25 @@ class AaclipCfg(ctypes.Structure):
     ]
 
 
+class AaclipTextCfg(ctypes.Structure):
+    """Mirror of ``struct AaclipTextCfg`` (include/aaclip.h)."""
+
+    _fields_ = [
+        ("context", ctypes.c_int32),
+        ("vocab", ctypes.c_int32),
+        ("width", ctypes.c_int32),
+        ("heads", ctypes.c_int32),
+        ("layers", ctypes.c_int32),
+        ("mlp_dim", ctypes.c_int32),
+        ("embed_dim", ctypes.c_int32),
+        ("adapt_until", ctypes.c_int32),
+        ("act", ctypes.c_int32),
+        ("adapt_weight", ctypes.c_float),
+        ("max_sentences", ctypes.c_int32),
+        ("operand_dtype", ctypes.c_int32),
+    ]
+
+
 def _sources():
     return sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("*.cuh")) + [HEADER]
 
@@ -84,7 +104,8 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: cannot build libaaclip_b200.so")
-    cmd = [nvcc, *NVCC_FLAGS, "-o", str(LIB_PATH), str(CSRC / "aaclip_api.cu")]
+    extra = os.environ.get("AACLIP_NVCC_EXTRA", "").split()   # e.g. -DAACLIP_ATTN_POLY_EVERY=0 for a variant sweep
+    cmd = [nvcc, *NVCC_FLAGS, *extra, "-o", str(LIB_PATH), str(CSRC / "aaclip_api.cu")]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
@@ -130,6 +151,20 @@ def _declare(lib):
     lib.aaclip_profile_enable.argtypes = [vp, i32]
     lib.aaclip_profile_read.restype = i32
     lib.aaclip_profile_read.argtypes = [vp, ctypes.POINTER(f32), ctypes.POINTER(i32), ctypes.POINTER(ctypes.c_double)]
+    lib.aaclip_text_create.restype = i32
+    lib.aaclip_text_create.argtypes = [ctypes.POINTER(AaclipTextCfg), _c_void_pp]
+    lib.aaclip_text_destroy.restype = None
+    lib.aaclip_text_destroy.argtypes = [vp]
+    lib.aaclip_text_set_weight.restype = i32
+    lib.aaclip_text_set_weight.argtypes = [vp, ctypes.c_char_p, vp, ctypes.POINTER(i64), i32, vp]
+    lib.aaclip_text_missing_weights.restype = i32
+    lib.aaclip_text_missing_weights.argtypes = [vp]
+    lib.aaclip_text_workspace_bytes.restype = sz
+    lib.aaclip_text_workspace_bytes.argtypes = [vp, i32]
+    lib.aaclip_encode_text.restype = i32
+    lib.aaclip_encode_text.argtypes = [vp, vp, i32, vp, sz, vp, vp]
+    lib.aaclip_text_anchors.restype = i32
+    lib.aaclip_text_anchors.argtypes = [vp, vp, i32, i32, vp, vp]
     lib.aaclip_gemm16.restype = i32
     lib.aaclip_gemm16.argtypes = [i32, vp, vp, i32, i32, i32, i32, vp, vp, vp, i32, vp]
     lib.aaclip_attention.restype = i32
@@ -145,6 +180,8 @@ EXPORTED_SYMBOLS = [
     "aaclip_missing_weights", "aaclip_workspace_bytes", "aaclip_forward", "aaclip_score_workspace_bytes",
     "aaclip_score_maps", "aaclip_last_launch_count", "aaclip_profile_enable", "aaclip_profile_read", "aaclip_gemm16", "aaclip_attention", "aaclip_layernorm",
     "aaclip_pack16",
+    "aaclip_text_create", "aaclip_text_destroy", "aaclip_text_set_weight", "aaclip_text_missing_weights",
+    "aaclip_text_workspace_bytes", "aaclip_encode_text", "aaclip_text_anchors",
 ]
 
 

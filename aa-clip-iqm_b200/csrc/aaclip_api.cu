@@ -720,6 +720,254 @@ int aaclip_score_maps(const float* const* seg, int32_t n_levels, const float* te
   return AACLIP_OK;
 }
 
+}  // extern "C"
+
+// =========================================================================================== text tower
+struct AaclipTextHandle {
+  AaclipTextCfg cfg;
+  bool bf16 = false;
+  uint8_t* arena = nullptr;
+  size_t arena_bytes = 0;
+  float *tok_emb, *pos, *lnf_g, *lnf_b;
+  std::vector<BlockW> blk;
+  std::vector<uint16_t*> w_adapter;  // [W,W] each (SimpleAdapter)
+  uint16_t* w_proj;                  // [E,W] final SimpleProj
+  std::vector<std::string> missing;
+};
+
+struct TextWsPlan { size_t x, xn, qkv, att, hid, abuf, eot, eot16, total; };
+static TextWsPlan plan_text_ws(const AaclipTextHandle* h, int n) {
+  const size_t W = h->cfg.width, F = h->cfg.mlp_dim;
+  const size_t M = (size_t)n * h->cfg.context;
+  ArenaPlan p;
+  TextWsPlan w;
+  w.x = p.take<float>(M * W);
+  w.xn = p.take<uint16_t>(M * W);
+  w.qkv = p.take<uint16_t>(M * 3 * W);
+  w.att = p.take<uint16_t>(M * W);
+  w.hid = p.take<uint16_t>(M * F);
+  w.abuf = p.take<float>(M * W);
+  w.eot = p.take<float>((size_t)n * W);
+  w.eot16 = p.take<uint16_t>((size_t)n * W);
+  w.total = p.off;
+  return w;
+}
+
+extern "C" {
+
+int aaclip_text_create(const AaclipTextCfg* cfg, AaclipTextHandle** out) {
+  if (cfg == nullptr || out == nullptr) return fail(AACLIP_EINVAL, "aaclip_text_create: null argument");
+  *out = nullptr;
+  if (int rc = ensure_device()) return rc;
+  const AaclipTextCfg& c = *cfg;
+  if (c.width != 768 && c.width != 1024) return fail(AACLIP_EINVAL, "text width %d unsupported (768 or 1024)", c.width);
+  if (c.heads * 64 != c.width) return fail(AACLIP_EINVAL, "text head dim must be 64 (width %d, heads %d)", c.width, c.heads);
+  if (c.mlp_dim % 256 != 0 || c.embed_dim % 256 != 0) return fail(AACLIP_EINVAL, "text mlp_dim/embed_dim must be multiples of 256");
+  if (c.context <= 0 || c.vocab <= 0 || c.layers <= 0 || c.adapt_until < 0 || c.adapt_until > c.layers || c.max_sentences <= 0)
+    return fail(AACLIP_EINVAL, "bad text configuration");
+  if (c.operand_dtype != AACLIP_DT_F16 && c.operand_dtype != AACLIP_DT_BF16) return fail(AACLIP_EINVAL, "operand_dtype must be AACLIP_DT_F16 or AACLIP_DT_BF16");
+  AaclipTextHandle* h = new AaclipTextHandle();
+  h->cfg = c;
+  h->bf16 = (c.operand_dtype == AACLIP_DT_BF16);
+  const size_t W = c.width, F = c.mlp_dim, E = c.embed_dim;
+  ArenaPlan plan;
+  const size_t o_tok = plan.take<float>((size_t)c.vocab * W), o_pos = plan.take<float>((size_t)c.context * W);
+  const size_t o_lg = plan.take<float>(W), o_lb = plan.take<float>(W);
+  struct BO { size_t ln1g, ln1b, ln2g, ln2b, bqkv, bout, bfc, bproj, wqkv, wout, wfc, wproj; };
+  std::vector<BO> bo(c.layers);
+  for (int i = 0; i < c.layers; ++i) {
+    bo[i].ln1g = plan.take<float>(W); bo[i].ln1b = plan.take<float>(W);
+    bo[i].ln2g = plan.take<float>(W); bo[i].ln2b = plan.take<float>(W);
+    bo[i].bqkv = plan.take<float>(3 * W); bo[i].bout = plan.take<float>(W);
+    bo[i].bfc = plan.take<float>(F); bo[i].bproj = plan.take<float>(W);
+    bo[i].wqkv = plan.take<uint16_t>(3 * W * W); bo[i].wout = plan.take<uint16_t>(W * W);
+    bo[i].wfc = plan.take<uint16_t>(F * W); bo[i].wproj = plan.take<uint16_t>(W * F);
+  }
+  std::vector<size_t> o_ad(c.adapt_until);
+  for (int i = 0; i < c.adapt_until; ++i) o_ad[i] = plan.take<uint16_t>(W * W);
+  const size_t o_proj = plan.take<uint16_t>(E * W);
+  h->arena_bytes = plan.off;
+  cudaError_t e = cudaMalloc(&h->arena, h->arena_bytes);
+  if (e == cudaSuccess) e = cudaMemset(h->arena, 0, h->arena_bytes);
+  if (e != cudaSuccess) {
+    if (h->arena) cudaFree(h->arena);
+    delete h;
+    return fail(AACLIP_ECUDA, "text weight arena (%zu bytes): %s", plan.off, cudaGetErrorString(e));
+  }
+  uint8_t* a = h->arena;
+  h->tok_emb = (float*)(a + o_tok); h->pos = (float*)(a + o_pos);
+  h->lnf_g = (float*)(a + o_lg); h->lnf_b = (float*)(a + o_lb);
+  h->blk.resize(c.layers);
+  for (int i = 0; i < c.layers; ++i) {
+    BlockW& b = h->blk[i];
+    b.ln1_g = (float*)(a + bo[i].ln1g); b.ln1_b = (float*)(a + bo[i].ln1b);
+    b.ln2_g = (float*)(a + bo[i].ln2g); b.ln2_b = (float*)(a + bo[i].ln2b);
+    b.b_qkv = (float*)(a + bo[i].bqkv); b.b_out = (float*)(a + bo[i].bout);
+    b.b_fc = (float*)(a + bo[i].bfc); b.b_proj = (float*)(a + bo[i].bproj);
+    b.w_qkv = (uint16_t*)(a + bo[i].wqkv); b.w_out = (uint16_t*)(a + bo[i].wout);
+    b.w_fc = (uint16_t*)(a + bo[i].wfc); b.w_proj = (uint16_t*)(a + bo[i].wproj);
+  }
+  for (int i = 0; i < c.adapt_until; ++i) h->w_adapter.push_back((uint16_t*)(a + o_ad[i]));
+  h->w_proj = (uint16_t*)(a + o_proj);
+  auto need = [&](const std::string& k) { h->missing.push_back(k); };
+  need("token_embedding.weight"); need("positional_embedding"); need("ln_final.weight"); need("ln_final.bias");
+  for (int i = 0; i < c.layers; ++i) {
+    const std::string p = "blk." + std::to_string(i) + ".";
+    for (const char* s : {"ln_1.weight", "ln_1.bias", "ln_2.weight", "ln_2.bias", "attn.in_proj_weight",
+                          "attn.in_proj_bias", "attn.out_proj.weight", "attn.out_proj.bias", "mlp.c_fc.weight",
+                          "mlp.c_fc.bias", "mlp.c_proj.weight", "mlp.c_proj.bias"})
+      need(p + s);
+  }
+  for (int i = 0; i <= c.adapt_until; ++i) need("text_adapter." + std::to_string(i));
+  *out = h;
+  return AACLIP_OK;
+}
+
+void aaclip_text_destroy(AaclipTextHandle* h) {
+  if (h == nullptr) return;
+  if (h->arena) cudaFree(h->arena);
+  delete h;
+}
+
+int aaclip_text_missing_weights(AaclipTextHandle* h) { return h ? static_cast<int>(h->missing.size()) : -1; }
+
+int aaclip_text_set_weight(AaclipTextHandle* h, const char* name, const float* data, const int64_t* shape,
+                           int32_t ndim, void* stream) {
+  if (!h || !name || !data || !shape || ndim <= 0) return fail(AACLIP_EINVAL, "aaclip_text_set_weight: null/empty argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const AaclipTextCfg& c = h->cfg;
+  const int64_t W = c.width, F = c.mlp_dim, E = c.embed_dim;
+  const int64_t n = numel(shape, ndim);
+  std::string k(name);
+  if (k.rfind("clipmodel.", 0) == 0) k = k.substr(strlen("clipmodel."));
+  auto loaded = [&](const std::string& key) {
+    for (size_t i = 0; i < h->missing.size(); ++i)
+      if (h->missing[i] == key) { h->missing.erase(h->missing.begin() + i); return; }
+  };
+  auto copy_f32 = [&](float* dst, int64_t expect, const std::string& key) -> int {
+    if (n != expect) return fail(AACLIP_EINVAL, "%s: expected %lld elements, got %lld", name, (long long)expect, (long long)n);
+    CUDA_TRY(cudaMemcpyAsync(dst, data, expect * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    loaded(key);
+    return AACLIP_OK;
+  };
+  auto pack = [&](uint16_t* dst, int64_t R, int64_t C, const std::string& key) -> int {
+    if (n != R * C) return fail(AACLIP_EINVAL, "%s: expected %lld x %lld elements, got %lld", name, (long long)R, (long long)C, (long long)n);
+    if (int rc = launch_pack(h->bf16, data, dst, R, C, C, st)) return rc;
+    loaded(key);
+    return AACLIP_OK;
+  };
+  if (k == "token_embedding.weight") return copy_f32(h->tok_emb, (int64_t)c.vocab * W, k);
+  if (k == "positional_embedding") return copy_f32(h->pos, (int64_t)c.context * W, k);
+  if (k == "ln_final.weight") return copy_f32(h->lnf_g, W, k);
+  if (k == "ln_final.bias") return copy_f32(h->lnf_b, W, k);
+  int idx = -1;
+  char tail[96];
+  if (sscanf(k.c_str(), "transformer.resblocks.%d.%95s", &idx, tail) == 2) {
+    if (idx < 0 || idx >= c.layers) return fail(AACLIP_EINVAL, "%s: block index out of range", name);
+    BlockW& b = h->blk[idx];
+    const std::string t(tail), key = "blk." + std::to_string(idx) + "." + t;
+    if (t == "ln_1.weight") return copy_f32(b.ln1_g, W, key);
+    if (t == "ln_1.bias") return copy_f32(b.ln1_b, W, key);
+    if (t == "ln_2.weight") return copy_f32(b.ln2_g, W, key);
+    if (t == "ln_2.bias") return copy_f32(b.ln2_b, W, key);
+    if (t == "attn.in_proj_bias") return copy_f32(b.b_qkv, 3 * W, key);
+    if (t == "attn.out_proj.bias") return copy_f32(b.b_out, W, key);
+    if (t == "mlp.c_fc.bias") return copy_f32(b.b_fc, F, key);
+    if (t == "mlp.c_proj.bias") return copy_f32(b.b_proj, W, key);
+    if (t == "attn.in_proj_weight") return pack(b.w_qkv, 3 * W, W, key);
+    if (t == "attn.out_proj.weight") return pack(b.w_out, W, W, key);
+    if (t == "mlp.c_fc.weight") return pack(b.w_fc, F, W, key);
+    if (t == "mlp.c_proj.weight") return pack(b.w_proj, W, F, key);
+    return fail(AACLIP_EINVAL, "%s: unknown block tensor", name);
+  }
+  if (sscanf(k.c_str(), "text_adapter.%d.%95s", &idx, tail) == 2) {
+    if (strcmp(tail, "fc.0.weight") != 0) return fail(AACLIP_EINVAL, "%s: unknown tensor", name);
+    if (idx < 0 || idx > c.adapt_until) return fail(AACLIP_EINVAL, "%s: text_adapter index out of range", name);
+    if (idx < c.adapt_until) return pack(h->w_adapter[idx], W, W, "text_adapter." + std::to_string(idx));
+    return pack(h->w_proj, E, W, "text_adapter." + std::to_string(idx));
+  }
+  return fail(AACLIP_EINVAL, "%s: unknown tensor name", name);
+}
+
+size_t aaclip_text_workspace_bytes(AaclipTextHandle* h, int32_t n) {
+  if (!h || n <= 0) return 0;
+  return plan_text_ws(h, n).total;
+}
+
+int aaclip_encode_text(AaclipTextHandle* h, const int32_t* tokens, int32_t n, void* workspace, size_t workspace_bytes,
+                       float* out, void* stream) {
+  if (!h || !tokens || !workspace || !out) return fail(AACLIP_EINVAL, "aaclip_encode_text: null argument");
+  if (n <= 0 || n > h->cfg.max_sentences) return fail(AACLIP_EINVAL, "aaclip_encode_text: %d sentences outside 1..%d", n, h->cfg.max_sentences);
+  if (!h->missing.empty())
+    return fail(AACLIP_ESTATE, "aaclip_encode_text: %zu weight tensors not set (first: %s)", h->missing.size(), h->missing[0].c_str());
+  const TextWsPlan ws = plan_text_ws(h, n);
+  if (workspace_bytes < ws.total) return fail(AACLIP_EINVAL, "aaclip_encode_text: workspace %zu < required %zu", workspace_bytes, ws.total);
+  if (reinterpret_cast<uintptr_t>(workspace) & 255) return fail(AACLIP_EINVAL, "aaclip_encode_text: workspace must be 256-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const AaclipTextCfg& c = h->cfg;
+  const int W = c.width, F = c.mlp_dim, E = c.embed_dim, T = c.context;
+  const int M = n * T;
+  const bool bf = h->bf16;
+  uint8_t* wsb = static_cast<uint8_t*>(workspace);
+  float* x = (float*)(wsb + ws.x);
+  uint16_t* xn = (uint16_t*)(wsb + ws.xn);
+  uint16_t* qkv = (uint16_t*)(wsb + ws.qkv);
+  uint16_t* att = (uint16_t*)(wsb + ws.att);
+  uint16_t* hid = (uint16_t*)(wsb + ws.hid);
+  float* abuf = (float*)(wsb + ws.abuf);
+  float* eot = (float*)(wsb + ws.eot);
+  uint16_t* eot16 = (uint16_t*)(wsb + ws.eot16);
+  int rc;
+
+  // token + positional embedding (model/adapter.py:277-281)
+  text_embed_kernel<<<M, 192, 0, st>>>(tokens, h->tok_emb, h->pos, x, T, W, c.vocab);
+  LAUNCH_CHECK("text_embed_kernel");
+  // 12 causal residual attention blocks + adapters (model/adapter.py:284-295)
+  for (int i = 0; i < c.layers; ++i) {
+    const BlockW& b = h->blk[i];
+    if ((rc = launch_layernorm(bf, x, b.ln1_g, b.ln1_b, xn, nullptr, M, W, 0, true, st))) return rc;
+    { GemmEpi e; e.bias = b.b_qkv; e.out_16 = qkv; e.ldo = 3 * W;
+      if ((rc = launch_gemm(EPI_BIAS_BF16, bf, xn, b.w_qkv, M, 3 * W, W, e, st))) return rc; }
+    if ((rc = launch_attention(bf, qkv, att, n, T, W, /*causal=*/1, st))) return rc;
+    { GemmEpi e; e.bias = b.b_out; e.out_f32 = x; e.ldo = W;
+      if ((rc = launch_gemm(EPI_BIAS_RESID_F32, bf, att, b.w_out, M, W, W, e, st))) return rc; }
+    if ((rc = launch_layernorm(bf, x, b.ln2_g, b.ln2_b, xn, nullptr, M, W, 0, true, st))) return rc;
+    { GemmEpi e; e.bias = b.b_fc; e.out_16 = hid; e.ldo = F;
+      if ((rc = launch_gemm(c.act == AACLIP_ACT_QUICK_GELU ? EPI_BIAS_QGELU_BF16 : EPI_BIAS_GELU_BF16, bf, xn, b.w_fc, M, F, W, e, st))) return rc; }
+    const bool adapt = i < c.adapt_until;
+    { GemmEpi e; e.bias = b.b_proj; e.out_f32 = x; e.ldo = W; e.out_16 = adapt ? xn : nullptr;
+      if ((rc = launch_gemm(EPI_BIAS_RESID_F32, bf, hid, b.w_proj, M, W, F, e, st))) return rc; }
+    if (adapt) {
+      { GemmEpi e; e.out_f32 = abuf; e.ldo = W;
+        if ((rc = launch_gemm(EPI_LEAKY_F32, bf, xn, h->w_adapter[i], M, W, W, e, st))) return rc; }
+      const int grid = (M + 7) / 8;
+      if (W == 1024) adapter_blend_kernel<1024><<<grid, 256, 0, st>>>(x, abuf, M, c.adapt_weight, 1.0f - c.adapt_weight);
+      else adapter_blend_kernel<768><<<grid, 256, 0, st>>>(x, abuf, M, c.adapt_weight, 1.0f - c.adapt_weight);
+      LAUNCH_CHECK("adapter_blend_kernel");
+    }
+  }
+  // EOT row -> ln_final -> SimpleProj + LeakyReLU (model/adapter.py:296-298)
+  text_gather_eot_kernel<<<n, 192, 0, st>>>(tokens, x, eot, T, W);
+  LAUNCH_CHECK("text_gather_eot_kernel");
+  if ((rc = launch_layernorm(bf, eot, h->lnf_g, h->lnf_b, eot16, nullptr, n, W, 0, true, st))) return rc;
+  { GemmEpi e; e.out_f32 = out; e.ldo = E;
+    if ((rc = launch_gemm(EPI_LEAKY_F32, bf, eot16, h->w_proj, n, E, W, e, st))) return rc; }
+  return AACLIP_OK;
+}
+
+int aaclip_text_anchors(const float* emb, const int32_t* offsets, int32_t n_groups, int32_t E, float* anchors,
+                        void* stream) {
+  if (!emb || !offsets || !anchors) return fail(AACLIP_EINVAL, "aaclip_text_anchors: null argument");
+  if (n_groups <= 0 || (n_groups & 1) || E <= 0) return fail(AACLIP_EINVAL, "aaclip_text_anchors: n_groups must be a positive even number");
+  text_ensemble_kernel<<<n_groups, 256, (E + 32) * sizeof(float), static_cast<cudaStream_t>(stream)>>>(emb, offsets, anchors, E);
+  LAUNCH_CHECK("text_ensemble_kernel");
+  return AACLIP_OK;
+}
+
+}  // extern "C"
+
+extern "C" {
+
 int aaclip_gemm16(int32_t dtype, const void* A, const void* W, int32_t M, int32_t N, int32_t K, int32_t epi,
                   const float* bias, float* out_f32, void* out_16, int32_t ldo, void* stream) {
   if (!A || !W) return fail(AACLIP_EINVAL, "aaclip_gemm16: null operand");

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <limits.h>
 #include "ptx.cuh"
 
 namespace aaclip {
@@ -313,6 +314,93 @@ __global__ void anomaly_map_kernel(const float* __restrict__ s, float* __restric
       }
     }
   }
+}
+
+}  // namespace aaclip
+
+// =========================================================================================================
+// Text-anchor path (AdaptedCLIP.encode_text, model/adapter.py:273-304; forward_utils.py:138-162)
+namespace aaclip {
+
+// x[s*ctx + t, :] = token_embedding[ids[s,t], :] + positional_embedding[t, :]   (model/adapter.py:277-281)
+// grid = n_sent * ctx rows, block = D/4 threads (float4 each). Out-of-vocabulary ids are clamped.
+__global__ void text_embed_kernel(const int32_t* __restrict__ ids, const float* __restrict__ tok_emb,
+                                  const float* __restrict__ pos, float* __restrict__ x, int ctx, int D, int vocab) {
+  const int row = blockIdx.x;
+  const int t = row % ctx;
+  const int id = min(max(ids[row], 0), vocab - 1);
+  const float4* e = reinterpret_cast<const float4*>(tok_emb + static_cast<size_t>(id) * D);
+  const float4* p = reinterpret_cast<const float4*>(pos + static_cast<size_t>(t) * D);
+  float4* o = reinterpret_cast<float4*>(x + static_cast<size_t>(row) * D);
+  for (int i = threadIdx.x; i < D / 4; i += blockDim.x) {
+    const float4 a = __ldg(e + i), b = __ldg(p + i);
+    o[i] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+  }
+}
+
+// out[s, :] = x[s*ctx + argmax_t ids[s,t], :]  -- the EOT row (highest token id; torch.argmax returns the FIRST
+// maximum), model/adapter.py:298. ln_final is row-wise, so it is applied after this gather on n_sent rows only.
+__global__ void text_gather_eot_kernel(const int32_t* __restrict__ ids, const float* __restrict__ x,
+                                       float* __restrict__ out, int ctx, int D) {
+  const int s = blockIdx.x;
+  __shared__ int s_best;
+  if (threadIdx.x < 32) {
+    int best_v = INT_MIN, best_i = 0;
+    for (int t = threadIdx.x; t < ctx; t += 32) {
+      const int v = ids[s * ctx + t];
+      if (v > best_v) { best_v = v; best_i = t; }     // strided scan keeps the first maximum per lane
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const int ov = __shfl_xor_sync(0xffffffffu, best_v, o), oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+      if (ov > best_v || (ov == best_v && oi < best_i)) { best_v = ov; best_i = oi; }
+    }
+    if (threadIdx.x == 0) s_best = best_i;
+  }
+  __syncthreads();
+  const float4* src = reinterpret_cast<const float4*>(x + (static_cast<size_t>(s) * ctx + s_best) * D);
+  float4* dst = reinterpret_cast<float4*>(out + static_cast<size_t>(s) * D);
+  for (int i = threadIdx.x; i < D / 4; i += blockDim.x) dst[i] = src[i];
+}
+
+// Prompt-ensemble anchors, forward_utils.py:155-161: for group g (rows offsets[g] .. offsets[g+1]-1 of emb):
+//   e_r = emb_r / ||emb_r|| ; m = mean_r e_r ; a = m / ||m|| ; anchors[g / 2, :, g % 2] = a
+// (two consecutive groups = normal / abnormal state of one class -> the [E,2] layout of torch.stack(dim=1)).
+// One CTA per group, fixed summation order.
+__global__ void text_ensemble_kernel(const float* __restrict__ emb, const int32_t* __restrict__ offsets,
+                                     float* __restrict__ anchors, int E) {
+  extern __shared__ float sm[];      // [E] accumulator + [32] reduction scratch
+  float* acc = sm;
+  float* red = sm + E;
+  const int g = blockIdx.x;
+  const int r0 = offsets[g], r1 = offsets[g + 1];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  auto block_sum = [&](float v) -> float {
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    float t = 0.f;
+    for (int w = 0; w < nwarps; ++w) t += red[w];
+    return t;
+  };
+  for (int i = threadIdx.x; i < E; i += blockDim.x) acc[i] = 0.f;
+  for (int r = r0; r < r1; ++r) {
+    const float* row = emb + static_cast<size_t>(r) * E;
+    float ss = 0.f;
+    for (int i = threadIdx.x; i < E; i += blockDim.x) ss += row[i] * row[i];
+    const float inv = 1.0f / sqrtf(block_sum(ss));
+    for (int i = threadIdx.x; i < E; i += blockDim.x) acc[i] += row[i] * inv;
+  }
+  const float cnt = static_cast<float>(r1 - r0);
+  float ss = 0.f;
+  for (int i = threadIdx.x; i < E; i += blockDim.x) {
+    acc[i] /= cnt;
+    ss += acc[i] * acc[i];
+  }
+  const float inv = 1.0f / sqrtf(block_sum(ss));
+  float* out = anchors + static_cast<size_t>(g >> 1) * E * 2 + (g & 1);
+  for (int i = threadIdx.x; i < E; i += blockDim.x) out[2 * i] = acc[i] * inv;
 }
 
 }  // namespace aaclip

@@ -252,3 +252,106 @@ class AaclipEngine:
     @property
     def last_launch_count(self) -> int:
         return self._lib.aaclip_last_launch_count(self._h)
+
+
+# ---------------------------------------------------------------------------------------- the text tower
+DEFAULT_TEXT_CFG = dict(context=77, vocab=49408, width=768, heads=12, layers=12, mlp_dim=3072, embed_dim=768,
+                        adapt_until=3, act=_lib.ACT_GELU_ERF, adapt_weight=0.1, max_sentences=512,
+                        operand_dtype=_lib.DT_F16)
+
+
+class AaclipTextEngine:
+    """Owns one AaclipTextHandle: the adapted CLIP text tower (AdaptedCLIP.encode_text, model/adapter.py:273-304)."""
+
+    def __init__(self, device: torch.device | str = "cuda", **cfg):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("AaclipTextEngine needs a CUDA (sm_100a) device; there is no CPU path")
+        full = dict(DEFAULT_TEXT_CFG)
+        full.update(cfg)
+        self.cfg = full
+        c = _lib.AaclipTextCfg()
+        for k in ("context", "vocab", "width", "heads", "layers", "mlp_dim", "embed_dim", "adapt_until", "act",
+                  "max_sentences", "operand_dtype"):
+            setattr(c, k, int(full[k]))
+        c.adapt_weight = float(full["adapt_weight"])
+        self._lib = _lib.load()
+        self._h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.aaclip_text_create(ctypes.byref(c), ctypes.byref(self._h)), "aaclip_text_create")
+        self._ws: Optional[torch.Tensor] = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.aaclip_text_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_weight(self, name: str, t: torch.Tensor):
+        t = t.detach().to(self.device, torch.float32).contiguous()
+        shape = (ctypes.c_int64 * t.dim())(*t.shape)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.aaclip_text_set_weight(self._h, name.encode(), _ptr(t), shape, t.dim(), _stream()),
+                       f"aaclip_text_set_weight({name})")
+            torch.cuda.current_stream().synchronize()
+
+    TEXT_KEYS = ("clipmodel.token_embedding.", "clipmodel.positional_embedding", "clipmodel.transformer.",
+                 "clipmodel.ln_final.", "text_adapter.")
+
+    def load_state_dict(self, sd: Dict[str, torch.Tensor]) -> int:
+        """Feed every text-path tensor of an AdaptedCLIP state_dict (clipmodel.* text tower + text_adapter.*)."""
+        n = 0
+        for k, v in sd.items():
+            if k.startswith(self.TEXT_KEYS):
+                self.set_weight(k, v)
+                n += 1
+        return n
+
+    @property
+    def missing(self) -> int:
+        return self._lib.aaclip_text_missing_weights(self._h)
+
+    def encode_text(self, tokens: torch.Tensor) -> torch.Tensor:
+        """tokens int [n, context] -> [n, E] fp32 on the device (un-normalised, as the reference returns them)."""
+        if tokens.dim() != 2 or tokens.shape[1] != self.cfg["context"]:
+            raise ValueError(f"tokens must be [n,{self.cfg['context']}], got {tuple(tokens.shape)}")
+        if tokens.numel() and (int(tokens.min()) < 0 or int(tokens.max()) >= self.cfg["vocab"]):
+            raise ValueError(f"token ids must lie in [0,{self.cfg['vocab']})")
+        n = tokens.shape[0]
+        if n == 0:
+            return torch.empty((0, self.cfg["embed_dim"]), dtype=torch.float32, device=self.device)
+        outs = []
+        step = self.cfg["max_sentences"]
+        for i in range(0, n, step):
+            tk = tokens[i:i + step].to(self.device, torch.int32).contiguous()
+            m = tk.shape[0]
+            need = self._lib.aaclip_text_workspace_bytes(self._h, m)
+            if self._ws is None or self._ws.numel() < need:
+                self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+            out = torch.empty((m, self.cfg["embed_dim"]), dtype=torch.float32, device=self.device)
+            with torch.cuda.device(self.device):
+                _lib.check(self._lib.aaclip_encode_text(self._h, _ptr(tk), m, _ptr(self._ws), self._ws.numel(), _ptr(out),
+                                                        _stream()), "aaclip_encode_text")
+            outs.append(out)
+        return outs[0] if len(outs) == 1 else torch.cat(outs)
+
+
+def text_anchors(emb: torch.Tensor, group_sizes: Sequence[int]) -> torch.Tensor:
+    """Prompt ensembling (forward_utils.py:152-161): emb [n,E] fp32, consecutive groups of `group_sizes` rows
+    (normal, abnormal, normal, abnormal, ...) -> anchors [n_classes, E, 2] (aaclip_text_anchors)."""
+    _need_cuda(emb)
+    emb = emb.contiguous().float()
+    if len(group_sizes) == 0 or len(group_sizes) % 2 or min(group_sizes) <= 0 or sum(group_sizes) != emb.shape[0]:
+        raise ValueError("group_sizes must be a non-empty list of positive sizes, two per class, covering emb")
+    off = torch.tensor([0] + list(torch.tensor(list(group_sizes)).cumsum(0)), dtype=torch.int32, device=emb.device)
+    E = emb.shape[1]
+    out = torch.empty((len(group_sizes) // 2, E, 2), dtype=torch.float32, device=emb.device)
+    with torch.cuda.device(emb.device):
+        _lib.check(_lib.load().aaclip_text_anchors(_ptr(emb), _ptr(off), len(group_sizes), E, _ptr(out), _stream()),
+                   "aaclip_text_anchors")
+    return out

@@ -64,6 +64,43 @@ def make_visual_state_dict(seed: int = 0, img_size: int = 518, relu: bool = Fals
     return sd
 
 
+def make_text_state_dict(seed: int = 0, cfg: dict = TEXT_B) -> Dict[str, torch.Tensor]:
+    """fp32 CPU tensors of the adapted text tower, keys relative to AdaptedCLIP (clipmodel.* / text_adapter.*).
+    Scales follow the reference's init (model/transformer.py TextTransformer.init_parameters: token embedding
+    std 0.02, positional 0.01, attn std W^-0.5, proj std (2W*layers)^-0.5... approximated) with non-trivial
+    biases / LayerNorm affines so every term is exercised."""
+    g = torch.Generator(device="cpu")
+    g.manual_seed(1000003 * seed + 29)
+    W, F, L = cfg["width"], cfg["mlp_dim"], cfg["layers"]
+
+    def rn(*shape, std=1.0, mean=0.0):
+        return torch.randn(*shape, generator=g, dtype=torch.float32) * std + mean
+
+    sd: Dict[str, torch.Tensor] = {}
+    p = "clipmodel."
+    sd[p + "token_embedding.weight"] = rn(cfg["vocab"], W, std=0.02)
+    sd[p + "positional_embedding"] = rn(cfg["context"], W, std=0.01)
+    for i in range(L):
+        b = f"{p}transformer.resblocks.{i}."
+        sd[b + "ln_1.weight"] = rn(W, std=0.1, mean=1.0)
+        sd[b + "ln_1.bias"] = rn(W, std=0.05)
+        sd[b + "attn.in_proj_weight"] = rn(3 * W, W, std=W ** -0.5)
+        sd[b + "attn.in_proj_bias"] = rn(3 * W, std=0.02)
+        sd[b + "attn.out_proj.weight"] = rn(W, W, std=(2 * W * L) ** -0.5 * 4)
+        sd[b + "attn.out_proj.bias"] = rn(W, std=0.02)
+        sd[b + "ln_2.weight"] = rn(W, std=0.1, mean=1.0)
+        sd[b + "ln_2.bias"] = rn(W, std=0.05)
+        sd[b + "mlp.c_fc.weight"] = rn(F, W, std=(2 * W) ** -0.5)
+        sd[b + "mlp.c_fc.bias"] = rn(F, std=0.02)
+        sd[b + "mlp.c_proj.weight"] = rn(W, F, std=(2 * W * L) ** -0.5 * 2)
+        sd[b + "mlp.c_proj.bias"] = rn(W, std=0.02)
+    sd[p + "ln_final.weight"] = rn(W, std=0.1, mean=1.0)
+    sd[p + "ln_final.bias"] = rn(W, std=0.05)
+    for i in range(cfg["adapt_until"] + 1):
+        sd[f"text_adapter.{i}.fc.0.weight"] = rn(W, W, std=0.036)
+    return sd
+
+
 def make_text_anchor(seed: int = 0, embed_dim: int = 768, batch: int | None = None) -> torch.Tensor:
     """Unit-norm synthetic text anchors [E,2] (column 0 normal, 1 abnormal) or [B,E,2]."""
     g = torch.Generator(device="cpu")

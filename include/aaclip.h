@@ -148,6 +148,57 @@ int aaclip_last_launch_count(AaclipHandle* h);
 int aaclip_profile_enable(AaclipHandle* h, int32_t enable);
 int aaclip_profile_read(AaclipHandle* h, float* ms, int32_t* launches, double* flops);
 
+/* ---- text anchors (BASELINE config 3) --------------------------------------------------------------------- */
+
+/* Static description of the adapted CLIP text tower (model/model_configs/ViT-L-14-336.json "text_cfg" +
+ * AdaptedCLIP.__init__ text_adapter, model/adapter.py:51-54). */
+typedef struct AaclipTextCfg {
+  int32_t context;       /* 77 */
+  int32_t vocab;         /* 49408 */
+  int32_t width;         /* 768 (head dim must be 64) */
+  int32_t heads;         /* 12 */
+  int32_t layers;        /* 12 */
+  int32_t mlp_dim;       /* 3072 */
+  int32_t embed_dim;     /* 768: output of text_adapter[-1] = SimpleProj(768, 768, relu=True) */
+  int32_t adapt_until;   /* residual adapters after blocks 0..adapt_until-1 (3) */
+  int32_t act;           /* AACLIP_ACT_* */
+  float adapt_weight;    /* t_w = 0.1 */
+  int32_t max_sentences; /* largest n accepted by aaclip_encode_text */
+  int32_t operand_dtype; /* AACLIP_DT_F16 (default) or AACLIP_DT_BF16 */
+} AaclipTextCfg;
+
+typedef struct AaclipTextHandle AaclipTextHandle;
+
+/* Replaces: building the CLIP text tower (model/model.py:119-172) + text_adapter (model/adapter.py:51-54). */
+int aaclip_text_create(const AaclipTextCfg* cfg, AaclipTextHandle** out);
+void aaclip_text_destroy(AaclipTextHandle* h);
+
+/* One fp32 DEVICE tensor of the text path; `name` is the AdaptedCLIP state_dict key:
+ *   "clipmodel.token_embedding.weight" [vocab,W]   "clipmodel.positional_embedding" [ctx,W]
+ *   "clipmodel.transformer.resblocks.<i>.{ln_1,ln_2}.{weight,bias}", ".attn.{in_proj_weight,in_proj_bias}",
+ *   ".attn.out_proj.{weight,bias}", ".mlp.{c_fc,c_proj}.{weight,bias}"   "clipmodel.ln_final.{weight,bias}"
+ *   "text_adapter.<i>.fc.0.weight" (i < adapt_until: SimpleAdapter; i == adapt_until: the final SimpleProj) */
+int aaclip_text_set_weight(AaclipTextHandle* h, const char* name, const float* data, const int64_t* shape,
+                           int32_t ndim, void* stream);
+int aaclip_text_missing_weights(AaclipTextHandle* h);
+size_t aaclip_text_workspace_bytes(AaclipTextHandle* h, int32_t n_sentences);
+
+/* Adapted text encoder. Replaces AdaptedCLIP.encode_text(text, adapt_text=True), model/adapter.py:273-304:
+ * token + positional embedding, 12 causal pre-LN residual attention blocks with residual adapters on the first
+ * `adapt_until`, ln_final, EOT-row gather (argmax of the token ids), SimpleProj + LeakyReLU.
+ *   tokens [n,ctx] int32 device; ids outside [0,vocab) are clamped by the kernel (the Python wrapper validates)
+ *   out    [n,E] fp32 (NOT normalised, exactly what encode_text returns) */
+int aaclip_encode_text(AaclipTextHandle* h, const int32_t* tokens, int32_t n_sentences, void* workspace,
+                       size_t workspace_bytes, float* out, void* stream);
+
+/* Prompt ensembling of forward_utils.get_adapted_single_class_text_embedding (forward_utils.py:152-161):
+ * group g = rows offsets[g]..offsets[g+1]-1 of emb; each row is L2-normalised, the group is averaged and the mean
+ * re-normalised. Groups 2c and 2c+1 are the normal / abnormal states of class c:
+ *   anchors [n_groups/2, E, 2] fp32  (== torch.stack([normal, abnormal], dim=1) per class)
+ *   offsets [n_groups+1] int32 DEVICE */
+int aaclip_text_anchors(const float* emb, const int32_t* offsets, int32_t n_groups, int32_t E, float* anchors,
+                        void* stream);
+
 /* ---- building blocks, exported for the parity tests (each is exactly what aaclip_forward launches) ---- */
 
 /* C[M,N] = A[M,K] * W[N,K]^T with a fused epilogue (tcgen05/TMEM/TMA GEMM). A, W: `dtype` row-major.

@@ -175,3 +175,32 @@ def predict(sd, images, text, img_size: int, domain: str = "Industrial", **kw):
     out["maps"] = anomaly_maps(out["seg"], text, img_size, domain)
     out["score"] = image_score(out["det"], text)
     return out
+
+
+# ------------------------------------------------------------------------------------------------ text anchors
+def encode_text(sd: Dict[str, torch.Tensor], tokens: torch.Tensor, heads: int = 12, layers: int = 12,
+                adapt_until: int = 3, adapt_weight: float = 0.1, quick_gelu: bool = False) -> torch.Tensor:
+    """AdaptedCLIP.encode_text(text, adapt_text=True), model/adapter.py:273-304. tokens: int [n, 77] -> [n, 768].
+    Causal additive mask as built by TextTransformer.build_attention_mask (model/transformer.py:629-635)."""
+    p = "clipmodel."
+    x = sd[p + "token_embedding.weight"][tokens.long()] + sd[p + "positional_embedding"]      # :277-281
+    T = x.shape[1]
+    mask = torch.full((T, T), float("-inf")).triu_(1)
+    for i in range(layers):                                                                      # :284 (hard-coded 12)
+        x = residual_attention_block(x, sd, f"{p}transformer.resblocks.{i}.", heads, quick_gelu, attn_mask=mask)
+        if i < adapt_until:                                                                      # :288-295
+            x = adapter_blend(x, sd[f"text_adapter.{i}.fc.0.weight"], adapt_weight)
+    x = layer_norm(x, sd[p + "ln_final.weight"], sd[p + "ln_final.bias"])                        # :297
+    eot = x[torch.arange(x.shape[0]), tokens.argmax(dim=-1)]                                     # :298 (EOT = highest id)
+    return F.leaky_relu(eot @ sd[f"text_adapter.{adapt_until}.fc.0.weight"].t(), 0.01)           # SimpleProj(relu=True)
+
+
+def text_anchor(emb_normal: torch.Tensor, emb_abnormal: torch.Tensor) -> torch.Tensor:
+    """forward_utils.get_adapted_single_class_text_embedding, forward_utils.py:152-161: per state, L2-normalise each
+    sentence embedding, average, re-normalise; stack the two states -> [E, 2]."""
+    feats = []
+    for e in (emb_normal, emb_abnormal):
+        e = e / e.norm(dim=-1, keepdim=True)
+        m = e.mean(dim=0)
+        feats.append(m / m.norm())
+    return torch.stack(feats, dim=1)
