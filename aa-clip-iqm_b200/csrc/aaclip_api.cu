@@ -94,6 +94,13 @@ int ensure_device() {
 }
 
 // ------------------------------------------------------------------------------------------ kernel launchers
+#ifndef AACLIP_GEMM_PAIR
+#define AACLIP_GEMM_PAIR 1        // 1: CTA-pair kernel (cta_group::2); 0: single-CTA kernel (kept for A/B measurement)
+#endif
+#ifndef AACLIP_GEMM_PAIR_BN128_MAX_N
+#define AACLIP_GEMM_PAIR_BN128_MAX_N 0   // N <= this uses 256x128 pair tiles (less wave quantisation on narrow GEMMs)
+#endif
+
 template <int EPI, bool BF16>
 int launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const GemmEpi& epi,
                   cudaStream_t st) {
@@ -110,6 +117,23 @@ int launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, in
   return AACLIP_OK;
 }
 
+template <int EPI, bool BF16, int BN>
+int launch_gemm_pair_t(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const GemmEpi& epi,
+                       cudaStream_t st) {
+  using C = GemmPairCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(gemm_pair_kernel<EPI, BF16, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  C::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int tiles = ((M + 2 * C::BM - 1) / (2 * C::BM)) * (N / BN);
+  const int pairs = tiles < g_num_sms / 2 ? tiles : g_num_sms / 2;
+  gemm_pair_kernel<EPI, BF16, BN><<<2 * pairs, C::THREADS, C::SMEM_BYTES, st>>>(ta, tb, M, N, K, epi);
+  LAUNCH_CHECK("gemm_pair_kernel");
+  return AACLIP_OK;
+}
+
 int launch_gemm(int epi_mode, bool bf16, const void* A, const void* W, int M, int N, int K, const GemmEpi& epi,
                 cudaStream_t st) {
   if (int rc = ensure_device()) return rc;
@@ -117,6 +141,8 @@ int launch_gemm(int epi_mode, bool bf16, const void* A, const void* W, int M, in
     return fail(AACLIP_EINVAL, "gemm: unsupported shape M=%d N=%d K=%d (need N%%256==0, K%%64==0)", M, N, K);
   if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(W) & 15))
     return fail(AACLIP_EINVAL, "gemm: operands must be 16-byte aligned");
+  const bool pair = AACLIP_GEMM_PAIR != 0;
+  const bool bn128 = pair && N <= AACLIP_GEMM_PAIR_BN128_MAX_N;
   CUtensorMap ta, tb;
   {
     const uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
@@ -127,12 +153,15 @@ int launch_gemm(int epi_mode, bool bf16, const void* A, const void* W, int M, in
   {
     const uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
     const uint64_t str[1] = {(uint64_t)K * 2};
-    const uint32_t box[2] = {gemm_cfg::BK, gemm_cfg::BN};
+    // single-CTA kernel: the whole 256-row W tile; pair kernel: this CTA's half of the (256 | 128)-row tile
+    const uint32_t box[2] = {gemm_cfg::BK, (uint32_t)(pair ? (bn128 ? 64 : 128) : gemm_cfg::BN)};
     if (int rc = make_tmap_16(&tb, W, 2, dims, str, box, bf16)) return rc;
   }
-#define AACLIP_GEMM_CASE(E)                                                              \
-  case E:                                                                                \
-    return bf16 ? launch_gemm_t<E, true>(ta, tb, M, N, K, epi, st) : launch_gemm_t<E, false>(ta, tb, M, N, K, epi, st);
+#define AACLIP_GEMM_CASE(E)                                                                                       \
+  case E:                                                                                                         \
+    if (!pair) return bf16 ? launch_gemm_t<E, true>(ta, tb, M, N, K, epi, st) : launch_gemm_t<E, false>(ta, tb, M, N, K, epi, st); \
+    if (bn128) return bf16 ? launch_gemm_pair_t<E, true, 128>(ta, tb, M, N, K, epi, st) : launch_gemm_pair_t<E, false, 128>(ta, tb, M, N, K, epi, st); \
+    return bf16 ? launch_gemm_pair_t<E, true, 256>(ta, tb, M, N, K, epi, st) : launch_gemm_pair_t<E, false, 256>(ta, tb, M, N, K, epi, st);
   switch (epi_mode) {
     AACLIP_GEMM_CASE(EPI_BIAS_BF16)
     AACLIP_GEMM_CASE(EPI_BIAS_GELU_BF16)

@@ -268,4 +268,196 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   }
 }
 
+
+// =========================================================================================================
+// CTA-pair variant (tcgen05 cta_group::2): one cluster of 2 CTAs computes a 256 x BN output tile.
+//   CTA r of the pair owns rows [256*m_pair + 128*r, +128) of C (its 128 TMEM lanes) and stages, per K step,
+//   its own 128 x 64 slice of A and HALF of the W tile (BN/2 rows) -- the tensor cores of both SMs read both
+//   halves, so every W byte is fetched from L2 and written to shared memory once per PAIR (2/3 of the single-CTA
+//   kernel's operand traffic at BN = 256) and the per-SM shared-memory read rate drops below the MMA rate.
+//   Only the leader (cluster rank 0) issues MMAs; TMA completions of both CTAs are counted on the leader's `full`
+//   barriers; tcgen05.commit multicasts to the `empty` / `tmem_full` barriers of both CTAs; the epilogue warps of
+//   both CTAs arrive on the leader's `tmem_empty`.
+template <int BN_>
+struct GemmPairCfg {
+  static constexpr int BM = 128, BN = BN_, BK = 64;
+  static constexpr int A_BYTES = BM * BK * 2;             // 16 KiB
+  static constexpr int B_BYTES = (BN / 2) * BK * 2;       // 16 KiB (BN 256) / 8 KiB (BN 128): this CTA's half
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 6 : 8;      // 192 KiB of operand ring either way
+  static constexpr int THREADS = 320;
+  static constexpr int EPI_WARPS = 8;
+  static constexpr int TMEM_COLS = 2 * BN;                // double-buffered accumulator
+  static constexpr int EPI_STAGE_BYTES = 32 * 128;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 512 + EPI_WARPS * EPI_STAGE_BYTES + 1024;
+};
+
+template <int EPI, bool BF16, int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
+gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, int M, int N,
+                 int K, GemmEpi epi) {
+  using C = GemmPairCfg<BN>;
+  constexpr int BM = C::BM, BK = C::BK, STAGES = C::STAGES, STAGE_BYTES = C::STAGE_BYTES, A_BYTES = C::A_BYTES;
+  constexpr int EPI_WARPS = C::EPI_WARPS;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();           // 0 = leader
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const int m_pairs = (M + 2 * BM - 1) / (2 * BM);
+  const int n_tiles = N / BN;
+  const int num_tiles = m_pairs * n_tiles;
+  const int num_kb = K / BK;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmap_a);
+    ptx::prefetch_tmap(&tmap_b);
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);                    // leader's producer: arrive.expect_tx (bytes of both CTAs)
+      ptx::mbar_init(&empty_bar[s], 1);                   // multicast tcgen05.commit
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&tmem_full_bar[s], 1);               // multicast tcgen05.commit
+      ptx::mbar_init(&tmem_empty_bar[s], 2 * EPI_WARPS);  // epilogue warps of both CTAs (used on the leader only)
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc_pair<C::TMEM_COLS>(tmem_base_smem);
+    ptx::tmem_relinquish_pair();
+  }
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();                                // peer barriers initialised, both TMEM allocations done
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer (one per CTA) =====================
+    // The whole warp runs the loop (warp-uniform control flow and addresses -> plain uniform-register moves for the
+    // TMA / MMA operands); one elected lane issues. Under `if (lane == 0)` ptxas cannot prove uniformity and wraps
+    // every UTMALDG / UTCHMMA in an ELECT + R2UR.BROADCAST + BRA.U.ANY loop, which made the single issuing thread
+    // the bottleneck of the main loop (ncu: tensor pipe 76 % active with no barrier stall anywhere).
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t full0_leader = ptx::mapa_u32(ptx::smem_u32(&full_bar[0]), 0);
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      const int m_pair = tile / n_tiles, n_blk = tile - m_pair * n_tiles;
+      const int m_row = (2 * m_pair + static_cast<int>(rank)) * BM;
+      const int n_row = n_blk * BN + static_cast<int>(rank) * (BN / 2);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (ptx::elect_one()) {
+          if (rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          ptx::tma_load_2d_pair(sa, &tmap_a, full0_leader + stage * 8, kb * BK, m_row);
+          ptx::tma_load_2d_pair(sa + A_BYTES, &tmap_b, full0_leader + stage * 8, kb * BK, n_row);
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA; warp-uniform loop, one elected lane issues) =====================
+    if (rank == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_16(2 * BM, BN, 0, BF16);
+      const uint32_t smem_base = ptx::smem_u32(smem);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t sa = smem_base + stage * STAGE_BYTES;
+          const uint64_t a_desc = ptx::make_sw128_desc(sa);
+          const uint64_t b_desc = ptx::make_sw128_desc(sa + A_BYTES);
+          if (ptx::elect_one()) {
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              ptx::tc_mma_f16_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            ptx::tc_commit_pair(&empty_bar[stage]);                          // frees the slot in both CTAs
+            if (kb == num_kb - 1) ptx::tc_commit_pair(&tmem_full_bar[acc]);  // accumulators complete in both CTAs
+          }
+          __syncwarp();
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue warps (both CTAs, own 128 rows) =====================
+    constexpr int COLS_PER_WARP = BN / 2;          // two warps share a lane quarter, each takes half of the columns
+    constexpr int CHUNKS = COLS_PER_WARP / 32;
+    const int e = warp - 2;
+    const int q = warp & 3;
+    const int half = e >> 2;
+    uint8_t* stage = smem + STAGES * STAGE_BYTES + 512 + e * C::EPI_STAGE_BYTES;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      const int m_pair = tile / n_tiles, n_blk = tile - m_pair * n_tiles;
+      ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
+      ptx::tc_fence_after();
+      const int row0 = (2 * m_pair + static_cast<int>(rank)) * BM + q * 32;
+      const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + half * COLS_PER_WARP;
+      const int sub = lane >> 3, unit = lane & 7;
+#pragma unroll 1
+      for (int c = 0; c < CHUNKS; ++c) {
+        const int n = n_blk * BN + half * COLS_PER_WARP + c * 32 + unit * 4;
+        float4 resid[8];
+        if constexpr (EPI == EPI_BIAS_RESID_F32) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int rr = row0 + j * 4 + sub;
+            resid[j] = (rr < M) ? *reinterpret_cast<const float4*>(epi.out_f32 + static_cast<size_t>(rr) * epi.ldo + n)
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+        uint32_t r[32];
+        ptx::tmem_ld_32x32b_x32(t_base + c * 32, r);
+        ptx::tmem_ld_wait();
+        if (c == CHUNKS - 1) {
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa_u32(ptx::smem_u32(&tmem_empty_bar[acc]), 0));   // leader's barrier
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          *reinterpret_cast<uint4*>(stage + lane * 128 + ((u ^ (lane & 7)) << 4)) =
+              make_uint4(r[4 * u], r[4 * u + 1], r[4 * u + 2], r[4 * u + 3]);
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int rr = j * 4 + sub;
+          const float4 v = *reinterpret_cast<const float4*>(stage + rr * 128 + ((unit ^ (rr & 7)) << 4));
+          if (row0 + rr < M) {
+            if constexpr (EPI == EPI_BIAS_RESID_F32) epilogue_apply<EPI, BF16>(v, row0 + rr, n, epi, resid[j]);
+            else epilogue_apply<EPI, BF16>(v, row0 + rr, n, epi);
+          }
+        }
+        __syncwarp();
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();         // no CTA may free its TMEM / exit while its peer still multicasts into it
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc_pair<C::TMEM_COLS>(tmem_base);
+  }
+}
+
 }  // namespace aaclip

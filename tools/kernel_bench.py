@@ -10,6 +10,7 @@ import torch
 import aaclip_b200  # noqa: F401
 from aaclip_b200 import _lib, engine
 
+_lib.build()   # honours AACLIP_LIB_PATH / AACLIP_NVCC_EXTRA (tools/sweep.sh)
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 dev = "cuda"
 M = 1370 * B
