@@ -145,27 +145,36 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, uint16_t*
   } else if (warp == 8) {
     ptx::reg_dec<40>();
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    // (warp-uniform loop, one elected lane issues: keeps the UTMALDG / UTCHMMA operands in uniform registers
+    // without the per-instruction ELECT + R2UR.BROADCAST + BRA.U.ANY loop ptxas emits under `if (lane == 0)`)
+    if (ptx::elect_one()) {
       ptx::mbar_arrive_expect_tx(q_full, QT * TILE_BYTES);
       for (int t = 0; t < QT; ++t)
         ptx::tma_load_3d(smem + OFF_Q + t * TILE_BYTES, &tmap_qkv, q_full, h * HD, q_base + t * BQ, b);
-      int st = 0;
-      uint32_t ph = 0;
-      for (int j = 0; j < n_kv_tiles; ++j) {
-        ptx::mbar_wait(&k_empty[st], ph ^ 1);
+    }
+    __syncwarp();
+    int st = 0;
+    uint32_t ph = 0;
+    for (int j = 0; j < n_kv_tiles; ++j) {
+      ptx::mbar_wait(&k_empty[st], ph ^ 1);
+      if (ptx::elect_one()) {
         ptx::mbar_arrive_expect_tx(&k_full[st], TILE_BYTES);
         ptx::tma_load_3d(smem + OFF_K + st * TILE_BYTES, &tmap_qkv, &k_full[st], D + h * HD, j * BKV, b);
-        ptx::mbar_wait(&v_empty[st], ph ^ 1);
+      }
+      __syncwarp();
+      ptx::mbar_wait(&v_empty[st], ph ^ 1);
+      if (ptx::elect_one()) {
         ptx::mbar_arrive_expect_tx(&v_full[st], TILE_BYTES);
         ptx::tma_load_3d(smem + OFF_V + st * TILE_BYTES, &tmap_qkv, &v_full[st], 2 * D + h * HD, j * BKV, b);
-        if (++st == KV_STAGES) { st = 0; ph ^= 1; }
       }
+      __syncwarp();
+      if (++st == KV_STAGES) { st = 0; ph ^= 1; }
     }
   } else if (warp == 9 || warp == 10) {
     ptx::reg_dec<40>();
-    // ===================== MMA issuers (one thread per Q tile) =====================
+    // ===================== MMA issuers (one warp per Q tile; warp-uniform loop, one elected lane issues) ===========
     const int t = warp - 9;
-    if (lane == 0 && t < n_qt) {
+    if (t < n_qt) {
       constexpr uint32_t idesc_s = ptx::make_idesc_16(BQ, BKV, 0, BF16);   // S = Q K^T : both operands K-major
       constexpr uint32_t idesc_pv = ptx::make_idesc_16(BQ, HD, 1, BF16);   // O += P V  : V is MN-major
       const uint32_t q_addr = ptx::smem_u32(smem + OFF_Q) + t * TILE_BYTES;
@@ -176,25 +185,31 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, uint16_t*
       auto issue_s = [&](int stage) {
         const uint64_t a = ptx::make_sw128_desc(q_addr);
         const uint64_t bd = ptx::make_sw128_desc(k_addr + stage * TILE_BYTES);
+        if (ptx::elect_one()) {
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k)
-          ptx::tc_mma_f16(tmem_base + TM_S + t * BKV, a + 2 * k, bd + 2 * k, idesc_s, k != 0 ? 1u : 0u);
-        ptx::tc_commit(&s_full[t]);
-        ptx::tc_commit(&k_empty[stage]);
-        if (alone) ptx::tc_commit(&k_empty[stage]);
+          for (int k = 0; k < HD / 16; ++k)
+            ptx::tc_mma_f16(tmem_base + TM_S + t * BKV, a + 2 * k, bd + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+          ptx::tc_commit(&s_full[t]);
+          ptx::tc_commit(&k_empty[stage]);
+          if (alone) ptx::tc_commit(&k_empty[stage]);
+        }
+        __syncwarp();
       };
       auto issue_pv = [&](int stage, uint32_t accumulate) {
         const uint32_t va = v_addr + stage * TILE_BYTES;
+        if (ptx::elect_one()) {
 #pragma unroll
-        for (int k = 0; k < BKV / 16; ++k) {
-          // A: P_t in TMEM, 8 columns (16 packed K elements) per k-step.  B (MN-major): 16 kv rows of 128 B.
-          const uint64_t bd = ptx::make_sw128_desc(va + k * 16 * 128);
-          ptx::tc_mma_f16_ts(tmem_base + TM_O + t * HD, tmem_base + TM_P + t * (BKV / 2) + k * 8, bd, idesc_pv,
-                             (accumulate | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < BKV / 16; ++k) {
+            // A: P_t in TMEM, 8 columns (16 packed K elements) per k-step.  B (MN-major): 16 kv rows of 128 B.
+            const uint64_t bd = ptx::make_sw128_desc(va + k * 16 * 128);
+            ptx::tc_mma_f16_ts(tmem_base + TM_O + t * HD, tmem_base + TM_P + t * (BKV / 2) + k * 8, bd, idesc_pv,
+                               (accumulate | k) != 0 ? 1u : 0u);
+          }
+          ptx::tc_commit(&o_full[t]);
+          ptx::tc_commit(&v_empty[stage]);
+          if (alone) ptx::tc_commit(&v_empty[stage]);
         }
-        ptx::tc_commit(&o_full[t]);
-        ptx::tc_commit(&v_empty[stage]);
-        if (alone) ptx::tc_commit(&v_empty[stage]);
+        __syncwarp();
       };
 
       ptx::mbar_wait(q_full, 0);
