@@ -71,12 +71,17 @@ __device__ __forceinline__ float quick_gelu(float x) { return x / (1.0f + __expf
 
 // Fused epilogue on one float4 = accumulator values of (row, columns n..n+3), executed in the "coalesced
 // domain": after the smem transpose a quarter-warp owns 128 contiguous bytes of one output row.
+template <int EPI>
+__host__ __device__ constexpr bool epi_has_bias() {
+  return EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_QGELU_BF16 ||
+         EPI == EPI_BIAS_RESID_F32 || EPI == EPI_BIAS_F32;
+}
+
+// `b` = bias[n..n+3], loaded once per 32-column chunk by the caller (it does not depend on the row).
 template <int EPI, bool BF16>
-__device__ __forceinline__ void epilogue_apply(float4 v, int row, int n, const GemmEpi& e,
+__device__ __forceinline__ void epilogue_apply(float4 v, int row, int n, const GemmEpi& e, float4 b,
                                                float4 resid = make_float4(0.f, 0.f, 0.f, 0.f)) {
-  if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_QGELU_BF16 ||
-                EPI == EPI_BIAS_RESID_F32 || EPI == EPI_BIAS_F32) {
-    const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + n));
+  if constexpr (epi_has_bias<EPI>()) {
     v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
   }
   if constexpr (EPI == EPI_BIAS_GELU_BF16) {
@@ -207,7 +212,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int e = warp - 2;
     const int q = warp & 3;        // TMEM lane quarter this warp may access
     const int half = e >> 2;       // which 128 of the 256 accumulator columns
-    uint8_t* stage = smem + STAGES * STAGE_BYTES + 512 + e * EPI_STAGE_BYTES;  // this warp's transpose buffer
+    const uint32_t stage_u32 = ptx::smem_u32(smem + STAGES * STAGE_BYTES + 512 + e * EPI_STAGE_BYTES);  // transpose buffer
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -220,6 +225,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         const int n = n_blk * BN + half * 128 + c * 32 + unit * 4;
+        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if constexpr (epi_has_bias<EPI>()) bias4 = __ldg(reinterpret_cast<const float4*>(epi.bias + n));
         float4 resid[8];
         if constexpr (EPI == EPI_BIAS_RESID_F32) {
           // residual rows for this chunk: 8 independent coalesced loads issued before the TMEM load / transpose
@@ -242,16 +249,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         // thread-owns-row -> staging tile [32 rows][128 B], 16-B units XOR-swizzled by (row & 7): conflict-free
 #pragma unroll
         for (int u = 0; u < 8; ++u)
-          *reinterpret_cast<uint4*>(stage + lane * 128 + ((u ^ (lane & 7)) << 4)) =
-              make_uint4(r[4 * u], r[4 * u + 1], r[4 * u + 2], r[4 * u + 3]);
+          ptx::sts128(stage_u32 + lane * 128 + ((u ^ (lane & 7)) << 4), r[4 * u], r[4 * u + 1], r[4 * u + 2],
+                      r[4 * u + 3]);
         __syncwarp();
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int rr = j * 4 + sub;
-          const float4 v = *reinterpret_cast<const float4*>(stage + rr * 128 + ((unit ^ (rr & 7)) << 4));
+          const float4 v = ptx::lds128(stage_u32 + rr * 128 + ((unit ^ (rr & 7)) << 4));
           if (row0 + rr < M) {
-            if constexpr (EPI == EPI_BIAS_RESID_F32) epilogue_apply<EPI, BF16>(v, row0 + rr, n, epi, resid[j]);
-            else epilogue_apply<EPI, BF16>(v, row0 + rr, n, epi);
+            if constexpr (EPI == EPI_BIAS_RESID_F32) epilogue_apply<EPI, BF16>(v, row0 + rr, n, epi, bias4, resid[j]);
+            else epilogue_apply<EPI, BF16>(v, row0 + rr, n, epi, bias4);
           }
         }
         __syncwarp();
@@ -402,7 +409,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int e = warp - 2;
     const int q = warp & 3;
     const int half = e >> 2;
-    uint8_t* stage = smem + STAGES * STAGE_BYTES + 512 + e * C::EPI_STAGE_BYTES;
+    const uint32_t stage_u32 = ptx::smem_u32(smem + STAGES * STAGE_BYTES + 512 + e * C::EPI_STAGE_BYTES);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
@@ -415,6 +422,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll 1
       for (int c = 0; c < CHUNKS; ++c) {
         const int n = n_blk * BN + half * COLS_PER_WARP + c * 32 + unit * 4;
+        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if constexpr (epi_has_bias<EPI>()) bias4 = __ldg(reinterpret_cast<const float4*>(epi.bias + n));
         float4 resid[8];
         if constexpr (EPI == EPI_BIAS_RESID_F32) {
 #pragma unroll
@@ -434,16 +443,16 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u)
-          *reinterpret_cast<uint4*>(stage + lane * 128 + ((u ^ (lane & 7)) << 4)) =
-              make_uint4(r[4 * u], r[4 * u + 1], r[4 * u + 2], r[4 * u + 3]);
+          ptx::sts128(stage_u32 + lane * 128 + ((u ^ (lane & 7)) << 4), r[4 * u], r[4 * u + 1], r[4 * u + 2],
+                      r[4 * u + 3]);
         __syncwarp();
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int rr = j * 4 + sub;
-          const float4 v = *reinterpret_cast<const float4*>(stage + rr * 128 + ((unit ^ (rr & 7)) << 4));
+          const float4 v = ptx::lds128(stage_u32 + rr * 128 + ((unit ^ (rr & 7)) << 4));
           if (row0 + rr < M) {
-            if constexpr (EPI == EPI_BIAS_RESID_F32) epilogue_apply<EPI, BF16>(v, row0 + rr, n, epi, resid[j]);
-            else epilogue_apply<EPI, BF16>(v, row0 + rr, n, epi);
+            if constexpr (EPI == EPI_BIAS_RESID_F32) epilogue_apply<EPI, BF16>(v, row0 + rr, n, epi, bias4, resid[j]);
+            else epilogue_apply<EPI, BF16>(v, row0 + rr, n, epi, bias4);
           }
         }
         __syncwarp();
