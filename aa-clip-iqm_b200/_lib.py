@@ -35,6 +35,9 @@ EPI_BIAS_RESID_F32 = 3
 EPI_F32 = 4
 EPI_LEAKY_F32 = 5
 EPI_BIAS_F32 = 7
+EPI_LN_BIAS_BF16 = 8
+EPI_LN_BIAS_GELU_BF16 = 9
+EPI_LN_BIAS_QGELU_BF16 = 10
 
 DT_F16 = 0
 DT_BF16 = 1
@@ -167,6 +170,12 @@ def _declare(lib):
     lib.aaclip_text_anchors.argtypes = [vp, vp, i32, i32, vp, vp]
     lib.aaclip_gemm16.restype = i32
     lib.aaclip_gemm16.argtypes = [i32, vp, vp, i32, i32, i32, i32, vp, vp, vp, i32, vp]
+    lib.aaclip_ln_fold.restype = i32
+    lib.aaclip_ln_fold.argtypes = [i32, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp]
+    lib.aaclip_gemm16_ln.restype = i32
+    lib.aaclip_gemm16_ln.argtypes = [i32, vp, vp, i32, i32, i32, i32, vp, vp, vp, i32, i32, vp, i32, vp]
+    lib.aaclip_gemm16_resid.restype = i32
+    lib.aaclip_gemm16_resid.argtypes = [i32, vp, vp, i32, i32, i32, vp, vp, vp, vp, i32, vp]
     lib.aaclip_attention.restype = i32
     lib.aaclip_attention.argtypes = [i32, vp, vp, i32, i32, i32, i32, vp]
     lib.aaclip_layernorm.restype = i32
@@ -180,6 +189,7 @@ EXPORTED_SYMBOLS = [
     "aaclip_missing_weights", "aaclip_workspace_bytes", "aaclip_forward", "aaclip_score_workspace_bytes",
     "aaclip_score_maps", "aaclip_last_launch_count", "aaclip_profile_enable", "aaclip_profile_read", "aaclip_gemm16", "aaclip_attention", "aaclip_layernorm",
     "aaclip_pack16",
+    "aaclip_ln_fold", "aaclip_gemm16_ln", "aaclip_gemm16_resid",
     "aaclip_text_create", "aaclip_text_destroy", "aaclip_text_set_weight", "aaclip_text_missing_weights",
     "aaclip_text_workspace_bytes", "aaclip_encode_text", "aaclip_text_anchors",
 ]

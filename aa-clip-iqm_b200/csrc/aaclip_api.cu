@@ -94,74 +94,48 @@ int ensure_device() {
 }
 
 // ------------------------------------------------------------------------------------------ kernel launchers
-#ifndef AACLIP_GEMM_PAIR
-#define AACLIP_GEMM_PAIR 1        // 1: CTA-pair kernel (cta_group::2); 0: single-CTA kernel (kept for A/B measurement)
-#endif
-#ifndef AACLIP_GEMM_PAIR_BN128_MAX_N
-#define AACLIP_GEMM_PAIR_BN128_MAX_N 0   // N <= this uses 256x128 pair tiles (less wave quantisation on narrow GEMMs)
-#endif
-
 template <int EPI, bool BF16>
 int launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const GemmEpi& epi,
                   cudaStream_t st) {
+  using C = GemmPairCfg<256>;
   static bool attr_set = false;
   if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(gemm_tcgen05_kernel<EPI, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  gemm_cfg::SMEM_BYTES));
-    attr_set = true;
-  }
-  const int tiles = ((M + gemm_cfg::BM - 1) / gemm_cfg::BM) * (N / gemm_cfg::BN);
-  const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-  gemm_tcgen05_kernel<EPI, BF16><<<grid, gemm_cfg::THREADS, gemm_cfg::SMEM_BYTES, st>>>(ta, tb, M, N, K, epi);
-  LAUNCH_CHECK("gemm_tcgen05_kernel");
-  return AACLIP_OK;
-}
-
-template <int EPI, bool BF16, int BN>
-int launch_gemm_pair_t(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const GemmEpi& epi,
-                       cudaStream_t st) {
-  using C = GemmPairCfg<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(gemm_pair_kernel<EPI, BF16, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CUDA_TRY(cudaFuncSetAttribute(gemm_pair_kernel<EPI, BF16, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   C::SMEM_BYTES));
     attr_set = true;
   }
-  const int tiles = ((M + 2 * C::BM - 1) / (2 * C::BM)) * (N / BN);
+  // persistent: one CTA pair (cluster of 2) per two SMs, each looping over 256 x 256 output tiles
+  const int tiles = ((M + 2 * C::BM - 1) / (2 * C::BM)) * (N / C::BN);
   const int pairs = tiles < g_num_sms / 2 ? tiles : g_num_sms / 2;
-  gemm_pair_kernel<EPI, BF16, BN><<<2 * pairs, C::THREADS, C::SMEM_BYTES, st>>>(ta, tb, M, N, K, epi);
+  gemm_pair_kernel<EPI, BF16, 256><<<2 * pairs, C::THREADS, C::SMEM_BYTES, st>>>(ta, tb, M, N, K, epi);
   LAUNCH_CHECK("gemm_pair_kernel");
   return AACLIP_OK;
 }
 
 int launch_gemm(int epi_mode, bool bf16, const void* A, const void* W, int M, int N, int K, const GemmEpi& epi,
                 cudaStream_t st) {
+  using C = GemmPairCfg<256>;
   if (int rc = ensure_device()) return rc;
-  if (M <= 0 || N <= 0 || K <= 0 || N % gemm_cfg::BN != 0 || K % gemm_cfg::BK != 0)
+  if (M <= 0 || N <= 0 || K <= 0 || N % C::BN != 0 || K % C::BK != 0)
     return fail(AACLIP_EINVAL, "gemm: unsupported shape M=%d N=%d K=%d (need N%%256==0, K%%64==0)", M, N, K);
   if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(W) & 15))
     return fail(AACLIP_EINVAL, "gemm: operands must be 16-byte aligned");
-  const bool pair = AACLIP_GEMM_PAIR != 0;
-  const bool bn128 = pair && N <= AACLIP_GEMM_PAIR_BN128_MAX_N;
   CUtensorMap ta, tb;
   {
     const uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
     const uint64_t str[1] = {(uint64_t)K * 2};
-    const uint32_t box[2] = {gemm_cfg::BK, gemm_cfg::BM};
+    const uint32_t box[2] = {C::BK, C::BM};                 // this CTA's 128 rows of A
     if (int rc = make_tmap_16(&ta, A, 2, dims, str, box, bf16)) return rc;
   }
   {
     const uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
     const uint64_t str[1] = {(uint64_t)K * 2};
-    // single-CTA kernel: the whole 256-row W tile; pair kernel: this CTA's half of the (256 | 128)-row tile
-    const uint32_t box[2] = {gemm_cfg::BK, (uint32_t)(pair ? (bn128 ? 64 : 128) : gemm_cfg::BN)};
+    const uint32_t box[2] = {C::BK, C::BN / 2};             // this CTA's half of the 256-row W tile
     if (int rc = make_tmap_16(&tb, W, 2, dims, str, box, bf16)) return rc;
   }
-#define AACLIP_GEMM_CASE(E)                                                                                       \
-  case E:                                                                                                         \
-    if (!pair) return bf16 ? launch_gemm_t<E, true>(ta, tb, M, N, K, epi, st) : launch_gemm_t<E, false>(ta, tb, M, N, K, epi, st); \
-    if (bn128) return bf16 ? launch_gemm_pair_t<E, true, 128>(ta, tb, M, N, K, epi, st) : launch_gemm_pair_t<E, false, 128>(ta, tb, M, N, K, epi, st); \
-    return bf16 ? launch_gemm_pair_t<E, true, 256>(ta, tb, M, N, K, epi, st) : launch_gemm_pair_t<E, false, 256>(ta, tb, M, N, K, epi, st);
+#define AACLIP_GEMM_CASE(E)                                                              \
+  case E:                                                                                \
+    return bf16 ? launch_gemm_t<E, true>(ta, tb, M, N, K, epi, st) : launch_gemm_t<E, false>(ta, tb, M, N, K, epi, st);
   switch (epi_mode) {
     AACLIP_GEMM_CASE(EPI_BIAS_BF16)
     AACLIP_GEMM_CASE(EPI_BIAS_GELU_BF16)
@@ -171,6 +145,9 @@ int launch_gemm(int epi_mode, bool bf16, const void* A, const void* W, int M, in
     AACLIP_GEMM_CASE(EPI_LEAKY_F32)
     AACLIP_GEMM_CASE(EPI_PATCH_F32)
     AACLIP_GEMM_CASE(EPI_BIAS_F32)
+    AACLIP_GEMM_CASE(EPI_LN_BIAS_BF16)
+    AACLIP_GEMM_CASE(EPI_LN_BIAS_GELU_BF16)
+    AACLIP_GEMM_CASE(EPI_LN_BIAS_QGELU_BF16)
 #undef AACLIP_GEMM_CASE
     default: return fail(AACLIP_EINVAL, "gemm: unknown epilogue %d", epi_mode);
   }
@@ -205,22 +182,22 @@ int launch_attention(bool bf16, const void* qkv, void* out, int B, int N, int D,
 
 template <int D, bool BF16>
 void launch_layernorm_t(const float* x, const float* g, const float* b, void* out16, float* out_f32, int rows,
-                        int skipP, bool normalize, cudaStream_t st) {
+                        int skipP, bool normalize, cudaStream_t st, float* stats_out, int np) {
   const int threads = 256, grid = (rows + 7) / 8;
   uint16_t* o = reinterpret_cast<uint16_t*>(out16);
-  if (normalize) layernorm_kernel<D, true, BF16><<<grid, threads, 0, st>>>(x, g, b, o, out_f32, rows, skipP, 1e-5f);
-  else layernorm_kernel<D, false, BF16><<<grid, threads, 0, st>>>(x, g, b, o, out_f32, rows, skipP, 1e-5f);
+  if (normalize) layernorm_kernel<D, true, BF16><<<grid, threads, 0, st>>>(x, g, b, o, out_f32, rows, skipP, 1e-5f, stats_out, np);
+  else layernorm_kernel<D, false, BF16><<<grid, threads, 0, st>>>(x, g, b, o, out_f32, rows, skipP, 1e-5f, stats_out, np);
 }
 
 int launch_layernorm(bool bf16, const float* x, const float* g, const float* b, void* out16, float* out_f32, int rows,
-                     int D, int skipP, bool normalize, cudaStream_t st) {
+                     int D, int skipP, bool normalize, cudaStream_t st, float* stats_out = nullptr, int np = 0) {
   if (rows <= 0) return AACLIP_OK;
   if (D == 1024) {
-    if (bf16) launch_layernorm_t<1024, true>(x, g, b, out16, out_f32, rows, skipP, normalize, st);
-    else launch_layernorm_t<1024, false>(x, g, b, out16, out_f32, rows, skipP, normalize, st);
+    if (bf16) launch_layernorm_t<1024, true>(x, g, b, out16, out_f32, rows, skipP, normalize, st, stats_out, np);
+    else launch_layernorm_t<1024, false>(x, g, b, out16, out_f32, rows, skipP, normalize, st, stats_out, np);
   } else if (D == 768) {
-    if (bf16) launch_layernorm_t<768, true>(x, g, b, out16, out_f32, rows, skipP, normalize, st);
-    else launch_layernorm_t<768, false>(x, g, b, out16, out_f32, rows, skipP, normalize, st);
+    if (bf16) launch_layernorm_t<768, true>(x, g, b, out16, out_f32, rows, skipP, normalize, st, stats_out, np);
+    else launch_layernorm_t<768, false>(x, g, b, out16, out_f32, rows, skipP, normalize, st, stats_out, np);
   } else {
     return fail(AACLIP_EINVAL, "layernorm: D=%d unsupported (768 or 1024)", D);
   }
@@ -256,11 +233,160 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 }  // namespace
 
-// =========================================================================================== handle
+// =========================================================================================== transformer core
+// Shared by the visual tower (AaclipHandle) and the text tower (AaclipTextHandle): per-block weights, LayerNorm
+// folding, and the launch sequence of one pre-LN residual attention block (model/transformer.py:239-258).
 struct BlockW {
-  float *ln1_g, *ln1_b, *ln2_g, *ln2_b, *b_qkv, *b_out, *b_fc, *b_proj;
-  uint16_t *w_qkv, *w_out, *w_fc, *w_proj;
+  float *ln1_g, *ln1_b, *ln2_g, *ln2_b, *b_qkv, *b_out, *b_fc, *b_proj;   // raw fp32 parameters (arena)
+  uint16_t *w_qkv, *w_out, *w_fc, *w_proj;                               // 16-bit GEMM operands (arena)
+  // ln_1 / ln_2 folded into the QKV / c_fc GEMMs (ln_fold_kernel): w_qkv = in_proj * gamma_1, w_fc = c_fc * gamma_2
+  float *cs_qkv, *bf_qkv, *cs_fc, *bf_fc;                                // column sums of W', bias' (arena)
+  float *stage_qkv = nullptr, *stage_fc = nullptr;                       // fp32 weights kept until the fold (cudaMalloc)
 };
+
+namespace {
+
+struct ArenaPlan {
+  size_t off = 0;
+  template <typename T>
+  size_t take(size_t n) {
+    size_t o = off;
+    off = align_up(off + n * sizeof(T), 256);
+    return o;
+  }
+};
+
+int64_t numel(const int64_t* shape, int ndim) {
+  int64_t n = 1;
+  for (int i = 0; i < ndim; ++i) n *= shape[i];
+  return n;
+}
+
+void erase_key(std::vector<std::string>& v, const std::string& key) {
+  for (size_t i = 0; i < v.size(); ++i)
+    if (v[i] == key) { v.erase(v.begin() + i); return; }
+}
+
+struct BlockOff { size_t ln1g, ln1b, ln2g, ln2b, bqkv, bout, bfc, bproj, wqkv, wout, wfc, wproj, csq, bfq, csf, bff; };
+
+BlockOff plan_block(ArenaPlan& plan, size_t W, size_t F) {
+  BlockOff o;
+  o.ln1g = plan.take<float>(W); o.ln1b = plan.take<float>(W);
+  o.ln2g = plan.take<float>(W); o.ln2b = plan.take<float>(W);
+  o.bqkv = plan.take<float>(3 * W); o.bout = plan.take<float>(W);
+  o.bfc = plan.take<float>(F); o.bproj = plan.take<float>(W);
+  o.wqkv = plan.take<uint16_t>(3 * W * W); o.wout = plan.take<uint16_t>(W * W);
+  o.wfc = plan.take<uint16_t>(F * W); o.wproj = plan.take<uint16_t>(W * F);
+  o.csq = plan.take<float>(3 * W); o.bfq = plan.take<float>(3 * W);
+  o.csf = plan.take<float>(F); o.bff = plan.take<float>(F);
+  return o;
+}
+
+void bind_block(BlockW& b, uint8_t* a, const BlockOff& o) {
+  b.ln1_g = (float*)(a + o.ln1g); b.ln1_b = (float*)(a + o.ln1b);
+  b.ln2_g = (float*)(a + o.ln2g); b.ln2_b = (float*)(a + o.ln2b);
+  b.b_qkv = (float*)(a + o.bqkv); b.b_out = (float*)(a + o.bout);
+  b.b_fc = (float*)(a + o.bfc); b.b_proj = (float*)(a + o.bproj);
+  b.w_qkv = (uint16_t*)(a + o.wqkv); b.w_out = (uint16_t*)(a + o.wout);
+  b.w_fc = (uint16_t*)(a + o.wfc); b.w_proj = (uint16_t*)(a + o.wproj);
+  b.cs_qkv = (float*)(a + o.csq); b.bf_qkv = (float*)(a + o.bfq);
+  b.cs_fc = (float*)(a + o.csf); b.bf_fc = (float*)(a + o.bff);
+}
+
+const char* const kBlockTensors[] = {"ln_1.weight", "ln_1.bias", "ln_2.weight", "ln_2.bias", "attn.in_proj_weight",
+                                     "attn.in_proj_bias", "attn.out_proj.weight", "attn.out_proj.bias",
+                                     "mlp.c_fc.weight", "mlp.c_fc.bias", "mlp.c_proj.weight", "mlp.c_proj.bias"};
+
+// One tensor of a residual attention block ("ln_1.weight", "attn.in_proj_weight", ...). The weights that LayerNorm is
+// folded into (in_proj, c_fc) are kept in fp32 until fold_blocks() runs at the first forward; after that the block's
+// LayerNorm / in_proj / c_fc tensors are frozen (create a new handle to load different ones).
+int set_block_tensor(BlockW& b, const std::string& t, const std::string& key, std::vector<std::string>& missing,
+                     bool folded, bool bf16, int64_t W, int64_t F, const char* name, const float* data, int64_t n,
+                     cudaStream_t st) {
+  auto copy_f32 = [&](float* dst, int64_t expect) -> int {
+    if (n != expect) return fail(AACLIP_EINVAL, "%s: expected %lld elements, got %lld", name, (long long)expect, (long long)n);
+    CUDA_TRY(cudaMemcpyAsync(dst, data, expect * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    erase_key(missing, key);
+    return AACLIP_OK;
+  };
+  auto pack = [&](uint16_t* dst, int64_t R, int64_t C) -> int {
+    if (n != R * C) return fail(AACLIP_EINVAL, "%s: expected %lld x %lld elements, got %lld", name, (long long)R, (long long)C, (long long)n);
+    if (int rc = launch_pack(bf16, data, dst, R, C, C, st)) return rc;
+    erase_key(missing, key);
+    return AACLIP_OK;
+  };
+  auto stage = [&](float** slot, int64_t R, int64_t C) -> int {
+    if (n != R * C) return fail(AACLIP_EINVAL, "%s: expected %lld x %lld elements, got %lld", name, (long long)R, (long long)C, (long long)n);
+    if (*slot == nullptr) CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(slot), R * C * sizeof(float)));
+    CUDA_TRY(cudaMemcpyAsync(*slot, data, R * C * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    erase_key(missing, key);
+    return AACLIP_OK;
+  };
+  const bool fold_input = t == "ln_1.weight" || t == "ln_1.bias" || t == "ln_2.weight" || t == "ln_2.bias" ||
+                          t == "attn.in_proj_weight" || t == "attn.in_proj_bias" || t == "mlp.c_fc.weight" ||
+                          t == "mlp.c_fc.bias";
+  if (fold_input && folded)
+    return fail(AACLIP_ESTATE, "%s: LayerNorm has already been folded into this block's GEMM weights (first forward "
+                               "ran); create a new handle to load different backbone weights", name);
+  if (t == "ln_1.weight") return copy_f32(b.ln1_g, W);
+  if (t == "ln_1.bias") return copy_f32(b.ln1_b, W);
+  if (t == "ln_2.weight") return copy_f32(b.ln2_g, W);
+  if (t == "ln_2.bias") return copy_f32(b.ln2_b, W);
+  if (t == "attn.in_proj_bias") return copy_f32(b.b_qkv, 3 * W);
+  if (t == "attn.out_proj.bias") return copy_f32(b.b_out, W);
+  if (t == "mlp.c_fc.bias") return copy_f32(b.b_fc, F);
+  if (t == "mlp.c_proj.bias") return copy_f32(b.b_proj, W);
+  if (t == "attn.in_proj_weight") return stage(&b.stage_qkv, 3 * W, W);
+  if (t == "attn.out_proj.weight") return pack(b.w_out, W, W);
+  if (t == "mlp.c_fc.weight") return stage(&b.stage_fc, F, W);
+  if (t == "mlp.c_proj.weight") return pack(b.w_proj, W, F);
+  return fail(AACLIP_EINVAL, "%s: unknown block tensor", name);
+}
+
+int fold_blocks(std::vector<BlockW>& blk, bool bf16, int W, int F, cudaStream_t st) {
+  for (BlockW& b : blk) {
+    if (b.stage_qkv == nullptr || b.stage_fc == nullptr) return fail(AACLIP_ESTATE, "fold_blocks: staged weights missing");
+    if (bf16) {
+      ln_fold_kernel<true><<<(3 * W + 7) / 8, 256, 0, st>>>(b.stage_qkv, b.b_qkv, b.ln1_g, b.ln1_b, b.w_qkv, b.cs_qkv, b.bf_qkv, 3 * W, W);
+      ln_fold_kernel<true><<<(F + 7) / 8, 256, 0, st>>>(b.stage_fc, b.b_fc, b.ln2_g, b.ln2_b, b.w_fc, b.cs_fc, b.bf_fc, F, W);
+    } else {
+      ln_fold_kernel<false><<<(3 * W + 7) / 8, 256, 0, st>>>(b.stage_qkv, b.b_qkv, b.ln1_g, b.ln1_b, b.w_qkv, b.cs_qkv, b.bf_qkv, 3 * W, W);
+      ln_fold_kernel<false><<<(F + 7) / 8, 256, 0, st>>>(b.stage_fc, b.b_fc, b.ln2_g, b.ln2_b, b.w_fc, b.cs_fc, b.bf_fc, F, W);
+    }
+    LAUNCH_CHECK("ln_fold_kernel");
+  }
+  CUDA_TRY(cudaStreamSynchronize(st));      // load-time only: the staging copies are released right away
+  for (BlockW& b : blk) {
+    cudaFree(b.stage_qkv); cudaFree(b.stage_fc);
+    b.stage_qkv = b.stage_fc = nullptr;
+  }
+  return AACLIP_OK;
+}
+
+void free_block_staging(std::vector<BlockW>& blk) {
+  for (BlockW& b : blk) {
+    if (b.stage_qkv) cudaFree(b.stage_qkv);
+    if (b.stage_fc) cudaFree(b.stage_fc);
+    b.stage_qkv = b.stage_fc = nullptr;
+  }
+}
+
+// workspace of the block loop, shared layout for both towers (rows M = items * tokens)
+struct CoreWs { size_t x, x16, qkv, att, hid, abuf, stats, end; };
+CoreWs plan_core_ws(ArenaPlan& p, size_t M, size_t W, size_t F) {
+  CoreWs w;
+  w.x = p.take<float>(M * W);            // residual stream, fp32
+  w.x16 = p.take<uint16_t>(M * W);       // its raw 16-bit copy = A operand of QKV / c_fc / adapter GEMMs
+  w.qkv = p.take<uint16_t>(M * 3 * W);
+  w.att = p.take<uint16_t>(M * W);
+  w.hid = p.take<uint16_t>(M * F);
+  w.abuf = p.take<float>(M * W);
+  w.stats = p.take<float>(M * (W / 128) * 2);   // LayerNorm partials (sum, sumsq) per 128 columns
+  w.end = p.off;
+  return w;
+}
+
+}  // namespace
 
 struct AaclipHandle {
   AaclipCfg cfg;
@@ -272,6 +398,7 @@ struct AaclipHandle {
   float *cls, *pos, *lnpre_g, *lnpre_b, *lnpost_g, *lnpost_b;
   uint16_t* w_conv;  // [W, KP]
   std::vector<BlockW> blk;
+  bool folded = false;
   std::vector<uint16_t*> w_adapter;  // [W,W] each
   std::vector<uint16_t*> w_seg;      // [E,W] each
   uint16_t* w_det;                   // [E,W]
@@ -283,13 +410,13 @@ struct AaclipHandle {
   std::vector<ProfRec> prof;
 };
 
-// Records a CUDA-event pair around one launch on the launch stream when profiling is enabled.
+// Records a CUDA-event pair around one launch on the launch stream when profiling is enabled (h may be null).
 struct ProfScope {
   AaclipHandle* h;
   cudaStream_t st;
   size_t idx = 0;
   bool on;
-  ProfScope(AaclipHandle* h_, int cls, double flops, cudaStream_t st_) : h(h_), st(st_), on(h_->prof_on) {
+  ProfScope(AaclipHandle* h_, int cls, double flops, cudaStream_t st_) : h(h_), st(st_), on(h_ && h_->prof_on) {
     if (!on) return;
     AaclipHandle::ProfRec r;
     r.cls = cls;
@@ -307,32 +434,66 @@ struct ProfScope {
 
 namespace {
 
-struct ArenaPlan {
-  size_t off = 0;
-  template <typename T>
-  size_t take(size_t n) {
-    size_t o = off;
-    off = align_up(off + n * sizeof(T), 256);
-    return o;
+// One residual attention block (+ optional residual adapter), model/transformer.py:239-258 + model/adapter.py:163-170.
+//   x, x16, stats hold the residual stream on entry (fp32, raw 16-bit copy, LayerNorm partials) and on exit.
+// 5 launches (7 with an adapter): LayerNorms live in the GEMM epilogues.
+struct BlockRun {
+  AaclipHandle* prof;     // profiling sink (visual handle) or nullptr
+  bool bf16;
+  int items, tokens, W, F, causal, act;
+  float* x; uint16_t* x16; uint16_t* qkv; uint16_t* att; uint16_t* hid; float* abuf; float* stats;
+  cudaStream_t st;
+  int launches = 0;
+
+  int gemm(int epi, const void* A, const void* Wt, int m, int n, int k, const GemmEpi& e) {
+    ProfScope ps(prof, AACLIP_PROF_GEMM, 2.0 * m * n * k, st);
+    ++launches;
+    return launch_gemm(epi, bf16, A, Wt, m, n, k, e, st);
+  }
+
+  int run(const BlockW& b, const uint16_t* w_adapter, float adapt_weight) {
+    const int M = items * tokens, np = W / 128;
+    int rc;
+    { GemmEpi e; e.bias = b.bf_qkv; e.colsum = b.cs_qkv; e.stats = stats; e.n_partials = np; e.inv_width = 1.0f / W;
+      e.out_16 = qkv; e.ldo = 3 * W;
+      if ((rc = gemm(EPI_LN_BIAS_BF16, x16, b.w_qkv, M, 3 * W, W, e))) return rc; }
+    {
+      ProfScope ps(prof, AACLIP_PROF_ATTENTION, 4.0 * items * (W / 64) * (double)tokens * tokens * 64, st);
+      ++launches;
+      if ((rc = launch_attention(bf16, qkv, att, items, tokens, W, causal, st))) return rc;
+    }
+    { GemmEpi e; e.bias = b.b_out; e.out_f32 = x; e.out_16 = x16; e.stats_out = stats; e.ldo = W;
+      if ((rc = gemm(EPI_BIAS_RESID_F32, att, b.w_out, M, W, W, e))) return rc; }
+    { GemmEpi e; e.bias = b.bf_fc; e.colsum = b.cs_fc; e.stats = stats; e.n_partials = np; e.inv_width = 1.0f / W;
+      e.out_16 = hid; e.ldo = F;
+      if ((rc = gemm(act == AACLIP_ACT_QUICK_GELU ? EPI_LN_BIAS_QGELU_BF16 : EPI_LN_BIAS_GELU_BF16, x16, b.w_fc, M, F, W, e))) return rc; }
+    { GemmEpi e; e.bias = b.b_proj; e.out_f32 = x; e.out_16 = x16; e.stats_out = stats; e.ldo = W;
+      if ((rc = gemm(EPI_BIAS_RESID_F32, hid, b.w_proj, M, W, F, e))) return rc; }
+    if (w_adapter != nullptr) {
+      { GemmEpi e; e.out_f32 = abuf; e.ldo = W;
+        if ((rc = gemm(EPI_LEAKY_F32, x16, w_adapter, M, W, W, e))) return rc; }
+      ProfScope ps(prof, AACLIP_PROF_OTHER, 0.0, st);
+      const int grid = (M + 7) / 8;
+      const float w = adapt_weight, w1 = 1.0f - adapt_weight;
+      if (W == 1024) {
+        if (bf16) adapter_blend_kernel<1024, true><<<grid, 256, 0, st>>>(x, abuf, M, w, w1, x16, stats, np);
+        else adapter_blend_kernel<1024, false><<<grid, 256, 0, st>>>(x, abuf, M, w, w1, x16, stats, np);
+      } else {
+        if (bf16) adapter_blend_kernel<768, true><<<grid, 256, 0, st>>>(x, abuf, M, w, w1, x16, stats, np);
+        else adapter_blend_kernel<768, false><<<grid, 256, 0, st>>>(x, abuf, M, w, w1, x16, stats, np);
+      }
+      LAUNCH_CHECK("adapter_blend_kernel");
+      ++launches;
+    }
+    return AACLIP_OK;
   }
 };
-
-void mark_loaded(AaclipHandle* h, const std::string& key) {
-  for (size_t i = 0; i < h->missing.size(); ++i)
-    if (h->missing[i] == key) { h->missing.erase(h->missing.begin() + i); return; }
-}
-
-int64_t numel(const int64_t* shape, int ndim) {
-  int64_t n = 1;
-  for (int i = 0; i < ndim; ++i) n *= shape[i];
-  return n;
-}
 
 }  // namespace
 
 extern "C" {
 
-const char* aaclip_version(void) { return "aaclip_b200 0.1 sm_100a"; }
+const char* aaclip_version(void) { return "aaclip_b200 0.2 sm_100a"; }
 const char* aaclip_last_error(void) { return g_err; }
 
 int aaclip_create(const AaclipCfg* cfg, AaclipHandle** out) {
@@ -368,16 +529,8 @@ int aaclip_create(const AaclipCfg* cfg, AaclipHandle** out) {
   const size_t o_cls = plan.take<float>(W), o_pos = plan.take<float>((size_t)h->N * W);
   const size_t o_lpg = plan.take<float>(W), o_lpb = plan.take<float>(W), o_log = plan.take<float>(W), o_lob = plan.take<float>(W);
   const size_t o_conv = plan.take<uint16_t>(W * h->KP);
-  struct BO { size_t ln1g, ln1b, ln2g, ln2b, bqkv, bout, bfc, bproj, wqkv, wout, wfc, wproj; };
-  std::vector<BO> bo(c.layers);
-  for (int i = 0; i < c.layers; ++i) {
-    bo[i].ln1g = plan.take<float>(W); bo[i].ln1b = plan.take<float>(W);
-    bo[i].ln2g = plan.take<float>(W); bo[i].ln2b = plan.take<float>(W);
-    bo[i].bqkv = plan.take<float>(3 * W); bo[i].bout = plan.take<float>(W);
-    bo[i].bfc = plan.take<float>(F); bo[i].bproj = plan.take<float>(W);
-    bo[i].wqkv = plan.take<uint16_t>(3 * W * W); bo[i].wout = plan.take<uint16_t>(W * W);
-    bo[i].wfc = plan.take<uint16_t>(F * W); bo[i].wproj = plan.take<uint16_t>(W * F);
-  }
+  std::vector<BlockOff> bo(c.layers);
+  for (int i = 0; i < c.layers; ++i) bo[i] = plan_block(plan, W, F);
   std::vector<size_t> o_ad(c.adapt_until), o_seg(c.n_levels);
   for (int i = 0; i < c.adapt_until; ++i) o_ad[i] = plan.take<uint16_t>(W * W);
   for (int l = 0; l < c.n_levels; ++l) o_seg[l] = plan.take<uint16_t>(E * W);
@@ -401,15 +554,7 @@ int aaclip_create(const AaclipCfg* cfg, AaclipHandle** out) {
   h->lnpost_g = (float*)(a + o_log); h->lnpost_b = (float*)(a + o_lob);
   h->w_conv = (uint16_t*)(a + o_conv);
   h->blk.resize(c.layers);
-  for (int i = 0; i < c.layers; ++i) {
-    BlockW& b = h->blk[i];
-    b.ln1_g = (float*)(a + bo[i].ln1g); b.ln1_b = (float*)(a + bo[i].ln1b);
-    b.ln2_g = (float*)(a + bo[i].ln2g); b.ln2_b = (float*)(a + bo[i].ln2b);
-    b.b_qkv = (float*)(a + bo[i].bqkv); b.b_out = (float*)(a + bo[i].bout);
-    b.b_fc = (float*)(a + bo[i].bfc); b.b_proj = (float*)(a + bo[i].bproj);
-    b.w_qkv = (uint16_t*)(a + bo[i].wqkv); b.w_out = (uint16_t*)(a + bo[i].wout);
-    b.w_fc = (uint16_t*)(a + bo[i].wfc); b.w_proj = (uint16_t*)(a + bo[i].wproj);
-  }
+  for (int i = 0; i < c.layers; ++i) bind_block(h->blk[i], a, bo[i]);
   for (int i = 0; i < c.adapt_until; ++i) h->w_adapter.push_back((uint16_t*)(a + o_ad[i]));
   for (int l = 0; l < c.n_levels; ++l) h->w_seg.push_back((uint16_t*)(a + o_seg[l]));
   h->w_det = (uint16_t*)(a + o_det);
@@ -418,13 +563,8 @@ int aaclip_create(const AaclipCfg* cfg, AaclipHandle** out) {
   auto need = [&](const std::string& k) { h->missing.push_back(k); };
   need("conv1.weight"); need("class_embedding"); need("positional_embedding");
   need("ln_pre.weight"); need("ln_pre.bias"); need("ln_post.weight"); need("ln_post.bias");
-  for (int i = 0; i < c.layers; ++i) {
-    const std::string p = "blk." + std::to_string(i) + ".";
-    for (const char* s : {"ln_1.weight", "ln_1.bias", "ln_2.weight", "ln_2.bias", "attn.in_proj_weight",
-                          "attn.in_proj_bias", "attn.out_proj.weight", "attn.out_proj.bias", "mlp.c_fc.weight",
-                          "mlp.c_fc.bias", "mlp.c_proj.weight", "mlp.c_proj.bias"})
-      need(p + s);
-  }
+  for (int i = 0; i < c.layers; ++i)
+    for (const char* t : kBlockTensors) need("blk." + std::to_string(i) + "." + t);
   for (int i = 0; i < c.adapt_until; ++i) need("adapter." + std::to_string(i));
   for (int l = 0; l < c.n_levels; ++l) need("seg." + std::to_string(l));
   need("det");
@@ -434,6 +574,7 @@ int aaclip_create(const AaclipCfg* cfg, AaclipHandle** out) {
 
 void aaclip_destroy(AaclipHandle* h) {
   if (h == nullptr) return;
+  free_block_staging(h->blk);
   if (h->arena) cudaFree(h->arena);
   for (auto& r : h->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   delete h;
@@ -455,13 +596,13 @@ int aaclip_set_weight(AaclipHandle* h, const char* name, const float* data, cons
   auto copy_f32 = [&](float* dst, int64_t expect, const std::string& key) -> int {
     if (n != expect) return fail(AACLIP_EINVAL, "%s: expected %lld elements, got %lld", name, (long long)expect, (long long)n);
     CUDA_TRY(cudaMemcpyAsync(dst, data, expect * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    mark_loaded(h, key);
+    erase_key(h->missing, key);
     return AACLIP_OK;
   };
   auto pack = [&](uint16_t* dst, int64_t R, int64_t C, int64_t Cp, const std::string& key) -> int {
     if (n != R * C) return fail(AACLIP_EINVAL, "%s: expected %lld x %lld elements, got %lld", name, (long long)R, (long long)C, (long long)n);
     if (int rc = launch_pack(h->bf16, data, dst, R, C, Cp, st)) return rc;
-    mark_loaded(h, key);
+    erase_key(h->missing, key);
     return AACLIP_OK;
   };
 
@@ -477,21 +618,8 @@ int aaclip_set_weight(AaclipHandle* h, const char* name, const float* data, cons
   char tail[96];
   if (sscanf(k.c_str(), "transformer.resblocks.%d.%95s", &idx, tail) == 2) {
     if (idx < 0 || idx >= c.layers) return fail(AACLIP_EINVAL, "%s: block index out of range", name);
-    BlockW& b = h->blk[idx];
-    const std::string t(tail), key = "blk." + std::to_string(idx) + "." + t;
-    if (t == "ln_1.weight") return copy_f32(b.ln1_g, W, key);
-    if (t == "ln_1.bias") return copy_f32(b.ln1_b, W, key);
-    if (t == "ln_2.weight") return copy_f32(b.ln2_g, W, key);
-    if (t == "ln_2.bias") return copy_f32(b.ln2_b, W, key);
-    if (t == "attn.in_proj_bias") return copy_f32(b.b_qkv, 3 * W, key);
-    if (t == "attn.out_proj.bias") return copy_f32(b.b_out, W, key);
-    if (t == "mlp.c_fc.bias") return copy_f32(b.b_fc, F, key);
-    if (t == "mlp.c_proj.bias") return copy_f32(b.b_proj, W, key);
-    if (t == "attn.in_proj_weight") return pack(b.w_qkv, 3 * W, W, W, key);
-    if (t == "attn.out_proj.weight") return pack(b.w_out, W, W, W, key);
-    if (t == "mlp.c_fc.weight") return pack(b.w_fc, F, W, W, key);
-    if (t == "mlp.c_proj.weight") return pack(b.w_proj, W, F, F, key);
-    return fail(AACLIP_EINVAL, "%s: unknown block tensor", name);
+    return set_block_tensor(h->blk[idx], tail, "blk." + std::to_string(idx) + "." + tail, h->missing, h->folded, h->bf16,
+                            W, F, name, data, n, st);
   }
   if (sscanf(k.c_str(), "image_adapter.layer_adapters.%d.%95s", &idx, tail) == 2) {
     if (strcmp(tail, "fc.0.weight") != 0) return fail(AACLIP_EINVAL, "%s: unknown tensor", name);
@@ -509,19 +637,15 @@ int aaclip_set_weight(AaclipHandle* h, const char* name, const float* data, cons
 
 // workspace carve-up shared by aaclip_workspace_bytes and aaclip_forward
 struct WsPlan {
-  size_t x, xn, qkv, att, hid, abuf, patchA, tok, det, total;
+  CoreWs core;
+  size_t patchA, tok, det, total;
 };
 static WsPlan plan_ws(const AaclipHandle* h, int B) {
   const size_t W = h->cfg.width, F = h->cfg.mlp_dim, E = h->cfg.embed_dim;
   const size_t M = (size_t)B * h->N, MP = (size_t)B * h->P;
   ArenaPlan p;
   WsPlan w;
-  w.x = p.take<float>(M * W);
-  w.xn = p.take<uint16_t>(M * W);
-  w.qkv = p.take<uint16_t>(M * 3 * W);
-  w.att = p.take<uint16_t>(M * W);
-  w.hid = p.take<uint16_t>(M * F);
-  w.abuf = p.take<float>(M * W);
+  w.core = plan_core_ws(p, M, W, F);
   w.patchA = p.take<uint16_t>(MP * h->KP);
   w.tok = p.take<uint16_t>(MP * W);
   w.det = p.take<float>(MP * E);
@@ -550,30 +674,29 @@ int aaclip_forward(AaclipHandle* h, const float* images, int32_t B, void* worksp
   const AaclipCfg& c = h->cfg;
   const int W = c.width, F = c.mlp_dim, E = c.embed_dim, N = h->N, P = h->P;
   const int M = B * N, MP = B * P;
+  int rc;
+  if (!h->folded) {      // first forward: fold ln_1 / ln_2 into the in_proj / c_fc weights (load-time work)
+    if ((rc = fold_blocks(h->blk, h->bf16, W, F, st))) return rc;
+    h->folded = true;
+  }
   uint8_t* wsb = static_cast<uint8_t*>(workspace);
-  float* x = (float*)(wsb + ws.x);
-  uint16_t* xn = (uint16_t*)(wsb + ws.xn);
-  uint16_t* qkv = (uint16_t*)(wsb + ws.qkv);
-  uint16_t* att = (uint16_t*)(wsb + ws.att);
-  uint16_t* hid = (uint16_t*)(wsb + ws.hid);
-  float* abuf = (float*)(wsb + ws.abuf);
   uint16_t* patchA = (uint16_t*)(wsb + ws.patchA);
   uint16_t* tok = (uint16_t*)(wsb + ws.tok);
   float* detbuf = (float*)(wsb + ws.det);
-  int launches = 0;
-  int rc;
   const bool bf = h->bf16;
+  BlockRun run;
+  run.prof = h; run.bf16 = bf; run.items = B; run.tokens = N; run.W = W; run.F = F; run.causal = 0; run.act = c.act;
+  run.x = (float*)(wsb + ws.core.x); run.x16 = (uint16_t*)(wsb + ws.core.x16); run.qkv = (uint16_t*)(wsb + ws.core.qkv);
+  run.att = (uint16_t*)(wsb + ws.core.att); run.hid = (uint16_t*)(wsb + ws.core.hid);
+  run.abuf = (float*)(wsb + ws.core.abuf); run.stats = (float*)(wsb + ws.core.stats); run.st = st;
+  float* x = run.x;
+  int& launches = run.launches;
 
-  // every launch goes through one of these wrappers: launch counting + optional per-class event timing
-  auto gemm = [&](int epi, const void* A, const void* Wt, int m, int n, int k, const GemmEpi& e) -> int {
-    ProfScope ps(h, AACLIP_PROF_GEMM, 2.0 * m * n * k, st);
-    ++launches;
-    return launch_gemm(epi, bf, A, Wt, m, n, k, e, st);
-  };
-  auto lnorm = [&](const float* in, const float* g, const float* bta, void* o16, float* o32, int rows, int skipP) -> int {
+  auto lnorm = [&](const float* in, const float* g, const float* bta, void* o16, float* o32, int rows, int skipP,
+                   float* stats_out) -> int {
     ProfScope ps(h, AACLIP_PROF_LAYERNORM, 0.0, st);
     ++launches;
-    return launch_layernorm(bf, in, g, bta, o16, o32, rows, W, skipP, true, st);
+    return launch_layernorm(bf, in, g, bta, o16, o32, rows, W, skipP, true, st, stats_out, W / 128);
   };
   auto l2norm = [&](float* t, int rows) -> int {
     ProfScope ps(h, AACLIP_PROF_OTHER, 0.0, st);
@@ -594,55 +717,30 @@ int aaclip_forward(AaclipHandle* h, const float* images, int32_t B, void* worksp
   }
   {
     GemmEpi e; e.out_f32 = x; e.ldo = W; e.pos = h->pos; e.patches = P;
-    if ((rc = gemm(EPI_PATCH_F32, patchA, h->w_conv, MP, W, h->KP, e))) return rc;
+    if ((rc = run.gemm(EPI_PATCH_F32, patchA, h->w_conv, MP, W, h->KP, e))) return rc;
   }
   {
     ProfScope ps(h, AACLIP_PROF_OTHER, 0.0, st);
     cls_row_kernel<<<B, 256, 0, st>>>(x, h->cls, h->pos, N, W);
     LAUNCH_CHECK("cls_row_kernel"); ++launches;
   }
-  if ((rc = lnorm(x, h->lnpre_g, h->lnpre_b, nullptr, x, M, 0))) return rc;
+  // ln_pre in place; also emits the 16-bit copy and the LayerNorm partials block 0's folded ln_1 needs
+  if ((rc = lnorm(x, h->lnpre_g, h->lnpre_b, run.x16, x, M, 0, run.stats))) return rc;
 
   // ---- residual attention blocks (model/transformer.py:239-258) + adapters (model/adapter.py:161-172)
   int level_idx = 0;
   for (int i = 0; i < c.layers; ++i) {
-    const BlockW& b = h->blk[i];
-    if ((rc = lnorm(x, b.ln1_g, b.ln1_b, xn, nullptr, M, 0))) return rc;
-    { GemmEpi e; e.bias = b.b_qkv; e.out_16 = qkv; e.ldo = 3 * W;
-      if ((rc = gemm(EPI_BIAS_BF16, xn, b.w_qkv, M, 3 * W, W, e))) return rc; }
-    {
-      ProfScope ps(h, AACLIP_PROF_ATTENTION, 4.0 * B * (W / 64) * (double)N * N * 64, st);
-      ++launches;
-      if ((rc = launch_attention(bf, qkv, att, B, N, W, 0, st))) return rc;
-    }
-    { GemmEpi e; e.bias = b.b_out; e.out_f32 = x; e.ldo = W;
-      if ((rc = gemm(EPI_BIAS_RESID_F32, att, b.w_out, M, W, W, e))) return rc; }
-    if ((rc = lnorm(x, b.ln2_g, b.ln2_b, xn, nullptr, M, 0))) return rc;
-    { GemmEpi e; e.bias = b.b_fc; e.out_16 = hid; e.ldo = F;
-      if ((rc = gemm(c.act == AACLIP_ACT_QUICK_GELU ? EPI_BIAS_QGELU_BF16 : EPI_BIAS_GELU_BF16, xn, b.w_fc, M, F, W, e))) return rc; }
-    const bool adapt = i < c.adapt_until;
-    { GemmEpi e; e.bias = b.b_proj; e.out_f32 = x; e.ldo = W; e.out_16 = adapt ? xn : nullptr;
-      if ((rc = gemm(EPI_BIAS_RESID_F32, hid, b.w_proj, M, W, F, e))) return rc; }
-    if (adapt) {
-      { GemmEpi e; e.out_f32 = abuf; e.ldo = W;
-        if ((rc = gemm(EPI_LEAKY_F32, xn, h->w_adapter[i], M, W, W, e))) return rc; }
-      ProfScope ps(h, AACLIP_PROF_OTHER, 0.0, st);
-      const int grid = (M + 7) / 8;
-      if (W == 1024) adapter_blend_kernel<1024><<<grid, 256, 0, st>>>(x, abuf, M, c.adapt_weight, 1.0f - c.adapt_weight);
-      else adapter_blend_kernel<768><<<grid, 256, 0, st>>>(x, abuf, M, c.adapt_weight, 1.0f - c.adapt_weight);
-      LAUNCH_CHECK("adapter_blend_kernel");
-      ++launches;
-    }
+    if ((rc = run.run(h->blk[i], i < c.adapt_until ? h->w_adapter[i] : nullptr, c.adapt_weight))) return rc;
     if (level_idx < c.n_levels && c.levels[level_idx] == i + 1) {
       float* tok_f32 = (tokens_out != nullptr) ? tokens_out[level_idx] : nullptr;
-      if ((rc = lnorm(x, h->lnpost_g, h->lnpost_b, tok, tok_f32, MP, P))) return rc;
+      if ((rc = lnorm(x, h->lnpost_g, h->lnpost_b, tok, tok_f32, MP, P, nullptr))) return rc;
       const int proj_epi = c.proj_relu ? EPI_LEAKY_F32 : EPI_F32;
       { GemmEpi e; e.out_f32 = seg_out[level_idx]; e.ldo = E;
-        if ((rc = gemm(proj_epi, tok, h->w_seg[level_idx], MP, E, W, e))) return rc; }
+        if ((rc = run.gemm(proj_epi, tok, h->w_seg[level_idx], MP, E, W, e))) return rc; }
       if ((rc = l2norm(seg_out[level_idx], MP))) return rc;
       if (level_idx == c.n_levels - 1) {
         { GemmEpi e; e.out_f32 = detbuf; e.ldo = E;
-          if ((rc = gemm(proj_epi, tok, h->w_det, MP, E, W, e))) return rc; }
+          if ((rc = run.gemm(proj_epi, tok, h->w_det, MP, E, W, e))) return rc; }
         if ((rc = l2norm(detbuf, MP))) return rc;
         ProfScope ps(h, AACLIP_PROF_OTHER, 0.0, st);
         mean_over_patches_kernel<<<dim3((E + 127) / 128, B), 128, 0, st>>>(detbuf, det_out, P, E);
@@ -759,23 +857,19 @@ struct AaclipTextHandle {
   size_t arena_bytes = 0;
   float *tok_emb, *pos, *lnf_g, *lnf_b;
   std::vector<BlockW> blk;
+  bool folded = false;
   std::vector<uint16_t*> w_adapter;  // [W,W] each (SimpleAdapter)
   uint16_t* w_proj;                  // [E,W] final SimpleProj
   std::vector<std::string> missing;
 };
 
-struct TextWsPlan { size_t x, xn, qkv, att, hid, abuf, eot, eot16, total; };
+struct TextWsPlan { CoreWs core; size_t eot, eot16, total; };
 static TextWsPlan plan_text_ws(const AaclipTextHandle* h, int n) {
   const size_t W = h->cfg.width, F = h->cfg.mlp_dim;
   const size_t M = (size_t)n * h->cfg.context;
   ArenaPlan p;
   TextWsPlan w;
-  w.x = p.take<float>(M * W);
-  w.xn = p.take<uint16_t>(M * W);
-  w.qkv = p.take<uint16_t>(M * 3 * W);
-  w.att = p.take<uint16_t>(M * W);
-  w.hid = p.take<uint16_t>(M * F);
-  w.abuf = p.take<float>(M * W);
+  w.core = plan_core_ws(p, M, W, F);
   w.eot = p.take<float>((size_t)n * W);
   w.eot16 = p.take<uint16_t>((size_t)n * W);
   w.total = p.off;
@@ -802,16 +896,8 @@ int aaclip_text_create(const AaclipTextCfg* cfg, AaclipTextHandle** out) {
   ArenaPlan plan;
   const size_t o_tok = plan.take<float>((size_t)c.vocab * W), o_pos = plan.take<float>((size_t)c.context * W);
   const size_t o_lg = plan.take<float>(W), o_lb = plan.take<float>(W);
-  struct BO { size_t ln1g, ln1b, ln2g, ln2b, bqkv, bout, bfc, bproj, wqkv, wout, wfc, wproj; };
-  std::vector<BO> bo(c.layers);
-  for (int i = 0; i < c.layers; ++i) {
-    bo[i].ln1g = plan.take<float>(W); bo[i].ln1b = plan.take<float>(W);
-    bo[i].ln2g = plan.take<float>(W); bo[i].ln2b = plan.take<float>(W);
-    bo[i].bqkv = plan.take<float>(3 * W); bo[i].bout = plan.take<float>(W);
-    bo[i].bfc = plan.take<float>(F); bo[i].bproj = plan.take<float>(W);
-    bo[i].wqkv = plan.take<uint16_t>(3 * W * W); bo[i].wout = plan.take<uint16_t>(W * W);
-    bo[i].wfc = plan.take<uint16_t>(F * W); bo[i].wproj = plan.take<uint16_t>(W * F);
-  }
+  std::vector<BlockOff> bo(c.layers);
+  for (int i = 0; i < c.layers; ++i) bo[i] = plan_block(plan, W, F);
   std::vector<size_t> o_ad(c.adapt_until);
   for (int i = 0; i < c.adapt_until; ++i) o_ad[i] = plan.take<uint16_t>(W * W);
   const size_t o_proj = plan.take<uint16_t>(E * W);
@@ -827,26 +913,13 @@ int aaclip_text_create(const AaclipTextCfg* cfg, AaclipTextHandle** out) {
   h->tok_emb = (float*)(a + o_tok); h->pos = (float*)(a + o_pos);
   h->lnf_g = (float*)(a + o_lg); h->lnf_b = (float*)(a + o_lb);
   h->blk.resize(c.layers);
-  for (int i = 0; i < c.layers; ++i) {
-    BlockW& b = h->blk[i];
-    b.ln1_g = (float*)(a + bo[i].ln1g); b.ln1_b = (float*)(a + bo[i].ln1b);
-    b.ln2_g = (float*)(a + bo[i].ln2g); b.ln2_b = (float*)(a + bo[i].ln2b);
-    b.b_qkv = (float*)(a + bo[i].bqkv); b.b_out = (float*)(a + bo[i].bout);
-    b.b_fc = (float*)(a + bo[i].bfc); b.b_proj = (float*)(a + bo[i].bproj);
-    b.w_qkv = (uint16_t*)(a + bo[i].wqkv); b.w_out = (uint16_t*)(a + bo[i].wout);
-    b.w_fc = (uint16_t*)(a + bo[i].wfc); b.w_proj = (uint16_t*)(a + bo[i].wproj);
-  }
+  for (int i = 0; i < c.layers; ++i) bind_block(h->blk[i], a, bo[i]);
   for (int i = 0; i < c.adapt_until; ++i) h->w_adapter.push_back((uint16_t*)(a + o_ad[i]));
   h->w_proj = (uint16_t*)(a + o_proj);
   auto need = [&](const std::string& k) { h->missing.push_back(k); };
   need("token_embedding.weight"); need("positional_embedding"); need("ln_final.weight"); need("ln_final.bias");
-  for (int i = 0; i < c.layers; ++i) {
-    const std::string p = "blk." + std::to_string(i) + ".";
-    for (const char* s : {"ln_1.weight", "ln_1.bias", "ln_2.weight", "ln_2.bias", "attn.in_proj_weight",
-                          "attn.in_proj_bias", "attn.out_proj.weight", "attn.out_proj.bias", "mlp.c_fc.weight",
-                          "mlp.c_fc.bias", "mlp.c_proj.weight", "mlp.c_proj.bias"})
-      need(p + s);
-  }
+  for (int i = 0; i < c.layers; ++i)
+    for (const char* t : kBlockTensors) need("blk." + std::to_string(i) + "." + t);
   for (int i = 0; i <= c.adapt_until; ++i) need("text_adapter." + std::to_string(i));
   *out = h;
   return AACLIP_OK;
@@ -854,6 +927,7 @@ int aaclip_text_create(const AaclipTextCfg* cfg, AaclipTextHandle** out) {
 
 void aaclip_text_destroy(AaclipTextHandle* h) {
   if (h == nullptr) return;
+  free_block_staging(h->blk);
   if (h->arena) cudaFree(h->arena);
   delete h;
 }
@@ -869,20 +943,16 @@ int aaclip_text_set_weight(AaclipTextHandle* h, const char* name, const float* d
   const int64_t n = numel(shape, ndim);
   std::string k(name);
   if (k.rfind("clipmodel.", 0) == 0) k = k.substr(strlen("clipmodel."));
-  auto loaded = [&](const std::string& key) {
-    for (size_t i = 0; i < h->missing.size(); ++i)
-      if (h->missing[i] == key) { h->missing.erase(h->missing.begin() + i); return; }
-  };
   auto copy_f32 = [&](float* dst, int64_t expect, const std::string& key) -> int {
     if (n != expect) return fail(AACLIP_EINVAL, "%s: expected %lld elements, got %lld", name, (long long)expect, (long long)n);
     CUDA_TRY(cudaMemcpyAsync(dst, data, expect * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    loaded(key);
+    erase_key(h->missing, key);
     return AACLIP_OK;
   };
   auto pack = [&](uint16_t* dst, int64_t R, int64_t C, const std::string& key) -> int {
     if (n != R * C) return fail(AACLIP_EINVAL, "%s: expected %lld x %lld elements, got %lld", name, (long long)R, (long long)C, (long long)n);
     if (int rc = launch_pack(h->bf16, data, dst, R, C, C, st)) return rc;
-    loaded(key);
+    erase_key(h->missing, key);
     return AACLIP_OK;
   };
   if (k == "token_embedding.weight") return copy_f32(h->tok_emb, (int64_t)c.vocab * W, k);
@@ -893,21 +963,8 @@ int aaclip_text_set_weight(AaclipTextHandle* h, const char* name, const float* d
   char tail[96];
   if (sscanf(k.c_str(), "transformer.resblocks.%d.%95s", &idx, tail) == 2) {
     if (idx < 0 || idx >= c.layers) return fail(AACLIP_EINVAL, "%s: block index out of range", name);
-    BlockW& b = h->blk[idx];
-    const std::string t(tail), key = "blk." + std::to_string(idx) + "." + t;
-    if (t == "ln_1.weight") return copy_f32(b.ln1_g, W, key);
-    if (t == "ln_1.bias") return copy_f32(b.ln1_b, W, key);
-    if (t == "ln_2.weight") return copy_f32(b.ln2_g, W, key);
-    if (t == "ln_2.bias") return copy_f32(b.ln2_b, W, key);
-    if (t == "attn.in_proj_bias") return copy_f32(b.b_qkv, 3 * W, key);
-    if (t == "attn.out_proj.bias") return copy_f32(b.b_out, W, key);
-    if (t == "mlp.c_fc.bias") return copy_f32(b.b_fc, F, key);
-    if (t == "mlp.c_proj.bias") return copy_f32(b.b_proj, W, key);
-    if (t == "attn.in_proj_weight") return pack(b.w_qkv, 3 * W, W, key);
-    if (t == "attn.out_proj.weight") return pack(b.w_out, W, W, key);
-    if (t == "mlp.c_fc.weight") return pack(b.w_fc, F, W, key);
-    if (t == "mlp.c_proj.weight") return pack(b.w_proj, W, F, key);
-    return fail(AACLIP_EINVAL, "%s: unknown block tensor", name);
+    return set_block_tensor(h->blk[idx], tail, "blk." + std::to_string(idx) + "." + tail, h->missing, h->folded, h->bf16,
+                            W, F, name, data, n, st);
   }
   if (sscanf(k.c_str(), "text_adapter.%d.%95s", &idx, tail) == 2) {
     if (strcmp(tail, "fc.0.weight") != 0) return fail(AACLIP_EINVAL, "%s: unknown tensor", name);
@@ -937,46 +994,30 @@ int aaclip_encode_text(AaclipTextHandle* h, const int32_t* tokens, int32_t n, vo
   const int W = c.width, F = c.mlp_dim, E = c.embed_dim, T = c.context;
   const int M = n * T;
   const bool bf = h->bf16;
+  int rc;
+  if (!h->folded) {
+    if ((rc = fold_blocks(h->blk, bf, W, F, st))) return rc;
+    h->folded = true;
+  }
   uint8_t* wsb = static_cast<uint8_t*>(workspace);
-  float* x = (float*)(wsb + ws.x);
-  uint16_t* xn = (uint16_t*)(wsb + ws.xn);
-  uint16_t* qkv = (uint16_t*)(wsb + ws.qkv);
-  uint16_t* att = (uint16_t*)(wsb + ws.att);
-  uint16_t* hid = (uint16_t*)(wsb + ws.hid);
-  float* abuf = (float*)(wsb + ws.abuf);
+  BlockRun run;
+  run.prof = nullptr; run.bf16 = bf; run.items = n; run.tokens = T; run.W = W; run.F = F; run.causal = 1; run.act = c.act;
+  run.x = (float*)(wsb + ws.core.x); run.x16 = (uint16_t*)(wsb + ws.core.x16); run.qkv = (uint16_t*)(wsb + ws.core.qkv);
+  run.att = (uint16_t*)(wsb + ws.core.att); run.hid = (uint16_t*)(wsb + ws.core.hid);
+  run.abuf = (float*)(wsb + ws.core.abuf); run.stats = (float*)(wsb + ws.core.stats); run.st = st;
   float* eot = (float*)(wsb + ws.eot);
   uint16_t* eot16 = (uint16_t*)(wsb + ws.eot16);
-  int rc;
 
-  // token + positional embedding (model/adapter.py:277-281)
-  text_embed_kernel<<<M, 192, 0, st>>>(tokens, h->tok_emb, h->pos, x, T, W, c.vocab);
+  // token + positional embedding (model/adapter.py:277-281); an identity-LayerNorm pass (NORMALIZE=false) then
+  // produces the raw 16-bit copy and the LayerNorm partials block 0's folded ln_1 needs
+  text_embed_kernel<<<M, 192, 0, st>>>(tokens, h->tok_emb, h->pos, run.x, T, W, c.vocab);
   LAUNCH_CHECK("text_embed_kernel");
+  if ((rc = launch_layernorm(bf, run.x, nullptr, nullptr, run.x16, nullptr, M, W, 0, /*normalize=*/false, st, run.stats, W / 128))) return rc;
   // 12 causal residual attention blocks + adapters (model/adapter.py:284-295)
-  for (int i = 0; i < c.layers; ++i) {
-    const BlockW& b = h->blk[i];
-    if ((rc = launch_layernorm(bf, x, b.ln1_g, b.ln1_b, xn, nullptr, M, W, 0, true, st))) return rc;
-    { GemmEpi e; e.bias = b.b_qkv; e.out_16 = qkv; e.ldo = 3 * W;
-      if ((rc = launch_gemm(EPI_BIAS_BF16, bf, xn, b.w_qkv, M, 3 * W, W, e, st))) return rc; }
-    if ((rc = launch_attention(bf, qkv, att, n, T, W, /*causal=*/1, st))) return rc;
-    { GemmEpi e; e.bias = b.b_out; e.out_f32 = x; e.ldo = W;
-      if ((rc = launch_gemm(EPI_BIAS_RESID_F32, bf, att, b.w_out, M, W, W, e, st))) return rc; }
-    if ((rc = launch_layernorm(bf, x, b.ln2_g, b.ln2_b, xn, nullptr, M, W, 0, true, st))) return rc;
-    { GemmEpi e; e.bias = b.b_fc; e.out_16 = hid; e.ldo = F;
-      if ((rc = launch_gemm(c.act == AACLIP_ACT_QUICK_GELU ? EPI_BIAS_QGELU_BF16 : EPI_BIAS_GELU_BF16, bf, xn, b.w_fc, M, F, W, e, st))) return rc; }
-    const bool adapt = i < c.adapt_until;
-    { GemmEpi e; e.bias = b.b_proj; e.out_f32 = x; e.ldo = W; e.out_16 = adapt ? xn : nullptr;
-      if ((rc = launch_gemm(EPI_BIAS_RESID_F32, bf, hid, b.w_proj, M, W, F, e, st))) return rc; }
-    if (adapt) {
-      { GemmEpi e; e.out_f32 = abuf; e.ldo = W;
-        if ((rc = launch_gemm(EPI_LEAKY_F32, bf, xn, h->w_adapter[i], M, W, W, e, st))) return rc; }
-      const int grid = (M + 7) / 8;
-      if (W == 1024) adapter_blend_kernel<1024><<<grid, 256, 0, st>>>(x, abuf, M, c.adapt_weight, 1.0f - c.adapt_weight);
-      else adapter_blend_kernel<768><<<grid, 256, 0, st>>>(x, abuf, M, c.adapt_weight, 1.0f - c.adapt_weight);
-      LAUNCH_CHECK("adapter_blend_kernel");
-    }
-  }
+  for (int i = 0; i < c.layers; ++i)
+    if ((rc = run.run(h->blk[i], i < c.adapt_until ? h->w_adapter[i] : nullptr, c.adapt_weight))) return rc;
   // EOT row -> ln_final -> SimpleProj + LeakyReLU (model/adapter.py:296-298)
-  text_gather_eot_kernel<<<n, 192, 0, st>>>(tokens, x, eot, T, W);
+  text_gather_eot_kernel<<<n, 192, 0, st>>>(tokens, run.x, eot, T, W);
   LAUNCH_CHECK("text_gather_eot_kernel");
   if ((rc = launch_layernorm(bf, eot, h->lnf_g, h->lnf_b, eot16, nullptr, n, W, 0, true, st))) return rc;
   { GemmEpi e; e.out_f32 = out; e.ldo = E;
@@ -1001,7 +1042,7 @@ int aaclip_gemm16(int32_t dtype, const void* A, const void* W, int32_t M, int32_
                   const float* bias, float* out_f32, void* out_16, int32_t ldo, void* stream) {
   if (!A || !W) return fail(AACLIP_EINVAL, "aaclip_gemm16: null operand");
   if (dtype != AACLIP_DT_F16 && dtype != AACLIP_DT_BF16) return fail(AACLIP_EINVAL, "aaclip_gemm16: bad dtype %d", dtype);
-  if (epi == EPI_PATCH_F32) return fail(AACLIP_EINVAL, "aaclip_gemm16: patch epilogue is internal");
+  if (epi == EPI_PATCH_F32 || epi < 0 || epi > EPI_BIAS_F32) return fail(AACLIP_EINVAL, "aaclip_gemm16: epilogue %d is not available here (folded-LayerNorm epilogues: aaclip_gemm16_ln)", epi);
   const bool needs_bias = epi == EPI_BIAS_BF16 || epi == EPI_BIAS_GELU_BF16 || epi == EPI_BIAS_QGELU_BF16 ||
                           epi == EPI_BIAS_RESID_F32 || epi == EPI_BIAS_F32;
   const bool out16 = epi == EPI_BIAS_BF16 || epi == EPI_BIAS_GELU_BF16 || epi == EPI_BIAS_QGELU_BF16;
@@ -1012,6 +1053,45 @@ int aaclip_gemm16(int32_t dtype, const void* A, const void* W, int32_t M, int32_
   GemmEpi e;
   e.bias = bias; e.out_f32 = out_f32; e.out_16 = reinterpret_cast<uint16_t*>(out_16); e.ldo = ldo;
   return launch_gemm(epi, dtype == AACLIP_DT_BF16, A, W, M, N, K, e, static_cast<cudaStream_t>(stream));
+}
+
+int aaclip_ln_fold(int32_t dtype, const float* W, const float* b, const float* gamma, const float* beta, int32_t N,
+                   int32_t K, void* W16, float* colsum, float* bias_f, void* stream) {
+  if (!W || !b || !gamma || !beta || !W16 || !colsum || !bias_f || N <= 0 || K <= 0)
+    return fail(AACLIP_EINVAL, "aaclip_ln_fold: bad argument");
+  if (dtype != AACLIP_DT_F16 && dtype != AACLIP_DT_BF16) return fail(AACLIP_EINVAL, "aaclip_ln_fold: bad dtype %d", dtype);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint16_t* o = reinterpret_cast<uint16_t*>(W16);
+  if (dtype == AACLIP_DT_BF16) ln_fold_kernel<true><<<(N + 7) / 8, 256, 0, st>>>(W, b, gamma, beta, o, colsum, bias_f, N, K);
+  else ln_fold_kernel<false><<<(N + 7) / 8, 256, 0, st>>>(W, b, gamma, beta, o, colsum, bias_f, N, K);
+  LAUNCH_CHECK("ln_fold_kernel");
+  return AACLIP_OK;
+}
+
+int aaclip_gemm16_ln(int32_t dtype, const void* A, const void* W16, int32_t M, int32_t N, int32_t K, int32_t epi,
+                     const float* bias_f, const float* colsum, const float* stats, int32_t n_partials,
+                     int32_t ln_width, void* out_16, int32_t ldo, void* stream) {
+  if (!A || !W16 || !bias_f || !colsum || !stats || !out_16) return fail(AACLIP_EINVAL, "aaclip_gemm16_ln: null argument");
+  if (dtype != AACLIP_DT_F16 && dtype != AACLIP_DT_BF16) return fail(AACLIP_EINVAL, "aaclip_gemm16_ln: bad dtype %d", dtype);
+  if (epi != EPI_LN_BIAS_BF16 && epi != EPI_LN_BIAS_GELU_BF16 && epi != EPI_LN_BIAS_QGELU_BF16)
+    return fail(AACLIP_EINVAL, "aaclip_gemm16_ln: epilogue %d is not a folded-LayerNorm epilogue", epi);
+  if (n_partials < 1 || n_partials > 8 || ln_width <= 0) return fail(AACLIP_EINVAL, "aaclip_gemm16_ln: n_partials must be 1..8");
+  if (ldo < N || ldo % 8 != 0) return fail(AACLIP_EINVAL, "aaclip_gemm16_ln: ldo must be >= N and a multiple of 8");
+  GemmEpi e;
+  e.bias = bias_f; e.colsum = colsum; e.stats = stats; e.n_partials = n_partials; e.inv_width = 1.0f / ln_width;
+  e.out_16 = reinterpret_cast<uint16_t*>(out_16); e.ldo = ldo;
+  return launch_gemm(epi, dtype == AACLIP_DT_BF16, A, W16, M, N, K, e, static_cast<cudaStream_t>(stream));
+}
+
+int aaclip_gemm16_resid(int32_t dtype, const void* A, const void* W, int32_t M, int32_t N, int32_t K,
+                        const float* bias, float* x, void* x16_out, float* stats_out, int32_t ldo, void* stream) {
+  if (!A || !W || !bias || !x) return fail(AACLIP_EINVAL, "aaclip_gemm16_resid: null argument");
+  if (dtype != AACLIP_DT_F16 && dtype != AACLIP_DT_BF16) return fail(AACLIP_EINVAL, "aaclip_gemm16_resid: bad dtype %d", dtype);
+  if (ldo < N || ldo % 8 != 0) return fail(AACLIP_EINVAL, "aaclip_gemm16_resid: ldo must be >= N and a multiple of 8");
+  if (stats_out && N > 1024) return fail(AACLIP_EINVAL, "aaclip_gemm16_resid: statistics need N <= 1024 (8 partials)");
+  GemmEpi e;
+  e.bias = bias; e.out_f32 = x; e.out_16 = reinterpret_cast<uint16_t*>(x16_out); e.stats_out = stats_out; e.ldo = ldo;
+  return launch_gemm(EPI_BIAS_RESID_F32, dtype == AACLIP_DT_BF16, A, W, M, N, K, e, static_cast<cudaStream_t>(stream));
 }
 
 int aaclip_attention(int32_t dtype, const void* qkv, void* out, int32_t B, int32_t N, int32_t D, int32_t causal,

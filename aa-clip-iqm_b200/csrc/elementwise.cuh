@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <limits.h>
 #include "ptx.cuh"
@@ -55,10 +56,14 @@ __global__ void cls_row_kernel(float* __restrict__ x, const float* __restrict__ 
 // ln_1, ln_2, ln_post, ln_final). Two-pass in registers: mean, then sum of squared deviations.
 // skipP > 0: output row r = b*skipP + p reads input row b*(skipP+1) + 1 + p (drops the CLS row: x[1:], adapter.py:172).
 // NORMALIZE=false degrades to a plain fp32 -> bf16 cast (operand staging for the adapter GEMM).
+// stats_out != nullptr additionally emits (sum, sum of squares) of the OUTPUT row as partial 0 of stats_out[row][np][2]
+// (partials 1..np-1 zeroed): the LayerNorm statistics the next GEMM's folded-LN epilogue needs when this kernel
+// produces the residual stream (ln_pre).
 template <int D, bool NORMALIZE, bool BF16>
 __global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, uint16_t* __restrict__ out_bf16,
-                                 float* __restrict__ out_f32, int rows, int skipP, float eps) {
+                                 float* __restrict__ out_f32, int rows, int skipP, float eps,
+                                 float* __restrict__ stats_out = nullptr, int np = 0) {
   constexpr int V = D / 128;  // float4 per lane
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -106,15 +111,30 @@ __global__ void layernorm_kernel(const float* __restrict__ x, const float* __res
 #pragma unroll
     for (int j = 0; j < V; ++j) o[lane + 32 * j] = v[j];
   }
+  if (stats_out != nullptr) {
+    float s = 0.f, q = 0.f;
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+      q += (v[j].x * v[j].x + v[j].y * v[j].y) + (v[j].z * v[j].z + v[j].w * v[j].w);
+    }
+    s = warp_sum(s);
+    q = warp_sum(q);
+    float2* o = reinterpret_cast<float2*>(stats_out) + static_cast<size_t>(warp) * np;
+    if (lane < np) o[lane] = (lane == 0) ? make_float2(s, q) : make_float2(0.f, 0.f);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // Residual adapter blend (model/adapter.py:163-170 visual, :286-295 text):
 //   a <- a * ||x||_2 / ||a||_2  (per token, no eps) ;  x <- w*a + (1-w)*x.   a = LeakyReLU(x W^T) from the GEMM.
 // Optionally also emits bf16(x_new) (operand for the next GEMM). One warp per row.
-template <int D>
+// x16 != nullptr: also the 16-bit copy of the new x (A operand of the next GEMM); stats_out: its LayerNorm partials
+// (same format as layernorm_kernel's stats_out).
+template <int D, bool BF16>
 __global__ void adapter_blend_kernel(float* __restrict__ x, const float* __restrict__ a, int rows, float w,
-                                     float one_minus_w) {
+                                     float one_minus_w, uint16_t* __restrict__ x16 = nullptr,
+                                     float* __restrict__ stats_out = nullptr, int np = 0) {
   constexpr int V = D / 128;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -131,6 +151,7 @@ __global__ void adapter_blend_kernel(float* __restrict__ x, const float* __restr
     sa += (av[j].x * av[j].x + av[j].y * av[j].y) + (av[j].z * av[j].z + av[j].w * av[j].w);
   }
   const float nx = sqrtf(warp_sum(sx)), na = sqrtf(warp_sum(sa));
+  float s = 0.f, q = 0.f;
 #pragma unroll
   for (int j = 0; j < V; ++j) {
     float4 o;
@@ -139,6 +160,52 @@ __global__ void adapter_blend_kernel(float* __restrict__ x, const float* __restr
     o.z = w * (av[j].z * nx / na) + one_minus_w * xv[j].z;
     o.w = w * (av[j].w * nx / na) + one_minus_w * xv[j].w;
     xr[lane + 32 * j] = o;
+    if (x16 != nullptr)
+      reinterpret_cast<uint2*>(x16 + static_cast<size_t>(warp) * D)[lane + 32 * j] =
+          make_uint2(ptx::pack16<BF16>(o.x, o.y), ptx::pack16<BF16>(o.z, o.w));
+    s += (o.x + o.y) + (o.z + o.w);
+    q += (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w);
+  }
+  if (stats_out != nullptr) {
+    s = warp_sum(s);
+    q = warp_sum(q);
+    float2* o = reinterpret_cast<float2*>(stats_out) + static_cast<size_t>(warp) * np;
+    if (lane < np) o[lane] = (lane == 0) ? make_float2(s, q) : make_float2(0.f, 0.f);
+  }
+}
+
+// LayerNorm folding at weight-load time (model/transformer.py:245-254: LN followed by a Linear):
+//   W'[n,k] = W[n,k] * gamma[k] (rounded to the 16-bit operand type),  colsum[n] = sum_k W'_16[n,k],
+//   bias'[n] = b[n] + sum_k W[n,k] * beta[k].
+// The GEMM then consumes the RAW residual stream: LN(x) W^T + b = rstd * (x W'^T - mean * colsum) + bias'.
+// colsum is taken over the ROUNDED W' so that the mean term cancels exactly what the tensor core accumulates.
+// One warp per output feature n; fixed summation order.
+template <bool BF16>
+__global__ void ln_fold_kernel(const float* __restrict__ W, const float* __restrict__ b,
+                               const float* __restrict__ gamma, const float* __restrict__ beta,
+                               uint16_t* __restrict__ W16, float* __restrict__ colsum, float* __restrict__ bias_f,
+                               int N, int K) {
+  const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (n >= N) return;
+  const float* wr = W + static_cast<size_t>(n) * K;
+  uint16_t* o = W16 + static_cast<size_t>(n) * K;
+  float cs = 0.f, bs = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float w = wr[k];
+    const uint16_t h = ptx::cvt16<BF16>(w * gamma[k]);
+    o[k] = h;
+    float hv;
+    if constexpr (BF16) hv = __uint_as_float(static_cast<uint32_t>(h) << 16);
+    else hv = __half2float(__ushort_as_half(h));
+    cs += hv;
+    bs = fmaf(w, beta[k], bs);
+  }
+  cs = warp_sum(cs);
+  bs = warp_sum(bs);
+  if (lane == 0) {
+    colsum[n] = cs;
+    bias_f[n] = b[n] + bs;
   }
 }
 

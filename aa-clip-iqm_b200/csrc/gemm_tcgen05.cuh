@@ -1,16 +1,18 @@
 // Persistent, warp-specialised tcgen05 GEMM for sm_100a:  C[M,N] = A[M,K] * W[N,K]^T  (+ fused epilogue)
 //
 //   A : fp16|bf16 row-major [M,K] (activations, token-major)         -- TMA, SWIZZLE_128B, box 64(K) x 128(M)
-//   W : fp16|bf16 row-major [N,K] (nn.Linear weight layout, K-major) -- TMA, SWIZZLE_128B, box 64(K) x 256(N)
-//   D : fp32 accumulator in TMEM, 128 lanes x 256 columns, double-buffered (512 columns)
+//   W : fp16|bf16 row-major [N,K] (nn.Linear weight layout, K-major) -- TMA, SWIZZLE_128B, box 64(K) x 128(N half)
+//   D : fp32 accumulator in TMEM, 128 lanes x 256 columns per CTA, double-buffered (512 columns)
 //
-// Roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one lane) + TMEM owner,
+// One cluster of 2 CTAs (tcgen05 cta_group::2) computes a 256 x 256 output tile; see gemm_pair_kernel below.
+// Roles per CTA (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer (leader CTA only) + TMEM owner,
 // warps 2..9 = epilogue (TMEM -> registers -> swizzled smem transpose -> fused math -> row-coalesced global
 // accesses). The epilogue of tile i overlaps the main loop of tile i+1 through the second TMEM accumulator stage.
 //
 // Replaces, on the reference's path: F.linear / addmm calls inside nn.MultiheadAttention
 // (model/transformer.py:200,237), the MLP (model/transformer.py:211-219), SimpleAdapter / SimpleProj
-// (model/adapter_modules.py:6-26) and the patch-embedding conv (model/adapter.py:139).
+// (model/adapter_modules.py:6-26), the patch-embedding conv (model/adapter.py:139) and -- folded into the epilogues
+// of the GEMMs that consume / produce the residual stream -- the LayerNorms ln_1 / ln_2 (model/transformer.py:245,252).
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -28,6 +30,11 @@ enum EpiMode : int {
   EPI_LEAKY_F32 = 5,       // out_f32 = leaky_relu(acc, 0.01)          (nn.LeakyReLU default slope)
   EPI_PATCH_F32 = 6,       // out_f32[b*(P+1)+1+p, :] = acc + pos[p+1, :]   (m = b*P + p)
   EPI_BIAS_F32 = 7,        // out_f32 = acc + bias
+  // LayerNorm folded into the consuming GEMM: A is the RAW 16-bit copy of the residual stream, W already carries
+  // gamma (W' = W diag(gamma)), and  LN(x) W^T + b  =  rstd * (x W'^T - mean * colsum(W')) + (b + W beta):
+  EPI_LN_BIAS_BF16 = 8,       // out_16 = rstd*(acc - mean*colsum) + bias'
+  EPI_LN_BIAS_GELU_BF16 = 9,  // out_16 = gelu_erf(...)
+  EPI_LN_BIAS_QGELU_BF16 = 10,
 };
 
 struct GemmEpi {
@@ -37,19 +44,16 @@ struct GemmEpi {
   const float* pos = nullptr;         // EPI_PATCH_F32: positional embedding [(P+1), N]
   int ldo = 0;                        // leading dimension of the outputs, in elements
   int patches = 0;                    // EPI_PATCH_F32: P
+  // LayerNorm statistics of the residual stream, as per-row partial sums [rows][n_partials][2] = (sum, sum of squares)
+  // over disjoint column ranges; a row's mean / rstd are finished by whoever consumes it (fixed order: batch-invariant)
+  const float* stats = nullptr;       // EPI_LN_*: statistics of the A rows
+  const float* colsum = nullptr;      // EPI_LN_*: [N] column sums of the 16-bit W' actually multiplied
+  float* stats_out = nullptr;         // EPI_BIAS_RESID_F32 (optional): statistics of the new residual rows, N/128 partials
+  int n_partials = 0;                 // EPI_LN_*: partials per row in `stats`
+  float inv_width = 0.f;              // EPI_LN_*: 1 / (LayerNorm width)
+  float eps = 1e-5f;
 };
 
-namespace gemm_cfg {
-constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;
-constexpr int A_BYTES = BM * BK * 2;             // 16 KiB
-constexpr int B_BYTES = BN * BK * 2;             // 32 KiB
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;   // 48 KiB
-constexpr int THREADS = 320;                     // 10 warps
-constexpr int EPI_WARPS = 8;
-constexpr int TMEM_COLS = 512;                   // 2 accumulator stages x 256 columns
-constexpr int EPI_STAGE_BYTES = 32 * 128;        // per epilogue warp: 32 rows x 32 fp32, swizzled
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 512 /*barriers*/ + EPI_WARPS * EPI_STAGE_BYTES + 1024 /*align*/;
-}  // namespace gemm_cfg
 
 // erf-GELU, x * Phi(x), with erf from Abramowitz & Stegun 7.1.26 (|abs err| <= 1.5e-7, far below the 16-bit store):
 //   erf(z) = 1 - (a1 t + ... + a5 t^5) exp(-z^2),  t = 1/(1 + p z),  z >= 0.
@@ -74,207 +78,60 @@ __device__ __forceinline__ float quick_gelu(float x) { return x / (1.0f + __expf
 template <int EPI>
 __host__ __device__ constexpr bool epi_has_bias() {
   return EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_QGELU_BF16 ||
-         EPI == EPI_BIAS_RESID_F32 || EPI == EPI_BIAS_F32;
+         EPI == EPI_BIAS_RESID_F32 || EPI == EPI_BIAS_F32 || EPI == EPI_LN_BIAS_BF16 ||
+         EPI == EPI_LN_BIAS_GELU_BF16 || EPI == EPI_LN_BIAS_QGELU_BF16;
 }
 
-// `b` = bias[n..n+3], loaded once per 32-column chunk by the caller (it does not depend on the row).
+template <int EPI>
+__host__ __device__ constexpr bool epi_is_ln() {
+  return EPI == EPI_LN_BIAS_BF16 || EPI == EPI_LN_BIAS_GELU_BF16 || EPI == EPI_LN_BIAS_QGELU_BF16;
+}
+
+// `b` = bias[n..n+3] (and `cs` = colsum[n..n+3]) are loaded once per 32-column chunk by the caller; `mean` / `rstd`
+// are the LayerNorm statistics of this row (EPI_LN_* only). Returns the fp32 value written (EPI_BIAS_RESID_F32).
 template <int EPI, bool BF16>
-__device__ __forceinline__ void epilogue_apply(float4 v, int row, int n, const GemmEpi& e, float4 b,
-                                               float4 resid = make_float4(0.f, 0.f, 0.f, 0.f)) {
-  if constexpr (epi_has_bias<EPI>()) {
+__device__ __forceinline__ float4 epilogue_apply(float4 v, int row, int n, const GemmEpi& e, float4 b,
+                                                 float4 resid = make_float4(0.f, 0.f, 0.f, 0.f),
+                                                 float4 cs = make_float4(0.f, 0.f, 0.f, 0.f), float mean = 0.f,
+                                                 float rstd = 1.f) {
+  if constexpr (epi_is_ln<EPI>()) {
+    v.x = fmaf(rstd, fmaf(-mean, cs.x, v.x), b.x); v.y = fmaf(rstd, fmaf(-mean, cs.y, v.y), b.y);
+    v.z = fmaf(rstd, fmaf(-mean, cs.z, v.z), b.z); v.w = fmaf(rstd, fmaf(-mean, cs.w, v.w), b.w);
+  } else if constexpr (epi_has_bias<EPI>()) {
     v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
   }
-  if constexpr (EPI == EPI_BIAS_GELU_BF16) {
+  if constexpr (EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_LN_BIAS_GELU_BF16) {
     v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
   }
-  if constexpr (EPI == EPI_BIAS_QGELU_BF16) {
+  if constexpr (EPI == EPI_BIAS_QGELU_BF16 || EPI == EPI_LN_BIAS_QGELU_BF16) {
     v.x = quick_gelu(v.x); v.y = quick_gelu(v.y); v.z = quick_gelu(v.z); v.w = quick_gelu(v.w);
   }
   if constexpr (EPI == EPI_LEAKY_F32) {
     v.x = v.x > 0.f ? v.x : 0.01f * v.x; v.y = v.y > 0.f ? v.y : 0.01f * v.y;
     v.z = v.z > 0.f ? v.z : 0.01f * v.z; v.w = v.w > 0.f ? v.w : 0.01f * v.w;
   }
-  if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_QGELU_BF16) {
+  if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_QGELU_BF16 || epi_is_ln<EPI>()) {
     *reinterpret_cast<uint2*>(e.out_16 + static_cast<size_t>(row) * e.ldo + n) =
         make_uint2(ptx::pack16<BF16>(v.x, v.y), ptx::pack16<BF16>(v.z, v.w));
   } else if constexpr (EPI == EPI_BIAS_RESID_F32) {
     float4* o = reinterpret_cast<float4*>(e.out_f32 + static_cast<size_t>(row) * e.ldo + n);
-    float4 x = resid;   // loaded by the caller, 8 rows in flight, before the TMEM load
-    x.x += v.x; x.y += v.y; x.z += v.z; x.w += v.w;
-    *o = x;
+    v.x += resid.x; v.y += resid.y; v.z += resid.z; v.w += resid.w;   // residual loaded by the caller, 8 rows in flight
+    *o = v;
     if (e.out_16 != nullptr)
       *reinterpret_cast<uint2*>(e.out_16 + static_cast<size_t>(row) * e.ldo + n) =
-          make_uint2(ptx::pack16<BF16>(x.x, x.y), ptx::pack16<BF16>(x.z, x.w));
+          make_uint2(ptx::pack16<BF16>(v.x, v.y), ptx::pack16<BF16>(v.z, v.w));
   } else {
     size_t orow = static_cast<size_t>(row);
     if constexpr (EPI == EPI_PATCH_F32) {
-      const int b = row / e.patches, p = row - b * e.patches;
-      orow = static_cast<size_t>(b) * (e.patches + 1) + 1 + p;
+      const int bi = row / e.patches, p = row - bi * e.patches;
+      orow = static_cast<size_t>(bi) * (e.patches + 1) + 1 + p;
       const float4 q = __ldg(reinterpret_cast<const float4*>(e.pos + static_cast<size_t>(p + 1) * e.ldo + n));
       v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
     }
     *reinterpret_cast<float4*>(e.out_f32 + orow * e.ldo + n) = v;
   }
+  return v;
 }
-
-template <int EPI, bool BF16>
-__global__ void __launch_bounds__(gemm_cfg::THREADS, 1)
-gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, int M,
-                    int N, int K, GemmEpi epi) {
-  using namespace gemm_cfg;
-  extern __shared__ uint8_t smem_raw[];
-  // SWIZZLE_128B operand tiles need 1024-byte alignment
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
-  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int m_tiles = (M + BM - 1) / BM;
-  const int n_tiles = N / BN;
-  const int num_tiles = m_tiles * n_tiles;
-  const int num_kb = K / BK;
-
-  if (warp == 0 && lane == 0) {
-    ptx::prefetch_tmap(&tmap_a);
-    ptx::prefetch_tmap(&tmap_b);
-    for (int s = 0; s < STAGES; ++s) {
-      ptx::mbar_init(&full_bar[s], 1);
-      ptx::mbar_init(&empty_bar[s], 1);
-    }
-    for (int s = 0; s < 2; ++s) {
-      ptx::mbar_init(&tmem_full_bar[s], 1);
-      ptx::mbar_init(&tmem_empty_bar[s], EPI_WARPS);
-    }
-    ptx::fence_mbar_init();
-  }
-  if (warp == 1) {
-    ptx::tmem_alloc<TMEM_COLS>(tmem_base_smem);
-    ptx::tmem_relinquish();
-  }
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::tc_fence_after();
-  const uint32_t tmem_base = *tmem_base_smem;
-
-  if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-          ptx::mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
-          uint8_t* sa = smem + stage * STAGE_BYTES;
-          ptx::tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m_blk * BM);
-          ptx::tma_load_2d(sa + A_BYTES, &tmap_b, &full_bar[stage], kb * BK, n_blk * BN);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (single thread) =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = ptx::make_idesc_16(BM, BN, 0, BF16);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
-        ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          ptx::mbar_wait(&full_bar[stage], phase);
-          ptx::tc_fence_after();
-          const uint32_t sa = ptx::smem_u32(smem + stage * STAGE_BYTES);
-          const uint64_t a_desc = ptx::make_sw128_desc(sa);
-          const uint64_t b_desc = ptx::make_sw128_desc(sa + A_BYTES);
-#pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // advance 16 bf16 = 32 B along K inside the 128-B swizzle row: +2 in the (addr>>4) field
-            ptx::tc_mma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-          }
-          ptx::tc_commit(&empty_bar[stage]);                       // frees the smem slot when the MMAs retire
-          if (kb == num_kb - 1) ptx::tc_commit(&tmem_full_bar[acc]);  // accumulator complete
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
-        }
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-      }
-    }
-  } else {
-    // ===================== epilogue warps =====================
-    const int e = warp - 2;
-    const int q = warp & 3;        // TMEM lane quarter this warp may access
-    const int half = e >> 2;       // which 128 of the 256 accumulator columns
-    const uint32_t stage_u32 = ptx::smem_u32(smem + STAGES * STAGE_BYTES + 512 + e * EPI_STAGE_BYTES);  // transpose buffer
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
-      ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
-      ptx::tc_fence_after();
-      const int row0 = m_blk * BM + q * 32;   // first of this warp's 32 rows
-      const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + half * 128;
-      const int sub = lane >> 3, unit = lane & 7;   // coalesced domain: 4 rows x (8 lanes x 16 B) per instruction
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        const int n = n_blk * BN + half * 128 + c * 32 + unit * 4;
-        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if constexpr (epi_has_bias<EPI>()) bias4 = __ldg(reinterpret_cast<const float4*>(epi.bias + n));
-        float4 resid[8];
-        if constexpr (EPI == EPI_BIAS_RESID_F32) {
-          // residual rows for this chunk: 8 independent coalesced loads issued before the TMEM load / transpose
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int rr = row0 + j * 4 + sub;
-            resid[j] = (rr < M) ? *reinterpret_cast<const float4*>(epi.out_f32 + static_cast<size_t>(rr) * epi.ldo + n)
-                                : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-        }
-        uint32_t r[32];
-        ptx::tmem_ld_32x32b_x32(t_base + c * 32, r);
-        ptx::tmem_ld_wait();
-        if (c == 3) {
-          // all of this warp's TMEM reads for the tile are done: hand the accumulator stage back
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
-        }
-        // thread-owns-row -> staging tile [32 rows][128 B], 16-B units XOR-swizzled by (row & 7): conflict-free
-#pragma unroll
-        for (int u = 0; u < 8; ++u)
-          ptx::sts128(stage_u32 + lane * 128 + ((u ^ (lane & 7)) << 4), r[4 * u], r[4 * u + 1], r[4 * u + 2],
-                      r[4 * u + 3]);
-        __syncwarp();
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int rr = j * 4 + sub;
-          const float4 v = ptx::lds128(stage_u32 + rr * 128 + ((unit ^ (rr & 7)) << 4));
-          if (row0 + rr < M) {
-            if constexpr (EPI == EPI_BIAS_RESID_F32) epilogue_apply<EPI, BF16>(v, row0 + rr, n, epi, bias4, resid[j]);
-            else epilogue_apply<EPI, BF16>(v, row0 + rr, n, epi, bias4);
-          }
-        }
-        __syncwarp();
-      }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-    }
-  }
-
-  ptx::tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    ptx::tc_fence_after();
-    ptx::tmem_dealloc<TMEM_COLS>(tmem_base);
-  }
-}
-
 
 // =========================================================================================================
 // CTA-pair variant (tcgen05 cta_group::2): one cluster of 2 CTAs computes a 256 x BN output tile.
@@ -419,11 +276,36 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const int row0 = (2 * m_pair + static_cast<int>(rank)) * BM + q * 32;
       const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + half * COLS_PER_WARP;
       const int sub = lane >> 3, unit = lane & 7;
+      // coalesced domain: this thread handles rows row0 + j*4 + sub (j < 8) in every 32-column chunk
+      float mean_j[8], rstd_j[8];   // EPI_LN_*: LayerNorm statistics of its 8 rows
+      float st_s[8], st_q[8];       // EPI_BIAS_RESID_F32 + stats_out: running sum / sum of squares of the new rows
+      if constexpr (epi_is_ln<EPI>()) {
+        // lane `unit` fetches partial `unit` of the row; the 8 lanes of a row then add up in a fixed xor order
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int rr = row0 + j * 4 + sub;
+          float2 p = make_float2(0.f, 0.f);
+          if (rr < M && unit < epi.n_partials)
+            p = __ldg(reinterpret_cast<const float2*>(epi.stats) + static_cast<size_t>(rr) * epi.n_partials + unit);
+#pragma unroll
+          for (int o = 1; o < 8; o <<= 1) {
+            p.x += __shfl_xor_sync(0xffffffffu, p.x, o);
+            p.y += __shfl_xor_sync(0xffffffffu, p.y, o);
+          }
+          mean_j[j] = p.x * epi.inv_width;
+          rstd_j[j] = rsqrtf(fmaxf(p.y * epi.inv_width - mean_j[j] * mean_j[j], 0.f) + epi.eps);
+        }
+      }
+      if constexpr (EPI == EPI_BIAS_RESID_F32) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) st_s[j] = st_q[j] = 0.f;
+      }
 #pragma unroll 1
       for (int c = 0; c < CHUNKS; ++c) {
         const int n = n_blk * BN + half * COLS_PER_WARP + c * 32 + unit * 4;
-        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), cs4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if constexpr (epi_has_bias<EPI>()) bias4 = __ldg(reinterpret_cast<const float4*>(epi.bias + n));
+        if constexpr (epi_is_ln<EPI>()) cs4 = __ldg(reinterpret_cast<const float4*>(epi.colsum + n));
         float4 resid[8];
         if constexpr (EPI == EPI_BIAS_RESID_F32) {
 #pragma unroll
@@ -451,11 +333,36 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           const int rr = j * 4 + sub;
           const float4 v = ptx::lds128(stage_u32 + rr * 128 + ((unit ^ (rr & 7)) << 4));
           if (row0 + rr < M) {
-            if constexpr (EPI == EPI_BIAS_RESID_F32) epilogue_apply<EPI, BF16>(v, row0 + rr, n, epi, bias4, resid[j]);
-            else epilogue_apply<EPI, BF16>(v, row0 + rr, n, epi, bias4);
+            if constexpr (EPI == EPI_BIAS_RESID_F32) {
+              const float4 x = epilogue_apply<EPI, BF16>(v, row0 + rr, n, epi, bias4, resid[j]);
+              st_s[j] += (x.x + x.y) + (x.z + x.w);
+              st_q[j] += (x.x * x.x + x.y * x.y) + (x.z * x.z + x.w * x.w);
+            } else if constexpr (epi_is_ln<EPI>()) {
+              epilogue_apply<EPI, BF16>(v, row0 + rr, n, epi, bias4, make_float4(0.f, 0.f, 0.f, 0.f), cs4, mean_j[j],
+                                        rstd_j[j]);
+            } else {
+              epilogue_apply<EPI, BF16>(v, row0 + rr, n, epi, bias4);
+            }
           }
         }
         __syncwarp();
+      }
+      if constexpr (EPI == EPI_BIAS_RESID_F32) {
+        if (epi.stats_out != nullptr) {
+          // partial (sum, sumsq) of this warp's COLS_PER_WARP columns for each of its 32 rows
+          const int np = N / COLS_PER_WARP, pi = n_blk * 2 + half;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) {
+              st_s[j] += __shfl_xor_sync(0xffffffffu, st_s[j], o);
+              st_q[j] += __shfl_xor_sync(0xffffffffu, st_q[j], o);
+            }
+            const int rr = row0 + j * 4 + sub;
+            if (unit == 0 && rr < M)
+              reinterpret_cast<float2*>(epi.stats_out)[static_cast<size_t>(rr) * np + pi] = make_float2(st_s[j], st_q[j]);
+          }
+        }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }

@@ -77,6 +77,50 @@ def gemm16(a: torch.Tensor, w: torch.Tensor, epi: int, bias: Optional[torch.Tens
     return out_bf16 if bf16_out else out_f32
 
 
+def ln_fold(w: torch.Tensor, b: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor,
+            dtype: torch.dtype = torch.float16) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """(W' = W*gamma rounded to `dtype`, colsum(W'), b + W beta): LayerNorm folded into a Linear (aaclip_ln_fold)."""
+    _need_cuda(w, b, gamma, beta)
+    w = w.contiguous().float()
+    N, K = w.shape
+    w16 = torch.empty((N, K), dtype=dtype, device=w.device)
+    colsum = torch.empty((N,), dtype=torch.float32, device=w.device)
+    bias_f = torch.empty((N,), dtype=torch.float32, device=w.device)
+    _lib.check(_lib.load().aaclip_ln_fold(_dt(dtype), _ptr(w), _ptr(b.contiguous().float()), _ptr(gamma.contiguous().float()),
+                                          _ptr(beta.contiguous().float()), N, K, _ptr(w16), _ptr(colsum), _ptr(bias_f),
+                                          _stream()), "aaclip_ln_fold")
+    return w16, colsum, bias_f
+
+
+def gemm16_ln(a: torch.Tensor, w16: torch.Tensor, epi: int, bias_f: torch.Tensor, colsum: torch.Tensor,
+              stats: torch.Tensor, ln_width: int) -> torch.Tensor:
+    """act(LayerNorm(rows of x) @ W^T + b) from the raw 16-bit rows `a`, folded weights and row partials `stats`
+    [M, n_partials, 2] (aaclip_gemm16_ln)."""
+    _need_cuda(a, w16, bias_f, colsum, stats)
+    assert a.dtype == w16.dtype and a.is_contiguous() and w16.is_contiguous() and stats.is_contiguous()
+    M, K = a.shape
+    N = w16.shape[0]
+    out = torch.empty((M, N), dtype=a.dtype, device=a.device)
+    _lib.check(_lib.load().aaclip_gemm16_ln(_dt(a), _ptr(a), _ptr(w16), M, N, K, epi, _ptr(bias_f), _ptr(colsum),
+                                            _ptr(stats), stats.shape[1], ln_width, _ptr(out), N, _stream()),
+               "aaclip_gemm16_ln")
+    return out
+
+
+def gemm16_resid(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, x: torch.Tensor, want_x16: bool = True,
+                 want_stats: bool = True):
+    """x += a @ w^T + bias in place (fp32); returns (x16 | None, stats [M, N/128, 2] | None) (aaclip_gemm16_resid)."""
+    _need_cuda(a, w, bias, x)
+    assert a.dtype == w.dtype and a.is_contiguous() and w.is_contiguous() and x.is_contiguous() and x.dtype == torch.float32
+    M, K = a.shape
+    N = w.shape[0]
+    x16 = torch.empty((M, N), dtype=a.dtype, device=a.device) if want_x16 else None
+    stats = torch.empty((M, N // 128, 2), dtype=torch.float32, device=a.device) if want_stats else None
+    _lib.check(_lib.load().aaclip_gemm16_resid(_dt(a), _ptr(a), _ptr(w), M, N, K, _ptr(bias), _ptr(x), _ptr(x16),
+                                               _ptr(stats), N, _stream()), "aaclip_gemm16_resid")
+    return x16, stats
+
+
 def attention(qkv: torch.Tensor, causal: bool = False) -> torch.Tensor:
     """qkv fp16|bf16 [B,N,3D] -> same dtype [B,N,D] (aaclip_attention)."""
     _need_cuda(qkv)

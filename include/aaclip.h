@@ -53,6 +53,10 @@ extern "C" {
 #define AACLIP_EPI_F32 4
 #define AACLIP_EPI_LEAKY_F32 5
 #define AACLIP_EPI_BIAS_F32 7
+/* folded-LayerNorm epilogues of aaclip_gemm16_ln (ln_1 / ln_2 of model/transformer.py:245,252 live in the GEMMs) */
+#define AACLIP_EPI_LN_BIAS_BF16 8
+#define AACLIP_EPI_LN_BIAS_GELU_BF16 9
+#define AACLIP_EPI_LN_BIAS_QGELU_BF16 10
 
 /* Static description of the adapted visual tower (model/model_configs/ViT-L-14-336.json +
  * AdaptedCLIP.__init__, model/adapter.py:11-47). */
@@ -205,6 +209,25 @@ int aaclip_text_anchors(const float* emb, const int32_t* offsets, int32_t n_grou
  * N % 256 == 0, K % 64 == 0. out_f32 / out_16 as required by `epi`; ldo = leading dim of outputs. */
 int aaclip_gemm16(int32_t dtype, const void* A, const void* W, int32_t M, int32_t N, int32_t K, int32_t epi,
                   const float* bias, float* out_f32, void* out_16, int32_t ldo, void* stream);
+
+/* LayerNorm folding at weight-load time (what the first aaclip_forward does for every block):
+ *   W16[n,k] = W[n,k]*gamma[k] (rounded to `dtype`), colsum[n] = sum_k W16[n,k], bias_f[n] = b[n] + sum_k W[n,k]*beta[k],
+ * so that  LayerNorm(x) W^T + b  =  rstd * (x W16^T - mean * colsum) + bias_f  with x the RAW residual row. */
+int aaclip_ln_fold(int32_t dtype, const float* W, const float* b, const float* gamma, const float* beta, int32_t N,
+                   int32_t K, void* W16, float* colsum, float* bias_f, void* stream);
+
+/* GEMM with the LayerNorm of the A rows folded into the epilogue (epi = AACLIP_EPI_LN_*):
+ *   out_16 = act(rstd_m * (A W16^T - mean_m * colsum) + bias_f),
+ * mean / rstd (eps 1e-5, width ln_width) finished from stats [M][n_partials][2] = per-row partial (sum, sum of squares)
+ * over disjoint column ranges, n_partials <= 8 (written by aaclip_gemm16_resid / the ln_pre and adapter-blend kernels). */
+int aaclip_gemm16_ln(int32_t dtype, const void* A, const void* W16, int32_t M, int32_t N, int32_t K, int32_t epi,
+                     const float* bias_f, const float* colsum, const float* stats, int32_t n_partials,
+                     int32_t ln_width, void* out_16, int32_t ldo, void* stream);
+
+/* Residual GEMM: x[M,N] (fp32, in place) += A W^T + bias; optionally also the raw 16-bit copy of the new x and its
+ * LayerNorm partials stats_out [M][N/128][2] (the inputs of the next folded-LN GEMM). */
+int aaclip_gemm16_resid(int32_t dtype, const void* A, const void* W, int32_t M, int32_t N, int32_t K,
+                        const float* bias, float* x, void* x16_out, float* stats_out, int32_t ldo, void* stream);
 
 /* Fused multi-head attention: qkv `dtype` [B,N,3*D] -> out `dtype` [B,N,D]; head dim 64; softmax scale 1/8. */
 int aaclip_attention(int32_t dtype, const void* qkv, void* out, int32_t B, int32_t N, int32_t D, int32_t causal,

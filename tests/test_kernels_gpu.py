@@ -148,3 +148,57 @@ def test_score_maps_against_oracle(eng):
     m, _ = engine.score_maps(seg2, text, 225, test=True, ksize=9, sigma=1.5)
     ref = orc.anomaly_maps([seg2[0].cpu()], text.cpu(), 225, "Medical")
     assert (m.cpu() - ref).abs().max().item() < 1e-4
+
+
+# ---------------------------------------------------------------------------------------------------------
+# LayerNorm folded into the GEMMs that produce / consume the residual stream (model/transformer.py:245-254)
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("M,W,N", [(300, 1024, 3072), (2740, 1024, 4096), (77 * 3, 768, 2304)])
+def test_folded_layernorm_gemm_chain(eng, M, W, N, dtype):
+    """resid GEMM (x += a w^T + b, emits raw 16-bit x and row partials) followed by the folded-LN GEMM must equal
+    Linear(LayerNorm(x)) computed in fp32 torch on the same x -- to one 16-bit rounding of the operands."""
+    _lib, engine = eng
+    g = torch.Generator(device="cuda").manual_seed(M + W + N)
+    a, w_o, b_o = _ab(M, W, W, dtype)
+    x = torch.randn(M, W, device="cuda", generator=g) * 2.0 + 0.3          # non-zero row mean on purpose
+    x_ref = x + a.float() @ w_o.float().t() + b_o
+    x16, stats = engine.gemm16_resid(a, w_o, b_o, x)
+    assert (x - x_ref).abs().max().item() < 1e-3
+    assert (x16.float() - x).abs().max().item() <= x.abs().max().item() * EPS[dtype]
+    # the partials: (sum, sum of squares) over each 128-column slice of the new x
+    want = torch.stack([x.view(M, W // 128, 128).sum(-1), (x * x).view(M, W // 128, 128).sum(-1)], dim=-1)
+    assert torch.allclose(stats, want, rtol=1e-5, atol=1e-3)
+    # fold + consume
+    gamma = torch.randn(W, device="cuda", generator=g) * 0.1 + 1.0
+    beta = torch.randn(W, device="cuda", generator=g) * 0.05
+    w = torch.randn(N, W, device="cuda", generator=g) * W ** -0.5
+    b = torch.randn(N, device="cuda", generator=g) * 0.1
+    w16, colsum, bias_f = engine.ln_fold(w, b, gamma, beta, dtype)
+    assert torch.allclose(w16.float(), (w * gamma).to(dtype).float())
+    assert torch.allclose(colsum, w16.float().sum(-1), atol=1e-3)
+    assert torch.allclose(bias_f, b + w @ beta, atol=1e-4)
+    y_ref = F.layer_norm(x, (W,), gamma, beta, 1e-5) @ w.t() + b
+    tol = y_ref.abs().max().item() * 3 * EPS[dtype] + 2e-3
+    y = engine.gemm16_ln(x16, w16, _lib.EPI_LN_BIAS_BF16, bias_f, colsum, stats, W)
+    assert (y.float() - y_ref).abs().max().item() < tol
+    yg = engine.gemm16_ln(x16, w16, _lib.EPI_LN_BIAS_GELU_BF16, bias_f, colsum, stats, W)
+    assert (yg.float() - F.gelu(y_ref)).abs().max().item() < tol
+    yq = engine.gemm16_ln(x16, w16, _lib.EPI_LN_BIAS_QGELU_BF16, bias_f, colsum, stats, W)
+    assert (yq.float() - y_ref * torch.sigmoid(1.702 * y_ref)).abs().max().item() < tol
+
+
+def test_folded_layernorm_is_row_local(eng):
+    """Batch invariance: a row's folded-LN output must not depend on which other rows are in the launch."""
+    _lib, engine = eng
+    g = torch.Generator(device="cuda").manual_seed(5)
+    W, N = 1024, 3072
+    x = torch.randn(600, W, device="cuda", generator=g)
+    x16 = x.half()
+    stats = torch.stack([x16.float().view(600, 8, 128).sum(-1), (x16.float() ** 2).view(600, 8, 128).sum(-1)], -1).contiguous()
+    w16, colsum, bias_f = engine.ln_fold(torch.randn(N, W, device="cuda", generator=g) * 0.03,
+                                         torch.zeros(N, device="cuda"), torch.ones(W, device="cuda"),
+                                         torch.zeros(W, device="cuda"))
+    full = engine.gemm16_ln(x16, w16, _lib.EPI_LN_BIAS_BF16, bias_f, colsum, stats, W)
+    part = engine.gemm16_ln(x16[130:391].contiguous(), w16, _lib.EPI_LN_BIAS_BF16, bias_f, colsum,
+                            stats[130:391].contiguous(), W)
+    assert torch.equal(full[130:391], part)
