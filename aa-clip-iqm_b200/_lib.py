@@ -42,7 +42,7 @@ EPI_LN_BIAS_QGELU_BF16 = 10
 DT_F16 = 0
 DT_BF16 = 1
 
-PROF_CLASSES = ("gemm", "attention", "layernorm", "other")
+PROF_CLASSES = ("gemm_misc", "attention", "layernorm", "other", "gemm_qkv", "gemm_out", "gemm_fc", "gemm_proj")
 
 ACT_GELU_ERF = 0
 ACT_QUICK_GELU = 1
@@ -150,6 +150,8 @@ def _declare(lib):
                                       vp, vp]
     lib.aaclip_last_launch_count.restype = i32
     lib.aaclip_last_launch_count.argtypes = [vp]
+    lib.aaclip_stat_columns.restype = i32
+    lib.aaclip_stat_columns.argtypes = []
     lib.aaclip_profile_enable.restype = i32
     lib.aaclip_profile_enable.argtypes = [vp, i32]
     lib.aaclip_profile_read.restype = i32
@@ -187,7 +189,7 @@ def _declare(lib):
 EXPORTED_SYMBOLS = [
     "aaclip_version", "aaclip_last_error", "aaclip_create", "aaclip_destroy", "aaclip_set_weight",
     "aaclip_missing_weights", "aaclip_workspace_bytes", "aaclip_forward", "aaclip_score_workspace_bytes",
-    "aaclip_score_maps", "aaclip_last_launch_count", "aaclip_profile_enable", "aaclip_profile_read", "aaclip_gemm16", "aaclip_attention", "aaclip_layernorm",
+    "aaclip_score_maps", "aaclip_last_launch_count", "aaclip_stat_columns", "aaclip_profile_enable", "aaclip_profile_read", "aaclip_gemm16", "aaclip_attention", "aaclip_layernorm",
     "aaclip_pack16",
     "aaclip_ln_fold", "aaclip_gemm16_ln", "aaclip_gemm16_resid",
     "aaclip_text_create", "aaclip_text_destroy", "aaclip_text_set_weight", "aaclip_text_missing_weights",

@@ -372,6 +372,10 @@ void free_block_staging(std::vector<BlockW>& blk) {
 }
 
 // workspace of the block loop, shared layout for both towers (rows M = items * tokens)
+// partials per row of width W written by the residual-GEMM epilogue (one per epilogue warp column slice)
+constexpr int kStatCols = 256 / GemmPairCfg<256>::COL_GROUPS;
+inline int kStatPartials(size_t W) { return static_cast<int>(W) / kStatCols; }
+
 struct CoreWs { size_t x, x16, qkv, att, hid, abuf, stats, end; };
 CoreWs plan_core_ws(ArenaPlan& p, size_t M, size_t W, size_t F) {
   CoreWs w;
@@ -381,7 +385,7 @@ CoreWs plan_core_ws(ArenaPlan& p, size_t M, size_t W, size_t F) {
   w.att = p.take<uint16_t>(M * W);
   w.hid = p.take<uint16_t>(M * F);
   w.abuf = p.take<float>(M * W);
-  w.stats = p.take<float>(M * (W / 128) * 2);   // LayerNorm partials (sum, sumsq) per 128 columns
+  w.stats = p.take<float>(M * kStatPartials(W) * 2);   // LayerNorm partials (sum, sumsq) per epilogue-warp column slice
   w.end = p.off;
   return w;
 }
@@ -445,30 +449,30 @@ struct BlockRun {
   cudaStream_t st;
   int launches = 0;
 
-  int gemm(int epi, const void* A, const void* Wt, int m, int n, int k, const GemmEpi& e) {
-    ProfScope ps(prof, AACLIP_PROF_GEMM, 2.0 * m * n * k, st);
+  int gemm(int epi, const void* A, const void* Wt, int m, int n, int k, const GemmEpi& e, int cls = AACLIP_PROF_GEMM) {
+    ProfScope ps(prof, cls, 2.0 * m * n * k, st);
     ++launches;
     return launch_gemm(epi, bf16, A, Wt, m, n, k, e, st);
   }
 
   int run(const BlockW& b, const uint16_t* w_adapter, float adapt_weight) {
-    const int M = items * tokens, np = W / 128;
+    const int M = items * tokens, np = kStatPartials(W);
     int rc;
     { GemmEpi e; e.bias = b.bf_qkv; e.colsum = b.cs_qkv; e.stats = stats; e.n_partials = np; e.inv_width = 1.0f / W;
       e.out_16 = qkv; e.ldo = 3 * W;
-      if ((rc = gemm(EPI_LN_BIAS_BF16, x16, b.w_qkv, M, 3 * W, W, e))) return rc; }
+      if ((rc = gemm(EPI_LN_BIAS_BF16, x16, b.w_qkv, M, 3 * W, W, e, AACLIP_PROF_GEMM_QKV))) return rc; }
     {
       ProfScope ps(prof, AACLIP_PROF_ATTENTION, 4.0 * items * (W / 64) * (double)tokens * tokens * 64, st);
       ++launches;
       if ((rc = launch_attention(bf16, qkv, att, items, tokens, W, causal, st))) return rc;
     }
     { GemmEpi e; e.bias = b.b_out; e.out_f32 = x; e.out_16 = x16; e.stats_out = stats; e.ldo = W;
-      if ((rc = gemm(EPI_BIAS_RESID_F32, att, b.w_out, M, W, W, e))) return rc; }
+      if ((rc = gemm(EPI_BIAS_RESID_F32, att, b.w_out, M, W, W, e, AACLIP_PROF_GEMM_OUT))) return rc; }
     { GemmEpi e; e.bias = b.bf_fc; e.colsum = b.cs_fc; e.stats = stats; e.n_partials = np; e.inv_width = 1.0f / W;
       e.out_16 = hid; e.ldo = F;
-      if ((rc = gemm(act == AACLIP_ACT_QUICK_GELU ? EPI_LN_BIAS_QGELU_BF16 : EPI_LN_BIAS_GELU_BF16, x16, b.w_fc, M, F, W, e))) return rc; }
+      if ((rc = gemm(act == AACLIP_ACT_QUICK_GELU ? EPI_LN_BIAS_QGELU_BF16 : EPI_LN_BIAS_GELU_BF16, x16, b.w_fc, M, F, W, e, AACLIP_PROF_GEMM_FC))) return rc; }
     { GemmEpi e; e.bias = b.b_proj; e.out_f32 = x; e.out_16 = x16; e.stats_out = stats; e.ldo = W;
-      if ((rc = gemm(EPI_BIAS_RESID_F32, hid, b.w_proj, M, W, F, e))) return rc; }
+      if ((rc = gemm(EPI_BIAS_RESID_F32, hid, b.w_proj, M, W, F, e, AACLIP_PROF_GEMM_PROJ))) return rc; }
     if (w_adapter != nullptr) {
       { GemmEpi e; e.out_f32 = abuf; e.ldo = W;
         if ((rc = gemm(EPI_LEAKY_F32, x16, w_adapter, M, W, W, e))) return rc; }
@@ -696,7 +700,7 @@ int aaclip_forward(AaclipHandle* h, const float* images, int32_t B, void* worksp
                    float* stats_out) -> int {
     ProfScope ps(h, AACLIP_PROF_LAYERNORM, 0.0, st);
     ++launches;
-    return launch_layernorm(bf, in, g, bta, o16, o32, rows, W, skipP, true, st, stats_out, W / 128);
+    return launch_layernorm(bf, in, g, bta, o16, o32, rows, W, skipP, true, st, stats_out, kStatPartials(W));
   };
   auto l2norm = [&](float* t, int rows) -> int {
     ProfScope ps(h, AACLIP_PROF_OTHER, 0.0, st);
@@ -760,6 +764,8 @@ int aaclip_forward(AaclipHandle* h, const float* images, int32_t B, void* worksp
 }
 
 int aaclip_last_launch_count(AaclipHandle* h) { return h ? h->last_launches : -1; }
+
+int aaclip_stat_columns(void) { return kStatCols; }
 
 int aaclip_profile_enable(AaclipHandle* h, int32_t enable) {
   if (!h) return fail(AACLIP_EINVAL, "aaclip_profile_enable: null handle");
@@ -1012,7 +1018,7 @@ int aaclip_encode_text(AaclipTextHandle* h, const int32_t* tokens, int32_t n, vo
   // produces the raw 16-bit copy and the LayerNorm partials block 0's folded ln_1 needs
   text_embed_kernel<<<M, 192, 0, st>>>(tokens, h->tok_emb, h->pos, run.x, T, W, c.vocab);
   LAUNCH_CHECK("text_embed_kernel");
-  if ((rc = launch_layernorm(bf, run.x, nullptr, nullptr, run.x16, nullptr, M, W, 0, /*normalize=*/false, st, run.stats, W / 128))) return rc;
+  if ((rc = launch_layernorm(bf, run.x, nullptr, nullptr, run.x16, nullptr, M, W, 0, /*normalize=*/false, st, run.stats, kStatPartials(W)))) return rc;
   // 12 causal residual attention blocks + adapters (model/adapter.py:284-295)
   for (int i = 0; i < c.layers; ++i)
     if ((rc = run.run(h->blk[i], i < c.adapt_until ? h->w_adapter[i] : nullptr, c.adapt_weight))) return rc;
@@ -1075,7 +1081,7 @@ int aaclip_gemm16_ln(int32_t dtype, const void* A, const void* W16, int32_t M, i
   if (dtype != AACLIP_DT_F16 && dtype != AACLIP_DT_BF16) return fail(AACLIP_EINVAL, "aaclip_gemm16_ln: bad dtype %d", dtype);
   if (epi != EPI_LN_BIAS_BF16 && epi != EPI_LN_BIAS_GELU_BF16 && epi != EPI_LN_BIAS_QGELU_BF16)
     return fail(AACLIP_EINVAL, "aaclip_gemm16_ln: epilogue %d is not a folded-LayerNorm epilogue", epi);
-  if (n_partials < 1 || n_partials > 8 || ln_width <= 0) return fail(AACLIP_EINVAL, "aaclip_gemm16_ln: n_partials must be 1..8");
+  if (n_partials < 1 || n_partials > 16 || ln_width <= 0) return fail(AACLIP_EINVAL, "aaclip_gemm16_ln: n_partials must be 1..16");
   if (ldo < N || ldo % 8 != 0) return fail(AACLIP_EINVAL, "aaclip_gemm16_ln: ldo must be >= N and a multiple of 8");
   GemmEpi e;
   e.bias = bias_f; e.colsum = colsum; e.stats = stats; e.n_partials = n_partials; e.inv_width = 1.0f / ln_width;
@@ -1088,7 +1094,7 @@ int aaclip_gemm16_resid(int32_t dtype, const void* A, const void* W, int32_t M, 
   if (!A || !W || !bias || !x) return fail(AACLIP_EINVAL, "aaclip_gemm16_resid: null argument");
   if (dtype != AACLIP_DT_F16 && dtype != AACLIP_DT_BF16) return fail(AACLIP_EINVAL, "aaclip_gemm16_resid: bad dtype %d", dtype);
   if (ldo < N || ldo % 8 != 0) return fail(AACLIP_EINVAL, "aaclip_gemm16_resid: ldo must be >= N and a multiple of 8");
-  if (stats_out && N > 1024) return fail(AACLIP_EINVAL, "aaclip_gemm16_resid: statistics need N <= 1024 (8 partials)");
+  if (stats_out && N / kStatCols > 16) return fail(AACLIP_EINVAL, "aaclip_gemm16_resid: statistics need N <= %d (16 partials)", 16 * kStatCols);
   GemmEpi e;
   e.bias = bias; e.out_f32 = x; e.out_16 = reinterpret_cast<uint16_t*>(x16_out); e.stats_out = stats_out; e.ldo = ldo;
   return launch_gemm(EPI_BIAS_RESID_F32, dtype == AACLIP_DT_BF16, A, W, M, N, K, e, static_cast<cudaStream_t>(stream));

@@ -148,16 +148,24 @@ struct GemmPairCfg {
   static constexpr int A_BYTES = BM * BK * 2;             // 16 KiB
   static constexpr int B_BYTES = (BN / 2) * BK * 2;       // 16 KiB (BN 256) / 8 KiB (BN 128): this CTA's half
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 6 : 8;      // 192 KiB of operand ring either way
-  static constexpr int THREADS = 320;
-  static constexpr int EPI_WARPS = 8;
+#ifndef AACLIP_GEMM_EPI_WARPS
+#define AACLIP_GEMM_EPI_WARPS 8
+#endif
+  // Epilogue warps: EPI_WARPS/4 per TMEM lane quarter, splitting the accumulator columns. 16 warps (5-stage ring) run
+  // the c_fc epilogue 12 % faster on L2-resident inputs but lose 11 % inside the real step (HBM-fed, power-capped:
+  // 767 vs 809 images/s), so 8 warps with the deeper 6-stage ring is the default.
+  static constexpr int EPI_WARPS = AACLIP_GEMM_EPI_WARPS;
+  static constexpr int COL_GROUPS = EPI_WARPS / 4;        // warps sharing a lane quarter split the columns
+  static constexpr int THREADS = 64 + 32 * EPI_WARPS;
+  static constexpr int STAGES = (EPI_WARPS == 16) ? 5 : 6;   // 160 / 192 KiB of operand ring (+ 4 KiB staging per epilogue warp)
   static constexpr int TMEM_COLS = 2 * BN;                // double-buffered accumulator
   static constexpr int EPI_STAGE_BYTES = 32 * 128;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 512 + EPI_WARPS * EPI_STAGE_BYTES + 1024;
 };
 
 template <int EPI, bool BF16, int BN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
+// (18 warps are allocated like 20: 96 registers per thread at most -- __maxnreg__(112) is refused at launch)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GemmPairCfg<BN>::THREADS, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, int M, int N,
                  int K, GemmEpi epi) {
   using C = GemmPairCfg<BN>;
@@ -261,11 +269,11 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
   } else {
     // ===================== epilogue warps (both CTAs, own 128 rows) =====================
-    constexpr int COLS_PER_WARP = BN / 2;          // two warps share a lane quarter, each takes half of the columns
+    constexpr int COLS_PER_WARP = BN / C::COL_GROUPS;   // warps sharing a lane quarter split the accumulator columns
     constexpr int CHUNKS = COLS_PER_WARP / 32;
     const int e = warp - 2;
     const int q = warp & 3;
-    const int half = e >> 2;
+    const int cg = e >> 2;          // column group of this warp
     const uint32_t stage_u32 = ptx::smem_u32(smem + STAGES * STAGE_BYTES + 512 + e * C::EPI_STAGE_BYTES);
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -274,26 +282,34 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
       ptx::tc_fence_after();
       const int row0 = (2 * m_pair + static_cast<int>(rank)) * BM + q * 32;
-      const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + half * COLS_PER_WARP;
+      const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + cg * COLS_PER_WARP;
       const int sub = lane >> 3, unit = lane & 7;
       // coalesced domain: this thread handles rows row0 + j*4 + sub (j < 8) in every 32-column chunk
       float mean_j[8], rstd_j[8];   // EPI_LN_*: LayerNorm statistics of its 8 rows
       float st_s[8], st_q[8];       // EPI_BIAS_RESID_F32 + stats_out: running sum / sum of squares of the new rows
       if constexpr (epi_is_ln<EPI>()) {
-        // lane `unit` fetches partial `unit` of the row; the 8 lanes of a row then add up in a fixed xor order
+        // lane l finishes the statistics of row row0 + l from its partials (contiguous, fixed order), then the
+        // coalesced-domain owners of that row pick them up with one shuffle each
+        float mean = 0.f, rstd = 0.f;
+        if (row0 + lane < M) {
+          const float4* sp = reinterpret_cast<const float4*>(epi.stats + static_cast<size_t>(row0 + lane) * epi.n_partials * 2);
+          float sx = 0.f, sq = 0.f;
+          for (int i = 0; i < epi.n_partials / 2; ++i) {      // two (sum, sumsq) partials per 16-byte load
+            const float4 p = __ldg(sp + i);
+            sx += p.x + p.z;
+            sq += p.y + p.w;
+          }
+          if (epi.n_partials & 1) {
+            const float2 p = __ldg(reinterpret_cast<const float2*>(sp) + epi.n_partials - 1);
+            sx += p.x; sq += p.y;
+          }
+          mean = sx * epi.inv_width;
+          rstd = rsqrtf(fmaxf(sq * epi.inv_width - mean * mean, 0.f) + epi.eps);
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const int rr = row0 + j * 4 + sub;
-          float2 p = make_float2(0.f, 0.f);
-          if (rr < M && unit < epi.n_partials)
-            p = __ldg(reinterpret_cast<const float2*>(epi.stats) + static_cast<size_t>(rr) * epi.n_partials + unit);
-#pragma unroll
-          for (int o = 1; o < 8; o <<= 1) {
-            p.x += __shfl_xor_sync(0xffffffffu, p.x, o);
-            p.y += __shfl_xor_sync(0xffffffffu, p.y, o);
-          }
-          mean_j[j] = p.x * epi.inv_width;
-          rstd_j[j] = rsqrtf(fmaxf(p.y * epi.inv_width - mean_j[j] * mean_j[j], 0.f) + epi.eps);
+          mean_j[j] = __shfl_sync(0xffffffffu, mean, j * 4 + sub);
+          rstd_j[j] = __shfl_sync(0xffffffffu, rstd, j * 4 + sub);
         }
       }
       if constexpr (EPI == EPI_BIAS_RESID_F32) {
@@ -302,19 +318,22 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
 #pragma unroll 1
       for (int c = 0; c < CHUNKS; ++c) {
-        const int n = n_blk * BN + half * COLS_PER_WARP + c * 32 + unit * 4;
+        const int n = n_blk * BN + cg * COLS_PER_WARP + c * 32 + unit * 4;
         float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), cs4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if constexpr (epi_has_bias<EPI>()) bias4 = __ldg(reinterpret_cast<const float4*>(epi.bias + n));
         if constexpr (epi_is_ln<EPI>()) cs4 = __ldg(reinterpret_cast<const float4*>(epi.colsum + n));
-        float4 resid[8];
-        if constexpr (EPI == EPI_BIAS_RESID_F32) {
+        // residual rows of this chunk: rows j = 0..3 are fetched before the TMEM load, rows 4..7 right after the
+        // staging stores (when the 32 accumulator registers are dead) -- 4 + 4 coalesced loads in flight per thread
+        float4 resid_a[4], resid_b[4];
+        auto load_resid = [&](float4 (&dst)[4], int j0) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int rr = row0 + j * 4 + sub;
-            resid[j] = (rr < M) ? *reinterpret_cast<const float4*>(epi.out_f32 + static_cast<size_t>(rr) * epi.ldo + n)
-                                : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int j = 0; j < 4; ++j) {
+            const int rr = row0 + (j0 + j) * 4 + sub;
+            dst[j] = (rr < M) ? *reinterpret_cast<const float4*>(epi.out_f32 + static_cast<size_t>(rr) * epi.ldo + n)
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
           }
-        }
+        };
+        if constexpr (EPI == EPI_BIAS_RESID_F32) load_resid(resid_a, 0);
         uint32_t r[32];
         ptx::tmem_ld_32x32b_x32(t_base + c * 32, r);
         ptx::tmem_ld_wait();
@@ -327,6 +346,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         for (int u = 0; u < 8; ++u)
           ptx::sts128(stage_u32 + lane * 128 + ((u ^ (lane & 7)) << 4), r[4 * u], r[4 * u + 1], r[4 * u + 2],
                       r[4 * u + 3]);
+        if constexpr (EPI == EPI_BIAS_RESID_F32) load_resid(resid_b, 4);
         __syncwarp();
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -334,7 +354,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           const float4 v = ptx::lds128(stage_u32 + rr * 128 + ((unit ^ (rr & 7)) << 4));
           if (row0 + rr < M) {
             if constexpr (EPI == EPI_BIAS_RESID_F32) {
-              const float4 x = epilogue_apply<EPI, BF16>(v, row0 + rr, n, epi, bias4, resid[j]);
+              const float4 x = epilogue_apply<EPI, BF16>(v, row0 + rr, n, epi, bias4, j < 4 ? resid_a[j & 3] : resid_b[j & 3]);
               st_s[j] += (x.x + x.y) + (x.z + x.w);
               st_q[j] += (x.x * x.x + x.y * x.y) + (x.z * x.z + x.w * x.w);
             } else if constexpr (epi_is_ln<EPI>()) {
@@ -349,19 +369,46 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
       if constexpr (EPI == EPI_BIAS_RESID_F32) {
         if (epi.stats_out != nullptr) {
-          // partial (sum, sumsq) of this warp's COLS_PER_WARP columns for each of its 32 rows
-          const int np = N / COLS_PER_WARP, pi = n_blk * 2 + half;
+          // partial (sum, sumsq) of this warp's COLS_PER_WARP columns for each of its 32 rows. The 8 lanes of a row
+          // group (unit = 0..7) hold 8 rows x 2 values each; a halving butterfly (each xor step exchanges half of the
+          // still-live values) leaves lane `unit` with the complete sums of row j = unit: 14 shuffles instead of 48,
+          // every lane stores one row. Fixed order: bit-reproducible and batch-invariant.
+          const int np = N / COLS_PER_WARP, pi = n_blk * C::COL_GROUPS + cg;
+          float v[16];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
+          for (int j = 0; j < 8; ++j) { v[j] = st_s[j]; v[8 + j] = st_q[j]; }
+          // step xor 4: lanes with (unit & 4) keep rows 4..7, the others rows 0..3
+          {
+            const bool hi = (unit & 4) != 0;
 #pragma unroll
-            for (int o = 1; o < 8; o <<= 1) {
-              st_s[j] += __shfl_xor_sync(0xffffffffu, st_s[j], o);
-              st_q[j] += __shfl_xor_sync(0xffffffffu, st_q[j], o);
+            for (int j = 0; j < 4; ++j) {
+              const float send_s = hi ? v[j] : v[4 + j], send_q = hi ? v[8 + j] : v[12 + j];
+              const float got_s = __shfl_xor_sync(0xffffffffu, send_s, 4), got_q = __shfl_xor_sync(0xffffffffu, send_q, 4);
+              v[j] = (hi ? v[4 + j] : v[j]) + got_s;
+              v[8 + j] = (hi ? v[12 + j] : v[8 + j]) + got_q;
             }
-            const int rr = row0 + j * 4 + sub;
-            if (unit == 0 && rr < M)
-              reinterpret_cast<float2*>(epi.stats_out)[static_cast<size_t>(rr) * np + pi] = make_float2(st_s[j], st_q[j]);
           }
+          // step xor 2: of the 4 live rows, lanes with (unit & 2) keep the upper two
+          {
+            const bool hi = (unit & 2) != 0;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const float send_s = hi ? v[j] : v[2 + j], send_q = hi ? v[8 + j] : v[10 + j];
+              const float got_s = __shfl_xor_sync(0xffffffffu, send_s, 2), got_q = __shfl_xor_sync(0xffffffffu, send_q, 2);
+              v[j] = (hi ? v[2 + j] : v[j]) + got_s;
+              v[8 + j] = (hi ? v[10 + j] : v[8 + j]) + got_q;
+            }
+          }
+          // step xor 1
+          {
+            const bool hi = (unit & 1) != 0;
+            const float send_s = hi ? v[0] : v[1], send_q = hi ? v[8] : v[9];
+            const float got_s = __shfl_xor_sync(0xffffffffu, send_s, 1), got_q = __shfl_xor_sync(0xffffffffu, send_q, 1);
+            v[0] = (hi ? v[1] : v[0]) + got_s;
+            v[8] = (hi ? v[9] : v[8]) + got_q;
+          }
+          const int rr = row0 + unit * 4 + sub;      // lane `unit` now owns row j = unit of its sub-group
+          if (rr < M) reinterpret_cast<float2*>(epi.stats_out)[static_cast<size_t>(rr) * np + pi] = make_float2(v[0], v[8]);
         }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }

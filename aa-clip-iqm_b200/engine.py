@@ -109,13 +109,15 @@ def gemm16_ln(a: torch.Tensor, w16: torch.Tensor, epi: int, bias_f: torch.Tensor
 
 def gemm16_resid(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, x: torch.Tensor, want_x16: bool = True,
                  want_stats: bool = True):
-    """x += a @ w^T + bias in place (fp32); returns (x16 | None, stats [M, N/128, 2] | None) (aaclip_gemm16_resid)."""
+    """x += a @ w^T + bias in place (fp32); returns (x16 | None, stats [M, N/stat_columns, 2] | None)
+    (aaclip_gemm16_resid)."""
     _need_cuda(a, w, bias, x)
     assert a.dtype == w.dtype and a.is_contiguous() and w.is_contiguous() and x.is_contiguous() and x.dtype == torch.float32
     M, K = a.shape
     N = w.shape[0]
     x16 = torch.empty((M, N), dtype=a.dtype, device=a.device) if want_x16 else None
-    stats = torch.empty((M, N // 128, 2), dtype=torch.float32, device=a.device) if want_stats else None
+    sc = _lib.load().aaclip_stat_columns()
+    stats = torch.empty((M, N // sc, 2), dtype=torch.float32, device=a.device) if want_stats else None
     _lib.check(_lib.load().aaclip_gemm16_resid(_dt(a), _ptr(a), _ptr(w), M, N, K, _ptr(bias), _ptr(x), _ptr(x16),
                                                _ptr(stats), N, _stream()), "aaclip_gemm16_resid")
     return x16, stats

@@ -137,6 +137,9 @@ int aaclip_score_maps(const float* const* seg, int32_t n_levels, const float* te
                       void* workspace, size_t workspace_bytes, float* maps_out, const float* det, float* score_out,
                       void* stream);
 
+/* Columns covered by one LayerNorm partial written by aaclip_gemm16_resid (= accumulator columns per epilogue warp). */
+int aaclip_stat_columns(void);
+
 /* Kernel launches enqueued by the last aaclip_forward on this handle (for bench.py's gpu_launches). */
 int aaclip_last_launch_count(AaclipHandle* h);
 
@@ -144,11 +147,15 @@ int aaclip_last_launch_count(AaclipHandle* h);
  * by a CUDA-event pair on the launch stream. aaclip_profile_read waits for the recorded events, returns the
  * accumulated milliseconds / launch counts / algorithmic FLOPs (2*M*N*K per GEMM, 4*B*H*N*N*64 per attention) per
  * class since the last enable/read, and clears the records. Arrays have AACLIP_PROF_CLASSES entries. */
-#define AACLIP_PROF_GEMM 0
+#define AACLIP_PROF_GEMM 0        /* GEMMs outside the blocks: patch embed, adapters, seg / det projections */
 #define AACLIP_PROF_ATTENTION 1
 #define AACLIP_PROF_LAYERNORM 2
 #define AACLIP_PROF_OTHER 3
-#define AACLIP_PROF_CLASSES 4
+#define AACLIP_PROF_GEMM_QKV 4    /* the four GEMMs of a residual attention block, timed separately */
+#define AACLIP_PROF_GEMM_OUT 5
+#define AACLIP_PROF_GEMM_FC 6
+#define AACLIP_PROF_GEMM_PROJ 7
+#define AACLIP_PROF_CLASSES 8
 int aaclip_profile_enable(AaclipHandle* h, int32_t enable);
 int aaclip_profile_read(AaclipHandle* h, float* ms, int32_t* launches, double* flops);
 
@@ -219,13 +226,13 @@ int aaclip_ln_fold(int32_t dtype, const float* W, const float* b, const float* g
 /* GEMM with the LayerNorm of the A rows folded into the epilogue (epi = AACLIP_EPI_LN_*):
  *   out_16 = act(rstd_m * (A W16^T - mean_m * colsum) + bias_f),
  * mean / rstd (eps 1e-5, width ln_width) finished from stats [M][n_partials][2] = per-row partial (sum, sum of squares)
- * over disjoint column ranges, n_partials <= 8 (written by aaclip_gemm16_resid / the ln_pre and adapter-blend kernels). */
+ * over disjoint column ranges, n_partials <= 16 (written by aaclip_gemm16_resid / the ln_pre and adapter-blend kernels). */
 int aaclip_gemm16_ln(int32_t dtype, const void* A, const void* W16, int32_t M, int32_t N, int32_t K, int32_t epi,
                      const float* bias_f, const float* colsum, const float* stats, int32_t n_partials,
                      int32_t ln_width, void* out_16, int32_t ldo, void* stream);
 
 /* Residual GEMM: x[M,N] (fp32, in place) += A W^T + bias; optionally also the raw 16-bit copy of the new x and its
- * LayerNorm partials stats_out [M][N/128][2] (the inputs of the next folded-LN GEMM). */
+ * LayerNorm partials stats_out [M][N/aaclip_stat_columns()][2] (the inputs of the next folded-LN GEMM). */
 int aaclip_gemm16_resid(int32_t dtype, const void* A, const void* W, int32_t M, int32_t N, int32_t K,
                         const float* bias, float* x, void* x16_out, float* stats_out, int32_t ldo, void* stream);
 

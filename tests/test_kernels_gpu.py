@@ -166,7 +166,8 @@ def test_folded_layernorm_gemm_chain(eng, M, W, N, dtype):
     assert (x - x_ref).abs().max().item() < 1e-3
     assert (x16.float() - x).abs().max().item() <= x.abs().max().item() * EPS[dtype]
     # the partials: (sum, sum of squares) over each 128-column slice of the new x
-    want = torch.stack([x.view(M, W // 128, 128).sum(-1), (x * x).view(M, W // 128, 128).sum(-1)], dim=-1)
+    sc = _lib.load().aaclip_stat_columns()
+    want = torch.stack([x.view(M, W // sc, sc).sum(-1), (x * x).view(M, W // sc, sc).sum(-1)], dim=-1)
     assert torch.allclose(stats, want, rtol=1e-5, atol=1e-3)
     # fold + consume
     gamma = torch.randn(W, device="cuda", generator=g) * 0.1 + 1.0
@@ -194,7 +195,7 @@ def test_folded_layernorm_is_row_local(eng):
     W, N = 1024, 3072
     x = torch.randn(600, W, device="cuda", generator=g)
     x16 = x.half()
-    stats = torch.stack([x16.float().view(600, 8, 128).sum(-1), (x16.float() ** 2).view(600, 8, 128).sum(-1)], -1).contiguous()
+    stats = torch.stack([x16.float().view(600, 8, 128).sum(-1), (x16.float() ** 2).view(600, 8, 128).sum(-1)], -1).contiguous()   # any partition of the row is a valid set of partials
     w16, colsum, bias_f = engine.ln_fold(torch.randn(N, W, device="cuda", generator=g) * 0.03,
                                          torch.zeros(N, device="cuda"), torch.ones(W, device="cuda"),
                                          torch.zeros(W, device="cuda"))

@@ -40,6 +40,22 @@ for (N, K, epi, nm) in [(3072, 1024, _lib.EPI_BIAS_BF16, "qkv  bias->f16"), (102
     ms = timeit(lambda: engine.gemm16(a, w, epi, bias=bias, out_f32=o32, out_16=o16 if epi < 3 else None))
     print(f"gemm {nm:22s} M={M} N={N} K={K}: {ms:.3f} ms  {2.0 * M * N * K / ms / 1e9:7.1f} TFLOP/s", flush=True)
 
+# the folded-LayerNorm forms aaclip_forward actually launches
+x = torch.randn(M, 1024, device=dev)
+stats = torch.stack([x.view(M, 8, 128).sum(-1), (x * x).view(M, 8, 128).sum(-1)], -1).contiguous()
+x16 = x.half()
+for (N, epi, nm) in [(3072, _lib.EPI_LN_BIAS_BF16, "qkv  LN-fold bias->f16"), (4096, _lib.EPI_LN_BIAS_GELU_BF16, "fc   LN-fold gelu->f16")]:
+    w16, cs, bf = engine.ln_fold(torch.randn(N, 1024, device=dev) * 0.03, torch.zeros(N, device=dev),
+                                 torch.ones(1024, device=dev), torch.zeros(1024, device=dev))
+    ms = timeit(lambda: engine.gemm16_ln(x16, w16, epi, bf, cs, stats, 1024))
+    print(f"gemm {nm:22s} M={M} N={N} K=1024: {ms:.3f} ms  {2.0 * M * N * 1024 / ms / 1e9:7.1f} TFLOP/s", flush=True)
+for (K, nm) in [(1024, "out  resid+x16+stats"), (4096, "proj resid+x16+stats")]:
+    a = (torch.randn(M, K, device=dev) * 0.5).half()
+    w = (torch.randn(1024, K, device=dev) * K ** -0.5).half()
+    bias = torch.randn(1024, device=dev) * 0.1
+    ms = timeit(lambda: engine.gemm16_resid(a, w, bias, x))
+    print(f"gemm {nm:22s} M={M} N=1024 K={K}: {ms:.3f} ms  {2.0 * M * 1024 * K / ms / 1e9:7.1f} TFLOP/s", flush=True)
+
 qkv = torch.randn(B, 1370, 3072, device=dev).half()
 ms = timeit(lambda: engine.attention(qkv))
 print(f"attention B={B} N=1370 H=16 d=64: {ms:.3f} ms  {4.0 * B * 16 * 1370 * 1370 * 64 / ms / 1e9:7.1f} TFLOP/s (algorithmic)")
