@@ -89,8 +89,11 @@ __host__ __device__ constexpr bool epi_is_ln() {
 
 // `b` = bias[n..n+3] (and `cs` = colsum[n..n+3]) are loaded once per 32-column chunk by the caller; `mean` / `rstd`
 // are the LayerNorm statistics of this row (EPI_LN_* only). Returns the fp32 value written (EPI_BIAS_RESID_F32).
+// `ok` predicates the STORES only (row < M): the math runs unconditionally so that the 8 rows a thread handles per
+// chunk stay in one basic block and their dependency chains interleave (a branch per row serialised them: ~95
+// dependent instructions per 4 elements with 2 warps per scheduler made the c_fc epilogue slower than its MMAs).
 template <int EPI, bool BF16>
-__device__ __forceinline__ float4 epilogue_apply(float4 v, int row, int n, const GemmEpi& e, float4 b,
+__device__ __forceinline__ float4 epilogue_apply(bool ok, float4 v, int row, int n, const GemmEpi& e, float4 b,
                                                  float4 resid = make_float4(0.f, 0.f, 0.f, 0.f),
                                                  float4 cs = make_float4(0.f, 0.f, 0.f, 0.f), float mean = 0.f,
                                                  float rstd = 1.f) {
@@ -111,24 +114,25 @@ __device__ __forceinline__ float4 epilogue_apply(float4 v, int row, int n, const
     v.z = v.z > 0.f ? v.z : 0.01f * v.z; v.w = v.w > 0.f ? v.w : 0.01f * v.w;
   }
   if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_QGELU_BF16 || epi_is_ln<EPI>()) {
-    *reinterpret_cast<uint2*>(e.out_16 + static_cast<size_t>(row) * e.ldo + n) =
-        make_uint2(ptx::pack16<BF16>(v.x, v.y), ptx::pack16<BF16>(v.z, v.w));
+    const uint2 w = make_uint2(ptx::pack16<BF16>(v.x, v.y), ptx::pack16<BF16>(v.z, v.w));
+    if (ok) *reinterpret_cast<uint2*>(e.out_16 + static_cast<size_t>(row) * e.ldo + n) = w;
   } else if constexpr (EPI == EPI_BIAS_RESID_F32) {
-    float4* o = reinterpret_cast<float4*>(e.out_f32 + static_cast<size_t>(row) * e.ldo + n);
-    v.x += resid.x; v.y += resid.y; v.z += resid.z; v.w += resid.w;   // residual loaded by the caller, 8 rows in flight
-    *o = v;
-    if (e.out_16 != nullptr)
-      *reinterpret_cast<uint2*>(e.out_16 + static_cast<size_t>(row) * e.ldo + n) =
-          make_uint2(ptx::pack16<BF16>(v.x, v.y), ptx::pack16<BF16>(v.z, v.w));
+    v.x += resid.x; v.y += resid.y; v.z += resid.z; v.w += resid.w;   // residual loaded by the caller
+    const uint2 w = make_uint2(ptx::pack16<BF16>(v.x, v.y), ptx::pack16<BF16>(v.z, v.w));
+    if (ok) {
+      *reinterpret_cast<float4*>(e.out_f32 + static_cast<size_t>(row) * e.ldo + n) = v;
+      if (e.out_16 != nullptr) *reinterpret_cast<uint2*>(e.out_16 + static_cast<size_t>(row) * e.ldo + n) = w;
+    }
   } else {
     size_t orow = static_cast<size_t>(row);
     if constexpr (EPI == EPI_PATCH_F32) {
-      const int bi = row / e.patches, p = row - bi * e.patches;
+      const int rowc = ok ? row : 0;                                  // keep the positional-embedding load in range
+      const int bi = rowc / e.patches, p = rowc - bi * e.patches;
       orow = static_cast<size_t>(bi) * (e.patches + 1) + 1 + p;
       const float4 q = __ldg(reinterpret_cast<const float4*>(e.pos + static_cast<size_t>(p + 1) * e.ldo + n));
       v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
     }
-    *reinterpret_cast<float4*>(e.out_f32 + orow * e.ldo + n) = v;
+    if (ok) *reinterpret_cast<float4*>(e.out_f32 + orow * e.ldo + n) = v;
   }
   return v;
 }
@@ -352,17 +356,16 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         for (int j = 0; j < 8; ++j) {
           const int rr = j * 4 + sub;
           const float4 v = ptx::lds128(stage_u32 + rr * 128 + ((unit ^ (rr & 7)) << 4));
-          if (row0 + rr < M) {
-            if constexpr (EPI == EPI_BIAS_RESID_F32) {
-              const float4 x = epilogue_apply<EPI, BF16>(v, row0 + rr, n, epi, bias4, j < 4 ? resid_a[j & 3] : resid_b[j & 3]);
-              st_s[j] += (x.x + x.y) + (x.z + x.w);
-              st_q[j] += (x.x * x.x + x.y * x.y) + (x.z * x.z + x.w * x.w);
-            } else if constexpr (epi_is_ln<EPI>()) {
-              epilogue_apply<EPI, BF16>(v, row0 + rr, n, epi, bias4, make_float4(0.f, 0.f, 0.f, 0.f), cs4, mean_j[j],
-                                        rstd_j[j]);
-            } else {
-              epilogue_apply<EPI, BF16>(v, row0 + rr, n, epi, bias4);
-            }
+          const bool ok = row0 + rr < M;
+          if constexpr (EPI == EPI_BIAS_RESID_F32) {
+            const float4 x = epilogue_apply<EPI, BF16>(ok, v, row0 + rr, n, epi, bias4, j < 4 ? resid_a[j & 3] : resid_b[j & 3]);
+            st_s[j] += (x.x + x.y) + (x.z + x.w);      // rows >= M accumulate garbage that is never stored
+            st_q[j] += (x.x * x.x + x.y * x.y) + (x.z * x.z + x.w * x.w);
+          } else if constexpr (epi_is_ln<EPI>()) {
+            epilogue_apply<EPI, BF16>(ok, v, row0 + rr, n, epi, bias4, make_float4(0.f, 0.f, 0.f, 0.f), cs4, mean_j[j],
+                                      rstd_j[j]);
+          } else {
+            epilogue_apply<EPI, BF16>(ok, v, row0 + rr, n, epi, bias4);
           }
         }
         __syncwarp();
