@@ -56,20 +56,25 @@ struct GemmEpi {
 
 
 // erf-GELU, x * Phi(x), with erf from Abramowitz & Stegun 7.1.26 (|abs err| <= 1.5e-7, far below the 16-bit store):
-//   erf(z) = 1 - (a1 t + ... + a5 t^5) exp(-z^2),  t = 1/(1 + p z),  z >= 0.
-// ~14 instructions (2 MUFU) instead of ~30 for erff(): the c_fc epilogue must stay below the 8192-cycle MMA time of
-// its tile with 128 activations per epilogue thread.
+//   erf(z) = 1 - (a1 t + ... + a5 t^5) exp(-z^2),  t = 1/(1 + p z),  z = |x|/sqrt(2) >= 0.
+// Written for the instruction count (this epilogue runs 128 times per thread per tile and bounds the c_fc GEMM):
+//   u = |x| sqrt(log2(e)/2)  so that  exp(-z^2) = ex2(-u^2)  and  1 + p z = 1 + (p / sqrt(log2 e)) u;
+//   q = Phi(-|x|) = (poly t) e / 2 (the 1/2 folded into the coefficients);
+//   x Phi(x) = max(x, 0) - |x| q   (x >= 0: x - x q;  x < 0: x q)   -- no compare / select.
+// 11 FMA-pipe instructions + 2 MUFU (rcp, ex2) per element.
 __device__ __forceinline__ float gelu_erf(float x) {
-  const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  const float ax = fabsf(x);
+  const float u = ax * 0.84932180028801904f;                       // sqrt(log2(e) / 2)
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.27273748f, u, 1.0f)));   // p / sqrt(log2 e), p = 0.3275911
   float poly = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
   poly = fmaf(poly, t, 0.5f * 1.421413741f);
   poly = fmaf(poly, t, 0.5f * -0.284496736f);
   poly = fmaf(poly, t, 0.5f * 0.254829592f);
   float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * z * z));
-  const float q = poly * t * e;              // = (1 - erf(z)) / 2 = Phi(-|x|)
-  return x * (x >= 0.f ? 1.0f - q : q);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-u * u));
+  const float q = (poly * t) * e;                                  // = (1 - erf(z)) / 2 = Phi(-|x|)
+  return fmaf(-ax, q, fmaxf(x, 0.0f));
 }
 __device__ __forceinline__ float quick_gelu(float x) { return x / (1.0f + __expf(-1.702f * x)); }
 
@@ -152,6 +157,9 @@ struct GemmPairCfg {
   static constexpr int A_BYTES = BM * BK * 2;             // 16 KiB
   static constexpr int B_BYTES = (BN / 2) * BK * 2;       // 16 KiB (BN 256) / 8 KiB (BN 128): this CTA's half
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+#ifndef AACLIP_GEMM_RESID_PREFETCH
+#define AACLIP_GEMM_RESID_PREFETCH 1
+#endif
 #ifndef AACLIP_GEMM_EPI_WARPS
 #define AACLIP_GEMM_EPI_WARPS 8
 #endif
@@ -283,9 +291,19 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint32_t acc_phase = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
       const int m_pair = tile / n_tiles, n_blk = tile - m_pair * n_tiles;
+      const int row0 = (2 * m_pair + static_cast<int>(rank)) * BM + q * 32;
+      if constexpr (EPI == EPI_BIAS_RESID_F32 && AACLIP_GEMM_RESID_PREFETCH)
+        // The residual rows this warp will add come from HBM (the stream is 180 MB, far beyond L2): pull them into L2
+        // now, while the MMAs of this tile are still running, so that the loads in the chunk loop below are L2 hits
+        // (out-proj 3.39 -> 3.18 ms/step; skipped for long-K tiles, whose 20 us main loop outlives the prefetch).
+        // lane l: row row0 + l, COLS_PER_WARP fp32 = COLS_PER_WARP / 32 lines of 128 B.
+        if (num_kb <= 32 && row0 + lane < M) {
+          const float* rp = epi.out_f32 + static_cast<size_t>(row0 + lane) * epi.ldo + n_blk * BN + cg * COLS_PER_WARP;
+#pragma unroll
+          for (int i = 0; i < COLS_PER_WARP / 32; ++i) ptx::prefetch_l2(rp + i * 32);
+        }
       ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
       ptx::tc_fence_after();
-      const int row0 = (2 * m_pair + static_cast<int>(rank)) * BM + q * 32;
       const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + cg * COLS_PER_WARP;
       const int sub = lane >> 3, unit = lane & 7;
       // coalesced domain: this thread handles rows row0 + j*4 + sub (j < 8) in every 32-column chunk
