@@ -154,8 +154,7 @@ int launch_gemm(int epi_mode, bool bf16, const void* A, const void* W, int M, in
 }
 
 template <bool BF16>
-int launch_attention_t(const CUtensorMap& tq, const CUtensorMap& tkv, void* out, int B, int N, int D, int causal,
-                       cudaStream_t st) {
+int launch_attention_t(const CUtensorMap& tq, void* out, int B, int N, int D, int causal, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
     CUDA_TRY(cudaFuncSetAttribute(attention_tcgen05_kernel<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -165,7 +164,7 @@ int launch_attention_t(const CUtensorMap& tq, const CUtensorMap& tkv, void* out,
   dim3 grid((N + attn_cfg::BQ * attn_cfg::QT - 1) / (attn_cfg::BQ * attn_cfg::QT), D / 64, B);
   const float scale_log2 = 0.125f * 1.4426950408889634f;  // head_dim^-0.5 * log2(e)
   attention_tcgen05_kernel<BF16><<<grid, attn_cfg::THREADS, attn_cfg::SMEM_BYTES, st>>>(
-      tq, tkv, reinterpret_cast<uint16_t*>(out), N, D, causal, scale_log2);
+      tq, reinterpret_cast<uint16_t*>(out), N, D, causal, scale_log2);
   LAUNCH_CHECK("attention_tcgen05_kernel");
   return AACLIP_OK;
 }
@@ -173,16 +172,12 @@ int launch_attention_t(const CUtensorMap& tq, const CUtensorMap& tkv, void* out,
 int launch_attention(bool bf16, const void* qkv, void* out, int B, int N, int D, int causal, cudaStream_t st) {
   if (int rc = ensure_device()) return rc;
   if (B <= 0 || N <= 0 || D <= 0 || D % 64 != 0) return fail(AACLIP_EINVAL, "attention: bad shape B=%d N=%d D=%d", B, N, D);
-  // one tensor, two views: 128-row boxes for the Q tiles, 64-row boxes for the K / V tiles (rows past N read as zero)
-  CUtensorMap tq, tkv;
+  CUtensorMap tq;
   const uint64_t dims[3] = {(uint64_t)3 * D, (uint64_t)N, (uint64_t)B};
   const uint64_t str[2] = {(uint64_t)3 * D * 2, (uint64_t)N * 3 * D * 2};
-  const uint32_t box_q[3] = {attn_cfg::HD, attn_cfg::BQ, 1};
-  const uint32_t box_kv[3] = {attn_cfg::HD, attn_cfg::BKV, 1};
-  if (int rc = make_tmap_16(&tq, qkv, 3, dims, str, box_q, bf16)) return rc;
-  if (int rc = make_tmap_16(&tkv, qkv, 3, dims, str, box_kv, bf16)) return rc;
-  return bf16 ? launch_attention_t<true>(tq, tkv, out, B, N, D, causal, st)
-              : launch_attention_t<false>(tq, tkv, out, B, N, D, causal, st);
+  const uint32_t box[3] = {attn_cfg::HD, attn_cfg::BKV, 1};
+  if (int rc = make_tmap_16(&tq, qkv, 3, dims, str, box, bf16)) return rc;
+  return bf16 ? launch_attention_t<true>(tq, out, B, N, D, causal, st) : launch_attention_t<false>(tq, out, B, N, D, causal, st);
 }
 
 template <int D, bool BF16>
