@@ -53,10 +53,6 @@ constexpr float RESCALE_THRESHOLD = 8.0f;         // log2 units: P never exceeds
 #define AACLIP_ATTN_STAGGER 1
 #endif
 constexpr bool STAGGER = AACLIP_ATTN_STAGGER != 0;
-#ifndef AACLIP_ATTN_POLY_EVERY
-#define AACLIP_ATTN_POLY_EVERY 0
-#endif
-constexpr int POLY_EVERY = AACLIP_ATTN_POLY_EVERY;   // every POLY_EVERY-th PAIR computes its second exp2 on the FMA pipe (0 = never)
 }  // namespace attn_cfg
 
 __device__ __forceinline__ float max3(float a, float b, float c) {
@@ -68,21 +64,6 @@ __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
-}
-
-// exp2 on the FMA/ALU pipes (no MUFU): Cody-Waite split x = n + f, f in [-0.5, 0.5], cubic minimax 2^f (max rel.
-// error 7.5e-5, below the rounding of the 16-bit P it feeds), exponent patched in with one integer add.
-// The MUFU (4 ex2/clk per SM sub-partition) is the binding pipe of this kernel; a fixed share of the elements takes
-// this path so that both pipes finish together.
-__device__ __forceinline__ float ex2_poly(float x) {
-  x = fmaxf(x, -126.0f);
-  const float magic = 12582912.0f;            // 1.5 * 2^23: x + magic rounds x to the nearest integer in the low bits
-  const float t = x + magic;
-  const float f = x - (t - magic);
-  float p = fmaf(0.05517132207751274f, f, 0.24261054396629333f);
-  p = fmaf(p, f, 0.6932609677314758f);
-  p = fmaf(p, f, 0.9999281167984009f);
-  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
 
 template <bool BF16>
@@ -333,10 +314,8 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, uint16_t*
           uint32_t w[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            const float x0 = fmaf(__uint_as_float(s[c * 64 + 2 * i]), scale_log2, -m_used);
-            const float x1 = fmaf(__uint_as_float(s[c * 64 + 2 * i + 1]), scale_log2, -m_used);
-            const float p0 = ex2_approx(x0);
-            const float p1 = (POLY_EVERY > 0 && (i % POLY_EVERY) == POLY_EVERY - 1) ? ex2_poly(x1) : ex2_approx(x1);
+            const float p0 = ex2_approx(fmaf(__uint_as_float(s[c * 64 + 2 * i]), scale_log2, -m_used));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(s[c * 64 + 2 * i + 1]), scale_log2, -m_used));
             rs[(2 * i) & 3] += p0;
             rs[(2 * i + 1) & 3] += p1;
             w[i] = ptx::pack16<BF16>(p0, p1);
