@@ -23,11 +23,14 @@ KEEP = [
     "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__m_xbar2l1tex_read_bytes.sum.per_second",
     "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smsp__cycles_active.avg",
     "smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio", "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+    "sm__cycles_elapsed.max", "gpc__cycles_elapsed.avg.per_second", "smsp__issue_active.avg.pct_of_peak_sustained_active",
 ]
 
 
 def launches():
-    path = os.path.join(OUT, "launches.csv")
+    path = os.path.join(OUT, f"launches_{tag}.csv")
+    if not os.path.exists(path):
+        path = os.path.join(OUT, "launches.csv")
     if not os.path.exists(path):
         return
     lines = [l for l in open(path) if not l.startswith("==")]
@@ -36,8 +39,8 @@ def launches():
         name = row["Kernel Name"]
         v = float(row["Metric Value"].replace(",", ""))
         v *= {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(row["Metric Unit"], 1.0)
-        m = re.search(r"gemm_tcgen05_kernel<\(?(?:int\))?(\d+)", name)
-        key = f"gemm_tcgen05_kernel<EPI={m.group(1)}>" if m else re.sub(r"\(.*", "", name).replace("void ", "")
+        m = re.search(r"gemm_(?:tcgen05|pair)_kernel<\(?(?:int\))?(\d+)", name)
+        key = f"gemm_pair_kernel<EPI={m.group(1)}>" if m else re.sub(r"\(.*", "", name).replace("void ", "")
         a = agg.setdefault(key, [0, 0.0])
         a[0] += 1
         a[1] += v
