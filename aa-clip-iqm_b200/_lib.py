@@ -41,6 +41,7 @@ EPI_LN_BIAS_QGELU_BF16 = 10
 
 DT_F16 = 0
 DT_BF16 = 1
+DT_F32 = 2   # fp32-accuracy mode (handles only)
 
 PROF_CLASSES = ("gemm_misc", "attention", "layernorm", "other", "gemm_qkv", "gemm_out", "gemm_fc", "gemm_proj")
 

@@ -14,6 +14,7 @@
 #include "../../include/aaclip.h"
 #include "attention_tcgen05.cuh"
 #include "elementwise.cuh"
+#include "fp32_path.cuh"
 #include "gemm_tcgen05.cuh"
 
 namespace {
@@ -229,6 +230,42 @@ int launch_pack(bool bf16, const float* src, void* dst, long long R, long long C
   return AACLIP_OK;
 }
 
+// fp32-accuracy mode: SIMT SGEMM / attention (fp32_path.cuh)
+int launch_sgemm(int epi_mode, const float* A, const float* W, int M, int N, int K, const GemmEpi& epi, cudaStream_t st) {
+  if (M <= 0 || N <= 0 || K <= 0 || N % sgemm_cfg::BN != 0 || K % sgemm_cfg::BK != 0)
+    return fail(AACLIP_EINVAL, "sgemm: unsupported shape M=%d N=%d K=%d (need N%%128==0, K%%16==0)", M, N, K);
+  dim3 grid(N / sgemm_cfg::BN, (M + sgemm_cfg::BM - 1) / sgemm_cfg::BM);
+#define AACLIP_SGEMM_CASE(E) \
+  case E: sgemm_f32_kernel<E><<<grid, sgemm_cfg::THREADS, 0, st>>>(A, W, M, N, K, epi); break;
+  switch (epi_mode) {
+    AACLIP_SGEMM_CASE(EPI_BIAS_GELU_BF16)     // (names shared with the 16-bit epilogues; outputs are fp32 here)
+    AACLIP_SGEMM_CASE(EPI_BIAS_QGELU_BF16)
+    AACLIP_SGEMM_CASE(EPI_BIAS_RESID_F32)
+    AACLIP_SGEMM_CASE(EPI_F32)
+    AACLIP_SGEMM_CASE(EPI_LEAKY_F32)
+    AACLIP_SGEMM_CASE(EPI_PATCH_F32)
+    AACLIP_SGEMM_CASE(EPI_BIAS_F32)
+#undef AACLIP_SGEMM_CASE
+    default: return fail(AACLIP_EINVAL, "sgemm: unknown epilogue %d", epi_mode);
+  }
+  LAUNCH_CHECK("sgemm_f32_kernel");
+  return AACLIP_OK;
+}
+
+int launch_attention_f32(const float* qkv, float* out, int B, int N, int D, int causal, cudaStream_t st) {
+  if (B <= 0 || N <= 0 || D <= 0 || D % 64 != 0) return fail(AACLIP_EINVAL, "attention: bad shape B=%d N=%d D=%d", B, N, D);
+  attention_f32_kernel<<<dim3((N + 127) / 128, D / 64, B), 128, 0, st>>>(qkv, out, N, D, causal);
+  LAUNCH_CHECK("attention_f32_kernel");
+  return AACLIP_OK;
+}
+
+// fp32 [R,C] -> fp32 [R,Cp] (destination pre-zeroed): the fp32-mode counterpart of launch_pack
+int copy_pad_f32(const float* src, void* dst, long long R, long long C, long long Cp, cudaStream_t st) {
+  CUDA_TRY(cudaMemcpy2DAsync(dst, Cp * sizeof(float), src, C * sizeof(float), C * sizeof(float), R,
+                             cudaMemcpyDeviceToDevice, st));
+  return AACLIP_OK;
+}
+
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 }  // namespace
@@ -269,14 +306,16 @@ void erase_key(std::vector<std::string>& v, const std::string& key) {
 
 struct BlockOff { size_t ln1g, ln1b, ln2g, ln2b, bqkv, bout, bfc, bproj, wqkv, wout, wfc, wproj, csq, bfq, csf, bff; };
 
-BlockOff plan_block(ArenaPlan& plan, size_t W, size_t F) {
+// wb = bytes per GEMM-weight element: 2 (fp16 / bf16 operands) or 4 (fp32-accuracy mode: the uint16_t* weight
+// pointers of BlockW then address fp32 data)
+BlockOff plan_block(ArenaPlan& plan, size_t W, size_t F, size_t wb) {
   BlockOff o;
   o.ln1g = plan.take<float>(W); o.ln1b = plan.take<float>(W);
   o.ln2g = plan.take<float>(W); o.ln2b = plan.take<float>(W);
   o.bqkv = plan.take<float>(3 * W); o.bout = plan.take<float>(W);
   o.bfc = plan.take<float>(F); o.bproj = plan.take<float>(W);
-  o.wqkv = plan.take<uint16_t>(3 * W * W); o.wout = plan.take<uint16_t>(W * W);
-  o.wfc = plan.take<uint16_t>(F * W); o.wproj = plan.take<uint16_t>(W * F);
+  o.wqkv = plan.take<uint8_t>(3 * W * W * wb); o.wout = plan.take<uint8_t>(W * W * wb);
+  o.wfc = plan.take<uint8_t>(F * W * wb); o.wproj = plan.take<uint8_t>(W * F * wb);
   o.csq = plan.take<float>(3 * W); o.bfq = plan.take<float>(3 * W);
   o.csf = plan.take<float>(F); o.bff = plan.take<float>(F);
   return o;
@@ -301,8 +340,8 @@ const char* const kBlockTensors[] = {"ln_1.weight", "ln_1.bias", "ln_2.weight", 
 // folded into (in_proj, c_fc) are kept in fp32 until fold_blocks() runs at the first forward; after that the block's
 // LayerNorm / in_proj / c_fc tensors are frozen (create a new handle to load different ones).
 int set_block_tensor(BlockW& b, const std::string& t, const std::string& key, std::vector<std::string>& missing,
-                     bool folded, bool bf16, int64_t W, int64_t F, const char* name, const float* data, int64_t n,
-                     cudaStream_t st) {
+                     bool folded, bool bf16, bool f32, int64_t W, int64_t F, const char* name, const float* data,
+                     int64_t n, cudaStream_t st) {
   auto copy_f32 = [&](float* dst, int64_t expect) -> int {
     if (n != expect) return fail(AACLIP_EINVAL, "%s: expected %lld elements, got %lld", name, (long long)expect, (long long)n);
     CUDA_TRY(cudaMemcpyAsync(dst, data, expect * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -311,11 +350,16 @@ int set_block_tensor(BlockW& b, const std::string& t, const std::string& key, st
   };
   auto pack = [&](uint16_t* dst, int64_t R, int64_t C) -> int {
     if (n != R * C) return fail(AACLIP_EINVAL, "%s: expected %lld x %lld elements, got %lld", name, (long long)R, (long long)C, (long long)n);
-    if (int rc = launch_pack(bf16, data, dst, R, C, C, st)) return rc;
+    if (f32) {
+      CUDA_TRY(cudaMemcpyAsync(dst, data, R * C * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    } else if (int rc = launch_pack(bf16, data, dst, R, C, C, st)) {
+      return rc;
+    }
     erase_key(missing, key);
     return AACLIP_OK;
   };
-  auto stage = [&](float** slot, int64_t R, int64_t C) -> int {
+  auto stage = [&](float** slot, uint16_t* direct, int64_t R, int64_t C) -> int {
+    if (f32) return pack(direct, R, C);          // fp32 mode: no LayerNorm folding, the weight is used as is
     if (n != R * C) return fail(AACLIP_EINVAL, "%s: expected %lld x %lld elements, got %lld", name, (long long)R, (long long)C, (long long)n);
     if (*slot == nullptr) CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(slot), R * C * sizeof(float)));
     CUDA_TRY(cudaMemcpyAsync(*slot, data, R * C * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -336,9 +380,9 @@ int set_block_tensor(BlockW& b, const std::string& t, const std::string& key, st
   if (t == "attn.out_proj.bias") return copy_f32(b.b_out, W);
   if (t == "mlp.c_fc.bias") return copy_f32(b.b_fc, F);
   if (t == "mlp.c_proj.bias") return copy_f32(b.b_proj, W);
-  if (t == "attn.in_proj_weight") return stage(&b.stage_qkv, 3 * W, W);
+  if (t == "attn.in_proj_weight") return stage(&b.stage_qkv, b.w_qkv, 3 * W, W);
   if (t == "attn.out_proj.weight") return pack(b.w_out, W, W);
-  if (t == "mlp.c_fc.weight") return stage(&b.stage_fc, F, W);
+  if (t == "mlp.c_fc.weight") return stage(&b.stage_fc, b.w_fc, F, W);
   if (t == "mlp.c_proj.weight") return pack(b.w_proj, W, F);
   return fail(AACLIP_EINVAL, "%s: unknown block tensor", name);
 }
@@ -377,13 +421,14 @@ constexpr int kStatCols = 256 / GemmPairCfg<256>::COL_GROUPS;
 inline int kStatPartials(size_t W) { return static_cast<int>(W) / kStatCols; }
 
 struct CoreWs { size_t x, x16, qkv, att, hid, abuf, stats, end; };
-CoreWs plan_core_ws(ArenaPlan& p, size_t M, size_t W, size_t F) {
+// ab = bytes per activation-operand element: 2, or 4 in fp32-accuracy mode (x16 then holds the fp32 LayerNorm output)
+CoreWs plan_core_ws(ArenaPlan& p, size_t M, size_t W, size_t F, size_t ab) {
   CoreWs w;
   w.x = p.take<float>(M * W);            // residual stream, fp32
-  w.x16 = p.take<uint16_t>(M * W);       // its raw 16-bit copy = A operand of QKV / c_fc / adapter GEMMs
-  w.qkv = p.take<uint16_t>(M * 3 * W);
-  w.att = p.take<uint16_t>(M * W);
-  w.hid = p.take<uint16_t>(M * F);
+  w.x16 = p.take<uint8_t>(M * W * ab);   // its raw 16-bit copy = A operand of QKV / c_fc / adapter GEMMs
+  w.qkv = p.take<uint8_t>(M * 3 * W * ab);
+  w.att = p.take<uint8_t>(M * W * ab);
+  w.hid = p.take<uint8_t>(M * F * ab);
   w.abuf = p.take<float>(M * W);
   w.stats = p.take<float>(M * kStatPartials(W) * 2);   // LayerNorm partials (sum, sumsq) per epilogue-warp column slice
   w.end = p.off;
@@ -395,6 +440,7 @@ CoreWs plan_core_ws(ArenaPlan& p, size_t M, size_t W, size_t F) {
 struct AaclipHandle {
   AaclipCfg cfg;
   bool bf16 = false;      // 16-bit operand dtype: fp16 (default) or bf16
+  bool f32 = false;       // fp32-accuracy mode (AACLIP_DT_F32): SIMT kernels, fp32 weights behind the uint16_t* pointers
   int G, P, N, KP;        // grid side, patches, tokens, padded patch K
   uint8_t* arena = nullptr;
   size_t arena_bytes = 0;
@@ -493,6 +539,58 @@ struct BlockRun {
   }
 };
 
+// The same block in fp32-accuracy mode: un-folded LayerNorms, SIMT fp32 GEMMs and attention (fp32_path.cuh).
+// The uint16_t* weight pointers of BlockW address fp32 data in this mode.
+struct BlockRunF32 {
+  AaclipHandle* prof;
+  int items, tokens, W, F, causal, act;
+  float* x; float* xn; float* qkv; float* att; float* hid; float* abuf;
+  cudaStream_t st;
+  int launches = 0;
+
+  int gemm(int epi, const float* A, const void* Wt, int m, int n, int k, const GemmEpi& e, int cls = AACLIP_PROF_GEMM) {
+    ProfScope ps(prof, cls, 2.0 * m * n * k, st);
+    ++launches;
+    return launch_sgemm(epi, A, reinterpret_cast<const float*>(Wt), m, n, k, e, st);
+  }
+  int lnorm(const float* in, const float* g, const float* b, float* o, int rows, int skipP) {
+    ProfScope ps(prof, AACLIP_PROF_LAYERNORM, 0.0, st);
+    ++launches;
+    return launch_layernorm(false, in, g, b, nullptr, o, rows, W, skipP, true, st);
+  }
+  int run(const BlockW& b, const uint16_t* w_adapter, float adapt_weight) {
+    const int M = items * tokens;
+    int rc;
+    if ((rc = lnorm(x, b.ln1_g, b.ln1_b, xn, M, 0))) return rc;
+    { GemmEpi e; e.bias = b.b_qkv; e.out_f32 = qkv; e.ldo = 3 * W;
+      if ((rc = gemm(EPI_BIAS_F32, xn, b.w_qkv, M, 3 * W, W, e, AACLIP_PROF_GEMM_QKV))) return rc; }
+    {
+      ProfScope ps(prof, AACLIP_PROF_ATTENTION, 4.0 * items * (W / 64) * (double)tokens * tokens * 64, st);
+      ++launches;
+      if ((rc = launch_attention_f32(qkv, att, items, tokens, W, causal, st))) return rc;
+    }
+    { GemmEpi e; e.bias = b.b_out; e.out_f32 = x; e.ldo = W;
+      if ((rc = gemm(EPI_BIAS_RESID_F32, att, b.w_out, M, W, W, e, AACLIP_PROF_GEMM_OUT))) return rc; }
+    if ((rc = lnorm(x, b.ln2_g, b.ln2_b, xn, M, 0))) return rc;
+    { GemmEpi e; e.bias = b.b_fc; e.out_f32 = hid; e.ldo = F;
+      if ((rc = gemm(act == AACLIP_ACT_QUICK_GELU ? EPI_BIAS_QGELU_BF16 : EPI_BIAS_GELU_BF16, xn, b.w_fc, M, F, W, e, AACLIP_PROF_GEMM_FC))) return rc; }
+    { GemmEpi e; e.bias = b.b_proj; e.out_f32 = x; e.ldo = W;
+      if ((rc = gemm(EPI_BIAS_RESID_F32, hid, b.w_proj, M, W, F, e, AACLIP_PROF_GEMM_PROJ))) return rc; }
+    if (w_adapter != nullptr) {
+      { GemmEpi e; e.out_f32 = abuf; e.ldo = W;
+        if ((rc = gemm(EPI_LEAKY_F32, x, w_adapter, M, W, W, e))) return rc; }
+      ProfScope ps(prof, AACLIP_PROF_OTHER, 0.0, st);
+      const int grid = (M + 7) / 8;
+      const float w = adapt_weight, w1 = 1.0f - adapt_weight;
+      if (W == 1024) adapter_blend_kernel<1024, false><<<grid, 256, 0, st>>>(x, abuf, M, w, w1);
+      else adapter_blend_kernel<768, false><<<grid, 256, 0, st>>>(x, abuf, M, w, w1);
+      LAUNCH_CHECK("adapter_blend_kernel");
+      ++launches;
+    }
+    return AACLIP_OK;
+  }
+};
+
 }  // namespace
 
 extern "C" {
@@ -517,11 +615,14 @@ int aaclip_create(const AaclipCfg* cfg, AaclipHandle** out) {
       return fail(AACLIP_EINVAL, "levels must be ascending in 1..layers");
   }
   if (c.max_batch <= 0) return fail(AACLIP_EINVAL, "max_batch must be > 0");
-  if (c.operand_dtype != AACLIP_DT_F16 && c.operand_dtype != AACLIP_DT_BF16) return fail(AACLIP_EINVAL, "operand_dtype must be AACLIP_DT_F16 or AACLIP_DT_BF16");
+  if (c.operand_dtype != AACLIP_DT_F16 && c.operand_dtype != AACLIP_DT_BF16 && c.operand_dtype != AACLIP_DT_F32)
+    return fail(AACLIP_EINVAL, "operand_dtype must be AACLIP_DT_F16, AACLIP_DT_BF16 or AACLIP_DT_F32");
 
   AaclipHandle* h = new AaclipHandle();
   h->cfg = c;
   h->bf16 = (c.operand_dtype == AACLIP_DT_BF16);
+  h->f32 = (c.operand_dtype == AACLIP_DT_F32);
+  const size_t wb = h->f32 ? 4 : 2;       // bytes per GEMM-weight element
   h->G = c.img_size / c.patch;
   h->P = h->G * h->G;
   h->N = h->P + 1;
@@ -532,13 +633,13 @@ int aaclip_create(const AaclipCfg* cfg, AaclipHandle** out) {
   ArenaPlan plan;
   const size_t o_cls = plan.take<float>(W), o_pos = plan.take<float>((size_t)h->N * W);
   const size_t o_lpg = plan.take<float>(W), o_lpb = plan.take<float>(W), o_log = plan.take<float>(W), o_lob = plan.take<float>(W);
-  const size_t o_conv = plan.take<uint16_t>(W * h->KP);
+  const size_t o_conv = plan.take<uint8_t>(W * h->KP * wb);
   std::vector<BlockOff> bo(c.layers);
-  for (int i = 0; i < c.layers; ++i) bo[i] = plan_block(plan, W, F);
+  for (int i = 0; i < c.layers; ++i) bo[i] = plan_block(plan, W, F, wb);
   std::vector<size_t> o_ad(c.adapt_until), o_seg(c.n_levels);
-  for (int i = 0; i < c.adapt_until; ++i) o_ad[i] = plan.take<uint16_t>(W * W);
-  for (int l = 0; l < c.n_levels; ++l) o_seg[l] = plan.take<uint16_t>(E * W);
-  const size_t o_det = plan.take<uint16_t>(E * W);
+  for (int i = 0; i < c.adapt_until; ++i) o_ad[i] = plan.take<uint8_t>(W * W * wb);
+  for (int l = 0; l < c.n_levels; ++l) o_seg[l] = plan.take<uint8_t>(E * W * wb);
+  const size_t o_det = plan.take<uint8_t>(E * W * wb);
 
   h->arena_bytes = plan.off;
   cudaError_t e = cudaMalloc(&h->arena, h->arena_bytes);
@@ -605,7 +706,7 @@ int aaclip_set_weight(AaclipHandle* h, const char* name, const float* data, cons
   };
   auto pack = [&](uint16_t* dst, int64_t R, int64_t C, int64_t Cp, const std::string& key) -> int {
     if (n != R * C) return fail(AACLIP_EINVAL, "%s: expected %lld x %lld elements, got %lld", name, (long long)R, (long long)C, (long long)n);
-    if (int rc = launch_pack(h->bf16, data, dst, R, C, Cp, st)) return rc;
+    if (int rc = h->f32 ? copy_pad_f32(data, dst, R, C, Cp, st) : launch_pack(h->bf16, data, dst, R, C, Cp, st)) return rc;
     erase_key(h->missing, key);
     return AACLIP_OK;
   };
@@ -623,7 +724,7 @@ int aaclip_set_weight(AaclipHandle* h, const char* name, const float* data, cons
   if (sscanf(k.c_str(), "transformer.resblocks.%d.%95s", &idx, tail) == 2) {
     if (idx < 0 || idx >= c.layers) return fail(AACLIP_EINVAL, "%s: block index out of range", name);
     return set_block_tensor(h->blk[idx], tail, "blk." + std::to_string(idx) + "." + tail, h->missing, h->folded, h->bf16,
-                            W, F, name, data, n, st);
+                            h->f32, W, F, name, data, n, st);
   }
   if (sscanf(k.c_str(), "image_adapter.layer_adapters.%d.%95s", &idx, tail) == 2) {
     if (strcmp(tail, "fc.0.weight") != 0) return fail(AACLIP_EINVAL, "%s: unknown tensor", name);
@@ -649,13 +750,88 @@ static WsPlan plan_ws(const AaclipHandle* h, int B) {
   const size_t M = (size_t)B * h->N, MP = (size_t)B * h->P;
   ArenaPlan p;
   WsPlan w;
-  w.core = plan_core_ws(p, M, W, F);
-  w.patchA = p.take<uint16_t>(MP * h->KP);
-  w.tok = p.take<uint16_t>(MP * W);
+  const size_t ab = h->f32 ? 4 : 2;
+  w.core = plan_core_ws(p, M, W, F, ab);
+  w.patchA = p.take<uint8_t>(MP * h->KP * ab);
+  w.tok = p.take<uint8_t>(MP * W * ab);
   w.det = p.take<float>(MP * E);
   w.total = p.off;
   return w;
 }
+
+}  // extern "C"
+
+// aaclip_forward in fp32-accuracy mode: same data layout and launch order as the tensor-core path, un-folded
+// LayerNorms, SIMT fp32 GEMMs / attention, fp32 patch operand. Verification mode (BASELINE config 4).
+static int forward_f32(AaclipHandle* h, const float* images, int B, uint8_t* wsb, const WsPlan& ws, float* const* seg_out,
+                       float* det_out, float* const* tokens_out, float* cls_out, cudaStream_t st) {
+  const AaclipCfg& c = h->cfg;
+  const int W = c.width, F = c.mlp_dim, E = c.embed_dim, N = h->N, P = h->P;
+  const int M = B * N, MP = B * P;
+  int rc;
+  float* patchA = (float*)(wsb + ws.patchA);
+  float* tok = (float*)(wsb + ws.tok);
+  float* detbuf = (float*)(wsb + ws.det);
+  BlockRunF32 run;
+  run.prof = h; run.items = B; run.tokens = N; run.W = W; run.F = F; run.causal = 0; run.act = c.act;
+  run.x = (float*)(wsb + ws.core.x); run.xn = (float*)(wsb + ws.core.x16); run.qkv = (float*)(wsb + ws.core.qkv);
+  run.att = (float*)(wsb + ws.core.att); run.hid = (float*)(wsb + ws.core.hid); run.abuf = (float*)(wsb + ws.core.abuf);
+  run.st = st;
+  float* x = run.x;
+  int& launches = run.launches;
+  auto l2norm = [&](float* t, int rows) -> int {
+    ProfScope ps(h, AACLIP_PROF_OTHER, 0.0, st);
+    ++launches;
+    if (E == 768) l2norm_rows_kernel<768><<<(rows + 7) / 8, 256, 0, st>>>(t, rows);
+    else l2norm_rows_kernel<1024><<<(rows + 7) / 8, 256, 0, st>>>(t, rows);
+    LAUNCH_CHECK("l2norm_rows_kernel");
+    return AACLIP_OK;
+  };
+  {
+    ProfScope ps(h, AACLIP_PROF_OTHER, 0.0, st);
+    patch_gather_f32_kernel<<<dim3(h->G, B), 256, 0, st>>>(images, patchA, c.img_size, h->G, c.patch, h->KP);
+    LAUNCH_CHECK("patch_gather_f32_kernel"); ++launches;
+  }
+  { GemmEpi e; e.out_f32 = x; e.ldo = W; e.pos = h->pos; e.patches = P;
+    if ((rc = run.gemm(EPI_PATCH_F32, patchA, h->w_conv, MP, W, h->KP, e))) return rc; }
+  {
+    ProfScope ps(h, AACLIP_PROF_OTHER, 0.0, st);
+    cls_row_kernel<<<B, 256, 0, st>>>(x, h->cls, h->pos, N, W);
+    LAUNCH_CHECK("cls_row_kernel"); ++launches;
+  }
+  if ((rc = run.lnorm(x, h->lnpre_g, h->lnpre_b, x, M, 0))) return rc;
+  int level_idx = 0;
+  for (int i = 0; i < c.layers; ++i) {
+    if ((rc = run.run(h->blk[i], i < c.adapt_until ? h->w_adapter[i] : nullptr, c.adapt_weight))) return rc;
+    if (level_idx < c.n_levels && c.levels[level_idx] == i + 1) {
+      float* tok_out = (tokens_out != nullptr && tokens_out[level_idx] != nullptr) ? tokens_out[level_idx] : tok;
+      if ((rc = run.lnorm(x, h->lnpost_g, h->lnpost_b, tok_out, MP, P))) return rc;
+      const int proj_epi = c.proj_relu ? EPI_LEAKY_F32 : EPI_F32;
+      { GemmEpi e; e.out_f32 = seg_out[level_idx]; e.ldo = E;
+        if ((rc = run.gemm(proj_epi, tok_out, h->w_seg[level_idx], MP, E, W, e))) return rc; }
+      if ((rc = l2norm(seg_out[level_idx], MP))) return rc;
+      if (level_idx == c.n_levels - 1) {
+        { GemmEpi e; e.out_f32 = detbuf; e.ldo = E;
+          if ((rc = run.gemm(proj_epi, tok_out, h->w_det, MP, E, W, e))) return rc; }
+        if ((rc = l2norm(detbuf, MP))) return rc;
+        ProfScope ps(h, AACLIP_PROF_OTHER, 0.0, st);
+        mean_over_patches_kernel<<<dim3((E + 127) / 128, B), 128, 0, st>>>(detbuf, det_out, P, E);
+        LAUNCH_CHECK("mean_over_patches_kernel");
+        ++launches;
+      }
+      ++level_idx;
+    }
+  }
+  if (cls_out != nullptr) {
+    ProfScope ps(h, AACLIP_PROF_OTHER, 0.0, st);
+    gather_cls_kernel<<<B, 256, 0, st>>>(x, cls_out, N, W);
+    LAUNCH_CHECK("gather_cls_kernel"); ++launches;
+  }
+  h->last_launches = launches;
+  return AACLIP_OK;
+}
+
+extern "C" {
 
 size_t aaclip_workspace_bytes(AaclipHandle* h, int32_t B) {
   if (!h || B <= 0) return 0;
@@ -679,6 +855,7 @@ int aaclip_forward(AaclipHandle* h, const float* images, int32_t B, void* worksp
   const int W = c.width, F = c.mlp_dim, E = c.embed_dim, N = h->N, P = h->P;
   const int M = B * N, MP = B * P;
   int rc;
+  if (h->f32) return forward_f32(h, images, B, static_cast<uint8_t*>(workspace), ws, seg_out, det_out, tokens_out, cls_out, st);
   if (!h->folded) {      // first forward: fold ln_1 / ln_2 into the in_proj / c_fc weights (load-time work)
     if ((rc = fold_blocks(h->blk, h->bf16, W, F, st))) return rc;
     h->folded = true;
@@ -859,6 +1036,7 @@ int aaclip_score_maps(const float* const* seg, int32_t n_levels, const float* te
 struct AaclipTextHandle {
   AaclipTextCfg cfg;
   bool bf16 = false;
+  bool f32 = false;       // fp32-accuracy mode
   uint8_t* arena = nullptr;
   size_t arena_bytes = 0;
   float *tok_emb, *pos, *lnf_g, *lnf_b;
@@ -875,9 +1053,9 @@ static TextWsPlan plan_text_ws(const AaclipTextHandle* h, int n) {
   const size_t M = (size_t)n * h->cfg.context;
   ArenaPlan p;
   TextWsPlan w;
-  w.core = plan_core_ws(p, M, W, F);
+  w.core = plan_core_ws(p, M, W, F, h->f32 ? 4 : 2);
   w.eot = p.take<float>((size_t)n * W);
-  w.eot16 = p.take<uint16_t>((size_t)n * W);
+  w.eot16 = p.take<float>((size_t)n * W);      // 16-bit in the tensor-core modes, fp32 in fp32 mode
   w.total = p.off;
   return w;
 }
@@ -894,19 +1072,22 @@ int aaclip_text_create(const AaclipTextCfg* cfg, AaclipTextHandle** out) {
   if (c.mlp_dim % 256 != 0 || c.embed_dim % 256 != 0) return fail(AACLIP_EINVAL, "text mlp_dim/embed_dim must be multiples of 256");
   if (c.context <= 0 || c.vocab <= 0 || c.layers <= 0 || c.adapt_until < 0 || c.adapt_until > c.layers || c.max_sentences <= 0)
     return fail(AACLIP_EINVAL, "bad text configuration");
-  if (c.operand_dtype != AACLIP_DT_F16 && c.operand_dtype != AACLIP_DT_BF16) return fail(AACLIP_EINVAL, "operand_dtype must be AACLIP_DT_F16 or AACLIP_DT_BF16");
+  if (c.operand_dtype != AACLIP_DT_F16 && c.operand_dtype != AACLIP_DT_BF16 && c.operand_dtype != AACLIP_DT_F32)
+    return fail(AACLIP_EINVAL, "operand_dtype must be AACLIP_DT_F16, AACLIP_DT_BF16 or AACLIP_DT_F32");
   AaclipTextHandle* h = new AaclipTextHandle();
   h->cfg = c;
   h->bf16 = (c.operand_dtype == AACLIP_DT_BF16);
+  h->f32 = (c.operand_dtype == AACLIP_DT_F32);
+  const size_t wb = h->f32 ? 4 : 2;
   const size_t W = c.width, F = c.mlp_dim, E = c.embed_dim;
   ArenaPlan plan;
   const size_t o_tok = plan.take<float>((size_t)c.vocab * W), o_pos = plan.take<float>((size_t)c.context * W);
   const size_t o_lg = plan.take<float>(W), o_lb = plan.take<float>(W);
   std::vector<BlockOff> bo(c.layers);
-  for (int i = 0; i < c.layers; ++i) bo[i] = plan_block(plan, W, F);
+  for (int i = 0; i < c.layers; ++i) bo[i] = plan_block(plan, W, F, wb);
   std::vector<size_t> o_ad(c.adapt_until);
-  for (int i = 0; i < c.adapt_until; ++i) o_ad[i] = plan.take<uint16_t>(W * W);
-  const size_t o_proj = plan.take<uint16_t>(E * W);
+  for (int i = 0; i < c.adapt_until; ++i) o_ad[i] = plan.take<uint8_t>(W * W * wb);
+  const size_t o_proj = plan.take<uint8_t>(E * W * wb);
   h->arena_bytes = plan.off;
   cudaError_t e = cudaMalloc(&h->arena, h->arena_bytes);
   if (e == cudaSuccess) e = cudaMemset(h->arena, 0, h->arena_bytes);
@@ -957,7 +1138,7 @@ int aaclip_text_set_weight(AaclipTextHandle* h, const char* name, const float* d
   };
   auto pack = [&](uint16_t* dst, int64_t R, int64_t C, const std::string& key) -> int {
     if (n != R * C) return fail(AACLIP_EINVAL, "%s: expected %lld x %lld elements, got %lld", name, (long long)R, (long long)C, (long long)n);
-    if (int rc = launch_pack(h->bf16, data, dst, R, C, C, st)) return rc;
+    if (int rc = h->f32 ? copy_pad_f32(data, dst, R, C, C, st) : launch_pack(h->bf16, data, dst, R, C, C, st)) return rc;
     erase_key(h->missing, key);
     return AACLIP_OK;
   };
@@ -970,7 +1151,7 @@ int aaclip_text_set_weight(AaclipTextHandle* h, const char* name, const float* d
   if (sscanf(k.c_str(), "transformer.resblocks.%d.%95s", &idx, tail) == 2) {
     if (idx < 0 || idx >= c.layers) return fail(AACLIP_EINVAL, "%s: block index out of range", name);
     return set_block_tensor(h->blk[idx], tail, "blk." + std::to_string(idx) + "." + tail, h->missing, h->folded, h->bf16,
-                            W, F, name, data, n, st);
+                            h->f32, W, F, name, data, n, st);
   }
   if (sscanf(k.c_str(), "text_adapter.%d.%95s", &idx, tail) == 2) {
     if (strcmp(tail, "fc.0.weight") != 0) return fail(AACLIP_EINVAL, "%s: unknown tensor", name);
@@ -1001,11 +1182,30 @@ int aaclip_encode_text(AaclipTextHandle* h, const int32_t* tokens, int32_t n, vo
   const int M = n * T;
   const bool bf = h->bf16;
   int rc;
+  uint8_t* wsb = static_cast<uint8_t*>(workspace);
+  if (h->f32) {
+    // fp32-accuracy mode: same sequence, un-folded LayerNorms, SIMT fp32 kernels
+    BlockRunF32 r32;
+    r32.prof = nullptr; r32.items = n; r32.tokens = T; r32.W = W; r32.F = F; r32.causal = 1; r32.act = c.act;
+    r32.x = (float*)(wsb + ws.core.x); r32.xn = (float*)(wsb + ws.core.x16); r32.qkv = (float*)(wsb + ws.core.qkv);
+    r32.att = (float*)(wsb + ws.core.att); r32.hid = (float*)(wsb + ws.core.hid); r32.abuf = (float*)(wsb + ws.core.abuf);
+    r32.st = st;
+    float* eot32 = (float*)(wsb + ws.eot);
+    float* eotn = (float*)(wsb + ws.eot16);
+    text_embed_kernel<<<M, 192, 0, st>>>(tokens, h->tok_emb, h->pos, r32.x, T, W, c.vocab);
+    LAUNCH_CHECK("text_embed_kernel");
+    for (int i = 0; i < c.layers; ++i)
+      if ((rc = r32.run(h->blk[i], i < c.adapt_until ? h->w_adapter[i] : nullptr, c.adapt_weight))) return rc;
+    text_gather_eot_kernel<<<n, 192, 0, st>>>(tokens, r32.x, eot32, T, W);
+    LAUNCH_CHECK("text_gather_eot_kernel");
+    if ((rc = r32.lnorm(eot32, h->lnf_g, h->lnf_b, eotn, n, 0))) return rc;
+    GemmEpi e; e.out_f32 = out; e.ldo = E;
+    return r32.gemm(EPI_LEAKY_F32, eotn, h->w_proj, n, E, W, e);
+  }
   if (!h->folded) {
     if ((rc = fold_blocks(h->blk, bf, W, F, st))) return rc;
     h->folded = true;
   }
-  uint8_t* wsb = static_cast<uint8_t*>(workspace);
   BlockRun run;
   run.prof = nullptr; run.bf16 = bf; run.items = n; run.tokens = T; run.W = W; run.F = F; run.causal = 1; run.act = c.act;
   run.x = (float*)(wsb + ws.core.x); run.x16 = (uint16_t*)(wsb + ws.core.x16); run.qkv = (uint16_t*)(wsb + ws.core.qkv);

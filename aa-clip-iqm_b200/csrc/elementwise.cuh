@@ -44,6 +44,26 @@ __global__ void patch_gather_kernel(const float* __restrict__ img, uint16_t* __r
   }
 }
 
+// fp32-accuracy mode: same gather, fp32 out (columns >= 3*ps*ps zeroed)
+__global__ void patch_gather_f32_kernel(const float* __restrict__ img, float* __restrict__ A, int S, int G, int ps,
+                                        int KP) {
+  const int py = blockIdx.x, b = blockIdx.y;
+  const int W = G * ps;
+  for (int cr = 0; cr < 3 * ps; ++cr) {
+    const int c = cr / ps, ky = cr - c * ps;
+    const float* src = img + ((static_cast<size_t>(b) * 3 + c) * S + (py * ps + ky)) * S;
+    for (int x = threadIdx.x; x < W; x += blockDim.x) {
+      const int px = x / ps, kx = x - px * ps;
+      A[((static_cast<size_t>(b) * G + py) * G + px) * KP + (c * ps + ky) * ps + kx] = src[x];
+    }
+  }
+  const int k_raw = 3 * ps * ps, pad = KP - k_raw;
+  for (int i = threadIdx.x; i < G * pad; i += blockDim.x) {
+    const int px = i / pad, k = k_raw + (i - px * pad);
+    A[((static_cast<size_t>(b) * G + py) * G + px) * KP + k] = 0.f;
+  }
+}
+
 // x[b*(P+1), :] = class_embedding + positional_embedding[0, :]      (model/adapter.py:143-153)
 __global__ void cls_row_kernel(float* __restrict__ x, const float* __restrict__ cls, const float* __restrict__ pos,
                                int tokens, int D) {

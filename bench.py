@@ -179,7 +179,7 @@ def run_ours(args):
     sd = weights.make_visual_state_dict(seed=args.seed, img_size=S)
     text = weights.make_text_anchor(args.seed)
     pred = pipeline.AnomalyPredictor(sd, text, img_size=S, device=dev, domain="Industrial", max_batch=B,
-                                     operand_dtype=_lib.DT_BF16 if args.dtype == "bf16" else _lib.DT_F16)
+                                     operand_dtype={"bf16": _lib.DT_BF16, "fp16": _lib.DT_F16, "fp32": _lib.DT_F32}[args.dtype])
     del sd
     # two resident input batches, alternated (2 x 103 MB > 126 MB L2; the step's own working set is > 1 GB anyway)
     n_in = 2
@@ -273,12 +273,14 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": max(Wm, 3),
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f16" if args.dtype == "fp16" else "bf16", "data": "synthetic",
+            "dtype": {"fp16": "f16", "bf16": "bf16", "fp32": "f32"}[args.dtype], "data": "synthetic",
             "config": {"workload": f"ViT-L-14-336 @{S} batch {B} per GPU (visual tower + adapters + similarity maps)",
                        "img_size": S, "batch_per_gpu": B, "global_batch": world * B, "parallelism": f"dp{world}",
                        "weights": "random-init (seeded), reference architecture",
-                       "operands": "fp16 tensor-core operands, fp32 accumulate/residual/LN/softmax"
-                       if args.dtype == "fp16" else "bf16 tensor-core operands, fp32 accumulate",
+                       "operands": {"fp16": "fp16 tensor-core operands, fp32 accumulate/residual/LN/softmax",
+                                    "bf16": "bf16 tensor-core operands, fp32 accumulate",
+                                    "fp32": "fp32-accuracy mode (BASELINE config 4): SIMT fp32 GEMM/attention, a "
+                                            "verification mode, not the headline path"}[args.dtype],
                        "l2": "2 input batches alternated (2x103 MB) and >1 GB activations per step: larger than the 126 MB L2"},
             "tensor_frac_of_burst_peak": ips / world * fpi / (pk["bf16_tflops"] * 1e12),
             "tensor_frac_of_sustained_peak": ips / world * fpi / ((pk["bf16_tflops_sustained"] or pk["bf16_tflops"]) * 1e12),
@@ -306,7 +308,8 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--batch", type=int, default=32, help="images per GPU per step (BASELINE configs[1]: 32)")
     ap.add_argument("--img-size", type=int, default=518)
-    ap.add_argument("--dtype", choices=["fp16", "bf16"], default="fp16", help="16-bit tensor-core operand type")
+    ap.add_argument("--dtype", choices=["fp16", "bf16", "fp32"], default="fp16",
+                    help="tensor-core operand type; fp32 = the fp32-accuracy verification mode (BASELINE config 4)")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -43,6 +43,9 @@ extern "C" {
  * (3 fewer mantissa bits) do not (DESIGN.md "Precision"). Stores saturate to +-65504 in F16 mode. */
 #define AACLIP_DT_F16 0
 #define AACLIP_DT_BF16 1
+/* fp32-accuracy mode (handles only): the same launch sequence with fp32 SIMT GEMM / attention kernels and un-folded
+ * LayerNorms; reproduces the reference's fp32 maps to <= 1e-4 (BASELINE config 4). A verification mode, ~30x slower. */
+#define AACLIP_DT_F32 2
 
 /* epilogue selectors of aaclip_gemm16 (unit-test / building-block entry point); "BF16" in these names means
  * "the 16-bit operand dtype" */
@@ -75,7 +78,7 @@ typedef struct AaclipCfg {
   int32_t proj_relu;     /* SimpleProj(relu=...) : LeakyReLU after seg/det projections */
   float adapt_weight;    /* i_w = 0.1 */
   int32_t max_batch;     /* largest B accepted by aaclip_forward */
-  int32_t operand_dtype; /* AACLIP_DT_F16 (default) or AACLIP_DT_BF16 */
+  int32_t operand_dtype; /* AACLIP_DT_F16 (default), AACLIP_DT_BF16, or AACLIP_DT_F32 (fp32-accuracy mode) */
 } AaclipCfg;
 
 typedef struct AaclipHandle AaclipHandle;

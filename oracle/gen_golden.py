@@ -28,10 +28,11 @@ CASES = [
     ("vitl_224_b2", 224, 2, 1, False),
     ("vitl_518_b1", 518, 1, 2, False),
     ("vitl_224_b1_relu", 224, 1, 3, True),
+    ("vitl_336_b2", 336, 2, 4, False),      # BASELINE config 4 (fp32-accuracy mode @336)
 ]
 
 
-def main():
+def main(only=None):
     ref_import.install()
     os.chdir(ref_import.REF_ROOT)  # the reference uses ./dataset/... relative paths at import time
     import aaclip_b200  # noqa: F401
@@ -44,6 +45,8 @@ def main():
     out_dir = os.path.join(REPO, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
     for name, S, B, seed, relu in CASES:
+        if only and name not in only:
+            continue
         t0 = time.time()
         sd = weights.make_visual_state_dict(seed=seed, img_size=S, relu=relu)
         clip = create_model("ViT-L-14-336", img_size=S, pretrained=None, force_image_size=S, device="cpu").eval()
@@ -100,4 +103,4 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    main(sys.argv[1:] or None)
