@@ -171,6 +171,16 @@ def _declare(lib):
     lib.aaclip_encode_text.argtypes = [vp, vp, i32, vp, sz, vp, vp]
     lib.aaclip_text_anchors.restype = i32
     lib.aaclip_text_anchors.argtypes = [vp, vp, i32, i32, vp, vp]
+    lib.aaclip_metrics_workspace_bytes.restype = sz
+    lib.aaclip_metrics_workspace_bytes.argtypes = []
+    lib.aaclip_minmax.restype = i32
+    lib.aaclip_minmax.argtypes = [vp, i64, vp, vp, i32, vp]
+    lib.aaclip_score_histogram.restype = i32
+    lib.aaclip_score_histogram.argtypes = [vp, vp, i64, vp, i32, vp, vp]
+    lib.aaclip_auc_ap.restype = i32
+    lib.aaclip_auc_ap.argtypes = [vp, i32, vp, vp]
+    lib.aaclip_row_max.restype = i32
+    lib.aaclip_row_max.argtypes = [vp, i32, i64, vp, vp]
     lib.aaclip_gemm16.restype = i32
     lib.aaclip_gemm16.argtypes = [i32, vp, vp, i32, i32, i32, i32, vp, vp, vp, i32, vp]
     lib.aaclip_ln_fold.restype = i32
@@ -192,6 +202,7 @@ EXPORTED_SYMBOLS = [
     "aaclip_missing_weights", "aaclip_workspace_bytes", "aaclip_forward", "aaclip_score_workspace_bytes",
     "aaclip_score_maps", "aaclip_last_launch_count", "aaclip_stat_columns", "aaclip_profile_enable", "aaclip_profile_read", "aaclip_gemm16", "aaclip_attention", "aaclip_layernorm",
     "aaclip_pack16",
+    "aaclip_metrics_workspace_bytes", "aaclip_minmax", "aaclip_score_histogram", "aaclip_auc_ap", "aaclip_row_max",
     "aaclip_ln_fold", "aaclip_gemm16_ln", "aaclip_gemm16_resid",
     "aaclip_text_create", "aaclip_text_destroy", "aaclip_text_set_weight", "aaclip_text_missing_weights",
     "aaclip_text_workspace_bytes", "aaclip_encode_text", "aaclip_text_anchors",

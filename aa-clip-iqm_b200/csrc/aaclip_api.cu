@@ -16,6 +16,7 @@
 #include "elementwise.cuh"
 #include "fp32_path.cuh"
 #include "gemm_tcgen05.cuh"
+#include "metrics.cuh"
 
 namespace {
 
@@ -1243,6 +1244,46 @@ int aaclip_text_anchors(const float* emb, const int32_t* offsets, int32_t n_grou
 }  // extern "C"
 
 extern "C" {
+
+// ---- on-device evaluation metrics (metrics.cuh)
+size_t aaclip_metrics_workspace_bytes(void) { return 2 * METRIC_PARTIALS * sizeof(float); }
+
+int aaclip_minmax(const float* x, int64_t n, void* workspace, float* minmax, int32_t merge, void* stream) {
+  if (!x || !workspace || !minmax || n <= 0) return fail(AACLIP_EINVAL, "aaclip_minmax: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long blocks_needed = (n + 1023) / 1024;
+  const int grid = static_cast<int>(blocks_needed < METRIC_PARTIALS ? blocks_needed : METRIC_PARTIALS);
+  float* partials = static_cast<float*>(workspace);
+  minmax_partial_kernel<<<grid, 256, 0, st>>>(x, n, partials);
+  LAUNCH_CHECK("minmax_partial_kernel");
+  minmax_final_kernel<<<1, 256, 0, st>>>(partials, grid, minmax, merge);
+  LAUNCH_CHECK("minmax_final_kernel");
+  return AACLIP_OK;
+}
+
+int aaclip_score_histogram(const float* x, const uint8_t* labels, int64_t n, const float* minmax, int32_t n_bins,
+                           uint32_t* hist, void* stream) {
+  if (!x || !labels || !hist || n <= 0 || n_bins < 2) return fail(AACLIP_EINVAL, "aaclip_score_histogram: bad argument");
+  const long long blocks_needed = (n + 255) / 256;
+  const int grid = static_cast<int>(blocks_needed < 148 * 16 ? blocks_needed : 148 * 16);
+  score_histogram_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, labels, n, minmax, minmax != nullptr, n_bins, hist);
+  LAUNCH_CHECK("score_histogram_kernel");
+  return AACLIP_OK;
+}
+
+int aaclip_auc_ap(const uint32_t* hist, int32_t n_bins, double* out, void* stream) {
+  if (!hist || !out || n_bins < 2) return fail(AACLIP_EINVAL, "aaclip_auc_ap: bad argument");
+  auc_ap_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(hist, n_bins, out);
+  LAUNCH_CHECK("auc_ap_kernel");
+  return AACLIP_OK;
+}
+
+int aaclip_row_max(const float* x, int32_t rows, int64_t cols, float* out, void* stream) {
+  if (!x || !out || rows <= 0 || cols <= 0) return fail(AACLIP_EINVAL, "aaclip_row_max: bad argument");
+  row_max_kernel<<<rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, cols, out);
+  LAUNCH_CHECK("row_max_kernel");
+  return AACLIP_OK;
+}
 
 int aaclip_gemm16(int32_t dtype, const void* A, const void* W, int32_t M, int32_t N, int32_t K, int32_t epi,
                   const float* bias, float* out_f32, void* out_16, int32_t ldo, void* stream) {

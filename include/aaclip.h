@@ -213,6 +213,23 @@ int aaclip_encode_text(AaclipTextHandle* h, const int32_t* tokens, int32_t n_sen
 int aaclip_text_anchors(const float* emb, const int32_t* offsets, int32_t n_groups, int32_t E, float* anchors,
                         void* stream);
 
+/* ---- on-device evaluation metrics ------------------------------------------------------ */
+/* Replace the scikit-learn calls of forward_utils.metrics_eval (forward_utils.py:246-249,275,288-296): global min-max
+ * normalisation, per-image maximum, AUROC and average precision, computed from two fine score histograms (positives,
+ * negatives). min/max and histograms are additive across ranks: a data-parallel evaluation all-reduces them instead
+ * of gathering the maps. */
+size_t aaclip_metrics_workspace_bytes(void);
+/* minmax[0..1] = (min, max) of x[0..n); merge != 0 also folds the previous content of minmax (streaming batches). */
+int aaclip_minmax(const float* x, int64_t n, void* workspace, float* minmax, int32_t merge, void* stream);
+/* hist[label * n_bins + bin] += 1, bin = floor(n_bins * (x - min) / (max - min)) (minmax == NULL: x is already in
+ * [0,1]); labels uint8 in {0,1}; hist uint32 [2][n_bins], zeroed by the caller before the first batch. */
+int aaclip_score_histogram(const float* x, const uint8_t* labels, int64_t n, const float* minmax, int32_t n_bins,
+                           uint32_t* hist, void* stream);
+/* out[0] = AUROC, out[1] = average precision, out[2] = #positives, out[3] = #negatives (doubles, device). */
+int aaclip_auc_ap(const uint32_t* hist, int32_t n_bins, double* out, void* stream);
+/* out[r] = max_c x[r, c]: the per-image maximum of the normalised maps (pmax, forward_utils.py:275). */
+int aaclip_row_max(const float* x, int32_t rows, int64_t cols, float* out, void* stream);
+
 /* ---- building blocks, exported for the parity tests (each is exactly what aaclip_forward launches) ---- */
 
 /* C[M,N] = A[M,K] * W[N,K]^T with a fused epilogue (tcgen05/TMEM/TMA GEMM). A, W: `dtype` row-major.

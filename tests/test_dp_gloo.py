@@ -84,3 +84,37 @@ def test_single_process_gather_is_identity():
     m, s = torch.zeros(3, 4, 4), torch.zeros(3)
     gm, gs = dp.gather_predictions(m, s)
     assert gm is m and gs is s
+
+
+def _metrics_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import aaclip_b200  # noqa: F401
+        from aaclip_b200 import metrics
+        # the statistics the device metrics reduce across ranks: (min, max) and the two count histograms
+        mm = metrics.reduce_minmax(torch.tensor([-1.0 - rank, 2.0 + 3 * rank]))
+        hist = torch.zeros(2, 16, dtype=torch.int32)
+        hist[rank, rank + 3] = 5 + rank
+        hist[0, 0] = 1
+        total = metrics.reduce_histogram(hist)
+        if rank == 0:
+            want = torch.zeros(2, 16, dtype=torch.int64)
+            want[0, 3], want[1, 4], want[0, 0] = 5, 6, 2
+            q.put((mm.tolist() == [-2.0, 5.0], torch.equal(total, want)))
+    finally:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def test_metric_statistics_reduce_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_metrics_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) == (True, True)
