@@ -16,6 +16,7 @@ class (tensor bound) timed live with CUDA events on the launch stream; cpu_basel
 box's host cores on a bounded sample (N=1 only). `--impl reference` times that CPU path alone.
 """
 import argparse
+import datetime
 import json
 import os
 import sys
@@ -170,7 +171,8 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # a short collective timeout: a rank that falls out of step must fail in minutes, not hold the box
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     S, B, K, Wm = args.img_size, args.batch, args.steps, args.warmup
     if os.environ.get("AACLIP_LIB_PATH"):
         _lib.build()  # developer sweep of kernel variants (tools/sweep.sh); the default run only loads the in-tree build
@@ -242,7 +244,7 @@ def run_ours(args):
         pred.engine.profile_enable(True)
         n_prof = min(K, 3)
         for i in range(n_prof):
-            step_device(i)
+            pred.predict_device(dev_imgs[i % n_in])   # rank-local: no collective here (only rank 0 profiles)
         torch.cuda.synchronize()
         prof = pred.engine.profile_read()
         pred.engine.profile_enable(False)
@@ -255,7 +257,7 @@ def run_ours(args):
                                tflops=g["flops"] / (g["ms"] * 1e-3) / 1e12)
         achieved = g["flops"] / (g["ms"] * 1e-3) / 1e12
         peak = pk["bf16_tflops_sustained"] or pk["bf16_tflops"]
-        roof = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (all epilogues)", "achieved": achieved, "peak": peak,
+        roof = {"bound": "tensor", "kernel": "gemm_pair_kernel (tcgen05 cta_group::2, all epilogues)", "achieved": achieved, "peak": peak,
                 "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
                 "peak_source": f"{pk['source']} (sustained cuBLAS bf16; burst {pk['bf16_tflops']})",
                 "avg_launch_ms": g["ms"] / max(1, g["launches"]), "launches_per_step": g["launches"] // n_prof,
