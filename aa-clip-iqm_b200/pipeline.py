@@ -62,3 +62,57 @@ class AnomalyPredictor:
         maps, scores = self.predict_device(dev_in)
         maps_out_pinned.copy_(maps, non_blocking=True)
         scores_out_pinned.copy_(scores, non_blocking=True)
+
+
+class HostStream:
+    """Pipelined host-to-host evaluation: pinned host images in, pinned host maps / scores out, with the PCIe copies of
+    batch i+1 and batch i-1 overlapped with the kernels of batch i (separate copy streams, two device slots).
+
+    This is the steady state of the reference's evaluation loop (test_last.py:70-151: ``image.to(device)`` ...
+    ``final_map.cpu().numpy()`` per batch) without its per-batch synchronisation. ``submit`` returns a CUDA event;
+    the outputs of that batch are valid once the event has completed (``event.synchronize()``)."""
+
+    def __init__(self, predictor: AnomalyPredictor, slots: int = 2):
+        self.p = predictor
+        dev, B, S = predictor.device, predictor.max_batch, predictor.img_size
+        self.slots = slots
+        self.h2d = torch.cuda.Stream(device=dev)
+        self.d2h = torch.cuda.Stream(device=dev)
+        self.compute = torch.cuda.Stream(device=dev)
+        self.dev_in = [torch.empty((B, 3, S, S), dtype=torch.float32, device=dev) for _ in range(slots)]
+        self.dev_maps = [None] * slots          # keeps the device outputs of a slot alive until its D2H has run
+        self.in_free = [torch.cuda.Event() for _ in range(slots)]     # compute has consumed dev_in[slot]
+        self.out_done = [torch.cuda.Event() for _ in range(slots)]    # D2H of the slot's outputs has completed
+        self.i = 0
+
+    def submit(self, images_pinned: torch.Tensor, maps_out_pinned: torch.Tensor,
+               scores_out_pinned: torch.Tensor) -> torch.cuda.Event:
+        slot = self.i % self.slots
+        first_use = self.i < self.slots
+        self.i += 1
+        B = images_pinned.shape[0]
+        with torch.cuda.stream(self.h2d):
+            if not first_use:
+                self.h2d.wait_event(self.in_free[slot])            # the previous occupant has been read by the kernels
+            self.dev_in[slot][:B].copy_(images_pinned, non_blocking=True)
+            copied = torch.cuda.Event()
+            copied.record(self.h2d)
+        with torch.cuda.stream(self.compute):
+            self.compute.wait_event(copied)
+            if not first_use:
+                self.compute.wait_event(self.out_done[slot])       # the slot's previous outputs have left the device
+            maps, scores = self.p.predict_device(self.dev_in[slot][:B])
+            self.in_free[slot].record(self.compute)
+            computed = torch.cuda.Event()
+            computed.record(self.compute)
+        self.dev_maps[slot] = (maps, scores)
+        with torch.cuda.stream(self.d2h):
+            self.d2h.wait_event(computed)
+            maps_out_pinned.copy_(maps, non_blocking=True)
+            scores_out_pinned.copy_(scores, non_blocking=True)
+            self.out_done[slot].record(self.d2h)
+        return self.out_done[slot]
+
+    def drain(self):
+        self.d2h.synchronize()
+        self.compute.synchronize()
