@@ -51,7 +51,7 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clock + throttle reasons of one GPU every 200 ms through NVML while the timed region runs."""
+    """Samples SM clock + throttle reasons of one GPU every 50 ms through NVML while the timed region runs."""
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
@@ -89,7 +89,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(nm)
             except Exception:
                 pass
-            self._stop_evt.wait(0.2)
+            self._stop_evt.wait(0.05)
 
     def stop(self):
         self._stop_evt.set()
@@ -273,7 +273,11 @@ def run_ours(args):
         achieved = g["flops"] / (g["ms"] * 1e-3) / 1e12
         peak = pk["bf16_tflops_sustained"] or pk["bf16_tflops"]
         roof = {"bound": "tensor", "kernel": "gemm_pair_kernel (tcgen05 cta_group::2, all epilogues)", "achieved": achieved, "peak": peak,
-                "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                "unit": "TFLOP/s", "frac": achieved / peak,
+                # dram__bytes_read + dram__bytes_write per launch, launch-weighted mean over one step's 108 GEMM launches
+                # (ncu --set full capture of the same kernels, profiles/r01b_prof_gemm_r01b.txt: qkv 319 MB, c_fc 413 MB,
+                # c_proj 826 MB, out-proj 488 MB, adapter 216 MB); only meaningful for the B=32 @518 workload
+                "traffic": 4.67e8 if (S == 518 and B == 32 and args.dtype != "fp32") else None,
                 "peak_source": f"{pk['source']} (sustained cuBLAS bf16; burst {pk['bf16_tflops']})",
                 "avg_launch_ms": g["ms"] / max(1, g["launches"]), "launches_per_step": g["launches"] // n_prof,
                 "share_of_step": (g["ms"] / n_prof) / (ms_total / K)}
