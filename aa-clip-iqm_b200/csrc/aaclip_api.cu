@@ -594,6 +594,12 @@ struct BlockRunF32 {
 
 }  // namespace
 
+#ifdef AACLIP_ATTN_DBG_TIMELINE
+extern "C" int aaclip_debug_attn_timeline(long long* dst) {
+  return cudaMemcpyFromSymbol(dst, aaclip::g_attn_timeline, sizeof(long long) * 2 * 16 * 8) == cudaSuccess ? 0 : -1;
+}
+#endif
+
 extern "C" {
 
 const char* aaclip_version(void) { return "aaclip_b200 0.2 sm_100a"; }

@@ -112,6 +112,23 @@ def test_attention_extreme_logits(eng):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+def test_attention_growing_logits_redo_path(eng, dtype):
+    """Every K/V tile's scores exceed the previous tile's by far more than the lazy-maximum pass tolerates: each tile
+    after the first overflows its row-sum check and is redone on the exact-max path (attention_tcgen05.cuh LAZYMAX)."""
+    _lib, engine = eng
+    g = torch.Generator(device="cuda").manual_seed(11)
+    N = 1370
+    qkv = torch.randn(2, N, 3 * 128, device="cuda", generator=g)
+    ramp = 1.0 + 4.0 * (torch.arange(N, device="cuda") // 128).float()   # key norm grows tile by tile
+    qkv[:, :, 128:256] *= ramp[None, :, None]
+    qkv[:, :, :128] *= 3.0
+    qkv = qkv.to(dtype)
+    out = engine.attention(qkv).float()
+    assert torch.isfinite(out).all()
+    assert (out - _attn_ref(qkv, False)).abs().max().item() < (3e-2 if dtype == torch.bfloat16 else 1e-2)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("D", [768, 1024])
 def test_layernorm(eng, D, dtype):
     _lib, engine = eng
