@@ -29,6 +29,22 @@
 // P never touches shared memory: smem bandwidth (128 B/clk) is what bounds SS MMAs at this tile shape, and a
 // P round trip through smem would double the traffic. O stays in TMEM for the whole K/V loop and is read once at
 // the end (scaled by 1/rowsum). While one Q tile is in its exponential phase the tensor core works for the other.
+//
+// What bounds it (measured, tools/ubench/{pipe_rates2,exp_loop,tmem_rates2}.cu and the clock64 timeline behind
+// -DAACLIP_ATTN_DBG_TIMELINE): each SM sub-partition runs one softmax warp of each Q tile. MUFU.EX2 issues once per
+// 8 clk per sub-partition; FFMA2 / FADD2 / F2FP / FMNMX3 are half-rate and hold the issue port for 2 clk each, so the
+// plain loop (scale-subtract, ex2, row sum, pack) needs 8 XU clk and ~4 issue clk per element, and every MIO
+// instruction of the warp that is NOT exponentiating (mbarrier try_wait / arrive, tcgen05.ld / st) queues behind the
+// other warp's MUFU stream (~140 clk per mbarrier op). Hence: (a) packed fp32 pairs for the scale-subtract and the row
+// sum (same issue cost, half the instructions and registers); (b) every POLY_EVERY-th pair of exponentials goes to a
+// degree-3 Cody-Waite polynomial on the FMA pipe, which balances the XU (6 clk/element) against the issue port
+// (6.25 clk/element) -- 0.412 -> 0.385 ms at B=32; (c) o_full(j-1) is awaited after the first half of tile j's
+// exponentials instead of before them. A steady-state tile takes ~2 550 clk per Q-tile pair against the 1 536 clk of
+// MUFU work left in it; prologue + epilogue are ~11 % of a CTA's life.
+// Build knobs kept for the record (all measured slower or equal on B200, see tools/experiments/README.md):
+// AACLIP_ATTN_QT=1 (two one-tile CTAs per SM), AACLIP_ATTN_SPLIT=2 (four softmax warps per sub-partition, half a row
+// each), AACLIP_ATTN_LAZYMAX=1 (no row maximum after the first tile, row-sum overflow check), AACLIP_ATTN_WIDE_TMEM=1
+// (one .x128 load / .x64 store per tile). AACLIP_ATTN_DBG_* are timing-only what-if switches (wrong results).
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
