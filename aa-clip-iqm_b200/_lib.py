@@ -181,6 +181,15 @@ def _declare(lib):
     lib.aaclip_auc_ap.argtypes = [vp, i32, vp, vp]
     lib.aaclip_row_max.restype = i32
     lib.aaclip_row_max.argtypes = [vp, i32, i64, vp, vp]
+    lib.aaclip_resample_ksize.restype = i32
+    lib.aaclip_resample_ksize.argtypes = [i32, i32]
+    lib.aaclip_resample_coeffs_host.restype = i32
+    lib.aaclip_resample_coeffs_host.argtypes = [i32, i32, vp, vp, i32]
+    lib.aaclip_preprocess_workspace_bytes.restype = sz
+    lib.aaclip_preprocess_workspace_bytes.argtypes = [i32, i32, i32]
+    lib.aaclip_preprocess_u8.restype = i32
+    lib.aaclip_preprocess_u8.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp, vp, ctypes.POINTER(f32), ctypes.POINTER(f32),
+                                         vp, sz, vp, vp]
     lib.aaclip_gemm16.restype = i32
     lib.aaclip_gemm16.argtypes = [i32, vp, vp, i32, i32, i32, i32, vp, vp, vp, i32, vp]
     lib.aaclip_ln_fold.restype = i32
@@ -206,6 +215,7 @@ EXPORTED_SYMBOLS = [
     "aaclip_ln_fold", "aaclip_gemm16_ln", "aaclip_gemm16_resid",
     "aaclip_text_create", "aaclip_text_destroy", "aaclip_text_set_weight", "aaclip_text_missing_weights",
     "aaclip_text_workspace_bytes", "aaclip_encode_text", "aaclip_text_anchors",
+    "aaclip_resample_ksize", "aaclip_resample_coeffs_host", "aaclip_preprocess_workspace_bytes", "aaclip_preprocess_u8",
 ]
 
 

@@ -13,6 +13,7 @@
 
 #include "../../include/aaclip.h"
 #include "attention_tcgen05.cuh"
+#include "preprocess.cuh"
 #include "elementwise.cuh"
 #include "fp32_path.cuh"
 #include "gemm_tcgen05.cuh"
@@ -1288,6 +1289,63 @@ int aaclip_row_max(const float* x, int32_t rows, int64_t cols, float* out, void*
   if (!x || !out || rows <= 0 || cols <= 0) return fail(AACLIP_EINVAL, "aaclip_row_max: bad argument");
   row_max_kernel<<<rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, cols, out);
   LAUNCH_CHECK("row_max_kernel");
+  return AACLIP_OK;
+}
+
+/* ---- image pre-processing (include/aaclip.h) ---------------------------------------------------------------------- */
+int32_t aaclip_resample_ksize(int32_t in_size, int32_t out_size) {
+  if (in_size <= 0 || out_size <= 0) return fail(AACLIP_EINVAL, "aaclip_resample_ksize: sizes must be positive");
+  return resample_ksize_host(in_size, out_size);
+}
+
+int aaclip_resample_coeffs_host(int32_t in_size, int32_t out_size, int32_t* bounds_host, int32_t* kk_host,
+                                int32_t kk_capacity) {
+  if (in_size <= 0 || out_size <= 0 || !bounds_host || !kk_host)
+    return fail(AACLIP_EINVAL, "aaclip_resample_coeffs_host: bad argument");
+  const int ksize = resample_ksize_host(in_size, out_size);
+  if (static_cast<int64_t>(kk_capacity) < static_cast<int64_t>(ksize) * out_size)
+    return fail(AACLIP_EINVAL, "aaclip_resample_coeffs_host: kk_host holds %d entries, %lld needed", kk_capacity,
+                static_cast<long long>(ksize) * out_size);
+  resample_coeffs_host(in_size, out_size, ksize, bounds_host, kk_host);
+  return AACLIP_OK;
+}
+
+size_t aaclip_preprocess_workspace_bytes(int32_t B, int32_t H, int32_t S) {
+  if (B <= 0 || H <= 0 || S <= 0) return 0;
+  return (static_cast<size_t>(B) * H * S * 3 + 255) & ~static_cast<size_t>(255);
+}
+
+int aaclip_preprocess_u8(const uint8_t* src, int32_t B, int32_t H, int32_t W, int32_t S, const int32_t* xbounds,
+                         const int32_t* xkk, const int32_t* ybounds, const int32_t* ykk, const float* mean_host,
+                         const float* std_host, void* workspace, size_t workspace_bytes, float* out, void* stream) {
+  if (int rc = ensure_device()) return rc;
+  if (!src || !xbounds || !xkk || !ybounds || !ykk || !mean_host || !std_host || !out)
+    return fail(AACLIP_EINVAL, "aaclip_preprocess_u8: null argument");
+  if (B <= 0 || H <= 0 || W <= 0 || S <= 0 || B > 65535 || S > 65535)
+    return fail(AACLIP_EINVAL, "aaclip_preprocess_u8: bad shape B=%d H=%d W=%d S=%d", B, H, W, S);
+  if (!workspace || workspace_bytes < aaclip_preprocess_workspace_bytes(B, H, S))
+    return fail(AACLIP_EINVAL, "aaclip_preprocess_u8: workspace too small (%zu < %zu)", workspace_bytes,
+                aaclip_preprocess_workspace_bytes(B, H, S));
+  const size_t row_smem = static_cast<size_t>(W) * 3 + 32;
+  if (row_smem > 200 * 1024) return fail(AACLIP_EINVAL, "aaclip_preprocess_u8: rows wider than 68 000 pixels are not supported");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  static size_t smem_set = 48 * 1024;
+  if (row_smem > smem_set) {
+    CUDA_TRY(cudaFuncSetAttribute(resample_horizontal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(row_smem)));
+    smem_set = row_smem;
+  }
+  uint8_t* tmp = reinterpret_cast<uint8_t*>(workspace);
+  const long long rows = static_cast<long long>(B) * H;
+  if (rows > 2147483647ll) return fail(AACLIP_EINVAL, "aaclip_preprocess_u8: too many rows");
+  resample_horizontal_kernel<<<static_cast<unsigned>(rows), 256, row_smem, st>>>(
+      src, tmp, W, S, xbounds, xkk, resample_ksize_host(W, S), rows * W * 3);
+  LAUNCH_CHECK("resample_horizontal_kernel");
+  dim3 grid((S + 127) / 128, S, B);
+  resample_vertical_normalize_kernel<<<grid, 128, 0, st>>>(tmp, out, H, S, ybounds, ykk, resample_ksize_host(H, S),
+                                                           mean_host[0], mean_host[1], mean_host[2], std_host[0],
+                                                           std_host[1], std_host[2]);
+  LAUNCH_CHECK("resample_vertical_normalize_kernel");
   return AACLIP_OK;
 }
 

@@ -1,0 +1,149 @@
+// Image pre-processing on the device: the reference's per-image transform
+//   transforms.Resize((S, S), Image.BICUBIC) -> ToTensor() -> Normalize(CLIP mean, std)      dataset/__init__.py:150-159
+// for a batch of decoded RGB images, bit-exact with PIL + torchvision:
+//   * Pillow's ImagingResample (src/libImaging/Resample.c) in its 8-bit fixed-point form -- antialiased bicubic
+//     (a = -0.5) taps normalised per output pixel and rounded to 22 fractional bits, accumulator seeded with 1 << 21,
+//     clip8 = clamp(acc >> 22, 0, 255) -- horizontal pass first, its uint8 result feeds the vertical pass;
+//   * ToTensor: float(u8) / 255 (IEEE fp32 division); Normalize: (x - mean) / std (IEEE fp32).
+// The tap tables (first tap, tap count, fixed-point weights per output coordinate) are computed once per (in, out) size
+// on the HOST in double precision exactly as precompute_coeffs / normalize_coeffs_8bpc do (aaclip_resample_coeffs_host).
+// Byte work, HBM bound: 3 B/pixel in, 12 B/pixel out; the uint8 intermediate [B, H, S, 3] stays in L2 for typical sizes.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+namespace aaclip {
+
+constexpr int RESAMPLE_PRECISION_BITS = 32 - 8 - 2;
+
+// ---- host: Resample.c precompute_coeffs + normalize_coeffs_8bpc for the box (0, in_size), bicubic filter ----------
+inline double bicubic_filter_host(double x) {
+  const double a = -0.5;
+  if (x < 0.0) x = -x;
+  if (x < 1.0) return ((a + 2.0) * x - (a + 3.0)) * x * x + 1;
+  if (x < 2.0) return (((x - 5) * x + 8) * x - 4) * a;
+  return 0.0;
+}
+inline int resample_ksize_host(int in_size, int out_size) {
+  double filterscale = static_cast<double>(in_size) / out_size;
+  if (filterscale < 1.0) filterscale = 1.0;
+  return static_cast<int>(ceil(2.0 * filterscale)) * 2 + 1;
+}
+// bounds [out_size][2] = (first tap, tap count), kk [out_size][ksize] (unused tail zero)
+inline void resample_coeffs_host(int in_size, int out_size, int ksize, int32_t* bounds, int32_t* kk) {
+  const double scale = static_cast<double>(in_size) / out_size;
+  const double filterscale = scale < 1.0 ? 1.0 : scale;
+  const double support = 2.0 * filterscale;
+  const double ss = 1.0 / filterscale;
+  double* k = new double[ksize];
+  for (int xx = 0; xx < out_size; ++xx) {
+    const double center = (xx + 0.5) * scale;
+    double ww = 0.0;
+    int xmin = static_cast<int>(center - support + 0.5);
+    if (xmin < 0) xmin = 0;
+    int xmax = static_cast<int>(center + support + 0.5);
+    if (xmax > in_size) xmax = in_size;
+    xmax -= xmin;
+    for (int x = 0; x < xmax; ++x) {
+      const double w = bicubic_filter_host((x + xmin - center + 0.5) * ss);
+      k[x] = w;
+      ww += w;
+    }
+    for (int x = 0; x < xmax; ++x)
+      if (ww != 0.0) k[x] /= ww;
+    for (int x = 0; x < ksize; ++x) {
+      int32_t v = 0;
+      if (x < xmax) {
+        const double f = k[x] * (1 << RESAMPLE_PRECISION_BITS);
+        v = k[x] < 0 ? static_cast<int32_t>(-0.5 + f) : static_cast<int32_t>(0.5 + f);
+      }
+      kk[static_cast<size_t>(xx) * ksize + x] = v;
+    }
+    bounds[2 * xx] = xmin;
+    bounds[2 * xx + 1] = xmax;
+  }
+  delete[] k;
+}
+
+__device__ __forceinline__ uint8_t clip8_fixed(int32_t acc) {
+  const int32_t v = acc >> RESAMPLE_PRECISION_BITS;   // arithmetic shift, as in Resample.c's clip8 lookup
+  return static_cast<uint8_t>(v < 0 ? 0 : (v > 255 ? 255 : v));
+}
+
+// Horizontal pass: src [rows, W, 3] uint8 -> dst [rows, S, 3] uint8. One CTA per image row: the row is staged in
+// shared memory with 16-byte loads (rows start at arbitrary byte offsets: W * 3 is rarely a multiple of 16), then every
+// thread produces output pixels (all three channels) from its taps.
+__global__ void __launch_bounds__(256)
+resample_horizontal_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int W, int S,
+                           const int32_t* __restrict__ bounds, const int32_t* __restrict__ kk, int ksize,
+                           long long total_bytes) {
+  extern __shared__ __align__(16) uint8_t row_smem[];
+  const long long row = blockIdx.x;
+  const long long r0 = row * W * 3;                  // first byte of this row
+  const long long r1 = r0 + static_cast<long long>(W) * 3;
+  const long long a0 = r0 & ~15ll;
+  const int skew = static_cast<int>(r0 - a0);
+  const int n_chunks = static_cast<int>((r1 - a0 + 15) >> 4);
+  for (int c = threadIdx.x; c < n_chunks; c += blockDim.x) {
+    const long long g = a0 + (static_cast<long long>(c) << 4);
+    if (g + 16 <= total_bytes) {
+      *reinterpret_cast<uint4*>(row_smem + (c << 4)) = *reinterpret_cast<const uint4*>(src + g);
+    } else {                                         // last chunk of the buffer: never read past its end
+      for (int b = 0; b < 16; ++b) row_smem[(c << 4) + b] = (g + b < total_bytes) ? src[g + b] : 0;
+    }
+  }
+  __syncthreads();
+  const uint8_t* in = row_smem + skew;
+  uint8_t* out = dst + row * S * 3;
+  for (int xo = threadIdx.x; xo < S; xo += blockDim.x) {
+    const int xmin = bounds[2 * xo], n = bounds[2 * xo + 1];
+    const int32_t* k = kk + static_cast<size_t>(xo) * ksize;
+    int32_t s0 = 1 << (RESAMPLE_PRECISION_BITS - 1), s1 = s0, s2 = s0;
+    const uint8_t* p = in + xmin * 3;
+    for (int x = 0; x < n; ++x) {
+      const int32_t w = k[x];
+      s0 += p[3 * x + 0] * w;
+      s1 += p[3 * x + 1] * w;
+      s2 += p[3 * x + 2] * w;
+    }
+    out[3 * xo + 0] = clip8_fixed(s0);
+    out[3 * xo + 1] = clip8_fixed(s1);
+    out[3 * xo + 2] = clip8_fixed(s2);
+  }
+}
+
+// Vertical pass fused with ToTensor + Normalize: tmp [B, H, S, 3] uint8 -> out [B, 3, S, S] fp32.
+// A warp reads 96 contiguous bytes per tap row and writes three 128-byte runs (one per channel plane).
+__global__ void __launch_bounds__(128)
+resample_vertical_normalize_kernel(const uint8_t* __restrict__ tmp, float* __restrict__ out, int H, int S,
+                                   const int32_t* __restrict__ bounds, const int32_t* __restrict__ kk, int ksize,
+                                   float m0, float m1, float m2, float d0, float d1, float d2) {
+  const int xo = blockIdx.x * blockDim.x + threadIdx.x;
+  const int yo = blockIdx.y, b = blockIdx.z;
+  if (xo >= S) return;
+  const int ymin = bounds[2 * yo], n = bounds[2 * yo + 1];
+  const int32_t* k = kk + static_cast<size_t>(yo) * ksize;
+  const uint8_t* p = tmp + ((static_cast<size_t>(b) * H + ymin) * S + xo) * 3;
+  const size_t stride = static_cast<size_t>(S) * 3;
+  int32_t s0 = 1 << (RESAMPLE_PRECISION_BITS - 1), s1 = s0, s2 = s0;
+  for (int y = 0; y < n; ++y) {
+    const int32_t w = k[y];
+    s0 += p[0] * w;
+    s1 += p[1] * w;
+    s2 += p[2] * w;
+    p += stride;
+  }
+  // ToTensor: u8 -> float, / 255; Normalize: (x - mean) / std. IEEE round-to-nearest division on purpose (bit parity
+  // with torch); never compiled with -use_fast_math.
+  const float v0 = __fdiv_rn(static_cast<float>(clip8_fixed(s0)), 255.0f);
+  const float v1 = __fdiv_rn(static_cast<float>(clip8_fixed(s1)), 255.0f);
+  const float v2 = __fdiv_rn(static_cast<float>(clip8_fixed(s2)), 255.0f);
+  const size_t plane = static_cast<size_t>(S) * S;
+  float* o = out + static_cast<size_t>(b) * 3 * plane + static_cast<size_t>(yo) * S + xo;
+  o[0] = __fdiv_rn(__fsub_rn(v0, m0), d0);
+  o[plane] = __fdiv_rn(__fsub_rn(v1, m1), d1);
+  o[2 * plane] = __fdiv_rn(__fsub_rn(v2, m2), d2);
+}
+
+}  // namespace aaclip

@@ -35,6 +35,7 @@ class AnomalyPredictor:
             raise RuntimeError(f"{self.engine.missing} weight tensors of the visual path are missing from the state dict")
         self.text = text.to(self.device, torch.float32).contiguous()
         self._stage_in: Optional[torch.Tensor] = None
+        self._pre = None
 
     # -- device-resident entry point (what bench.py's `value` times)
     def predict_device(self, images: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -42,6 +43,21 @@ class AnomalyPredictor:
         seg, det, _, _ = self.engine.forward(images)
         k, s = DOMAIN_BLUR[self.domain]
         return _engine.score_maps(seg, self.text, self.img_size, test=True, ksize=k, sigma=s, det=det)
+
+    # -- decoded images in: the dataset transform runs on the device too
+    def predict_u8(self, images_u8) -> Tuple[torch.Tensor, torch.Tensor]:
+        """images [B,H,W,3] uint8 (decoded RGB, one size) -> (maps [B,S,S], scores [B]) on the GPU. The reference's
+        per-image CPU transform (dataset/__init__.py:150-159: bicubic resize, ToTensor, Normalize) is executed by
+        aaclip_preprocess_u8, bit-exact with PIL + torchvision, straight into the tower's input layout."""
+        if self._pre is None:
+            from . import preprocess
+            self._pre = preprocess.ImagePreprocessor(self.img_size, device=self.device)
+        x = torch.as_tensor(images_u8)
+        B = x.shape[0]
+        if self._stage_in is None or self._stage_in.shape[0] < B:
+            self._stage_in = torch.empty((max(B, self.max_batch), 3, self.img_size, self.img_size), dtype=torch.float32,
+                                         device=self.device)
+        return self.predict_device(self._pre(x, out=self._stage_in[:B]))
 
     @property
     def launches_per_batch(self) -> int:

@@ -213,6 +213,25 @@ int aaclip_encode_text(AaclipTextHandle* h, const int32_t* tokens, int32_t n_sen
 int aaclip_text_anchors(const float* emb, const int32_t* offsets, int32_t n_groups, int32_t E, float* anchors,
                         void* stream);
 
+/* ---- image pre-processing on the device -------------------------------------------------- */
+/* Replaces the per-image CPU transform of the reference's datasets (dataset/__init__.py:150-159):
+ *   transforms.Resize((S, S), Image.BICUBIC) -> transforms.ToTensor() -> transforms.Normalize(mean, std)
+ * for a batch of decoded RGB images of one size, BIT-EXACT with PIL + torchvision: Pillow's 8-bit fixed-point
+ * antialiased bicubic resampling (horizontal pass, uint8, then vertical pass), float(u8) / 255, (x - mean) / std.
+ *
+ * The tap tables depend only on (input size, S) and are computed on the HOST in double precision, exactly like
+ * Resample.c's precompute_coeffs + normalize_coeffs_8bpc; the caller uploads them once per image size:
+ *   bounds [S, 2] int32 = (first tap, tap count) per output coordinate;  kk [S, ksize] int32 fixed-point (22 bit) taps */
+int32_t aaclip_resample_ksize(int32_t in_size, int32_t out_size);
+int aaclip_resample_coeffs_host(int32_t in_size, int32_t out_size, int32_t* bounds_host, int32_t* kk_host,
+                                int32_t kk_capacity /* entries available in kk_host, >= S * ksize */);
+size_t aaclip_preprocess_workspace_bytes(int32_t B, int32_t H, int32_t S);
+/*   src [B, H, W, 3] uint8 (HWC, RGB) DEVICE;  xbounds / xkk: tables of (W -> S), ybounds / ykk: tables of (H -> S),
+ *   DEVICE;  mean_host / std_host: 3 floats each, HOST;  out [B, 3, S, S] fp32 DEVICE (the layout aaclip_forward takes) */
+int aaclip_preprocess_u8(const uint8_t* src, int32_t B, int32_t H, int32_t W, int32_t S, const int32_t* xbounds,
+                         const int32_t* xkk, const int32_t* ybounds, const int32_t* ykk, const float* mean_host,
+                         const float* std_host, void* workspace, size_t workspace_bytes, float* out, void* stream);
+
 /* ---- on-device evaluation metrics ------------------------------------------------------ */
 /* Replace the scikit-learn calls of forward_utils.metrics_eval (forward_utils.py:246-249,275,288-296): global min-max
  * normalisation, per-image maximum, AUROC and average precision, computed from two fine score histograms (positives,
