@@ -1321,13 +1321,13 @@ int aaclip_preprocess_u8(const uint8_t* src, int32_t B, int32_t H, int32_t W, in
   if (int rc = ensure_device()) return rc;
   if (!src || !xbounds || !xkk || !ybounds || !ykk || !mean_host || !std_host || !out)
     return fail(AACLIP_EINVAL, "aaclip_preprocess_u8: null argument");
-  if (B <= 0 || H <= 0 || W <= 0 || S <= 0 || B > 65535 || S > 65535)
+  if (B <= 0 || H <= 0 || W <= 0 || S <= 0 || B > 65535 || S > 32768)
     return fail(AACLIP_EINVAL, "aaclip_preprocess_u8: bad shape B=%d H=%d W=%d S=%d", B, H, W, S);
   if (!workspace || workspace_bytes < aaclip_preprocess_workspace_bytes(B, H, S))
     return fail(AACLIP_EINVAL, "aaclip_preprocess_u8: workspace too small (%zu < %zu)", workspace_bytes,
                 aaclip_preprocess_workspace_bytes(B, H, S));
-  const size_t row_smem = static_cast<size_t>(W) * 3 + 32;
-  if (row_smem > 200 * 1024) return fail(AACLIP_EINVAL, "aaclip_preprocess_u8: rows wider than 68 000 pixels are not supported");
+  const size_t row_smem = static_cast<size_t>(HROWS) * W * 3 + 32;
+  if (row_smem > 200 * 1024) return fail(AACLIP_EINVAL, "aaclip_preprocess_u8: rows wider than 17 000 pixels are not supported");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   static size_t smem_set = 48 * 1024;
   if (row_smem > smem_set) {
@@ -1338,10 +1338,10 @@ int aaclip_preprocess_u8(const uint8_t* src, int32_t B, int32_t H, int32_t W, in
   uint8_t* tmp = reinterpret_cast<uint8_t*>(workspace);
   const long long rows = static_cast<long long>(B) * H;
   if (rows > 2147483647ll) return fail(AACLIP_EINVAL, "aaclip_preprocess_u8: too many rows");
-  resample_horizontal_kernel<<<static_cast<unsigned>(rows), 256, row_smem, st>>>(
-      src, tmp, W, S, xbounds, xkk, resample_ksize_host(W, S), rows * W * 3);
+  resample_horizontal_kernel<<<static_cast<unsigned>((rows + HROWS - 1) / HROWS), 256, row_smem, st>>>(
+      src, tmp, W, S, xbounds, xkk, resample_ksize_host(W, S), rows, rows * W * 3);
   LAUNCH_CHECK("resample_horizontal_kernel");
-  dim3 grid((S + 127) / 128, S, B);
+  dim3 grid((S * S + 127) / 128, B);
   resample_vertical_normalize_kernel<<<grid, 128, 0, st>>>(tmp, out, H, S, ybounds, ykk, resample_ksize_host(H, S),
                                                            mean_host[0], mean_host[1], mean_host[2], std_host[0],
                                                            std_host[1], std_host[2]);

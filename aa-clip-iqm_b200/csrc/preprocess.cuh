@@ -71,17 +71,19 @@ __device__ __forceinline__ uint8_t clip8_fixed(int32_t acc) {
   return static_cast<uint8_t>(v < 0 ? 0 : (v > 255 ? 255 : v));
 }
 
-// Horizontal pass: src [rows, W, 3] uint8 -> dst [rows, S, 3] uint8. One CTA per image row: the row is staged in
-// shared memory with 16-byte loads (rows start at arbitrary byte offsets: W * 3 is rarely a multiple of 16), then every
-// thread produces output pixels (all three channels) from its taps.
+// Horizontal pass: src [rows, W, 3] uint8 -> dst [rows, S, 3] uint8. One CTA per HROWS consecutive image rows: their
+// bytes (one contiguous span) are staged in shared memory with 16-byte loads (rows start at arbitrary byte offsets:
+// W * 3 is rarely a multiple of 16), then the CTA's threads share the HROWS * S output pixels (all three channels each).
+constexpr int HROWS = 4;
 __global__ void __launch_bounds__(256)
 resample_horizontal_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int W, int S,
                            const int32_t* __restrict__ bounds, const int32_t* __restrict__ kk, int ksize,
-                           long long total_bytes) {
+                           long long n_rows, long long total_bytes) {
   extern __shared__ __align__(16) uint8_t row_smem[];
-  const long long row = blockIdx.x;
-  const long long r0 = row * W * 3;                  // first byte of this row
-  const long long r1 = r0 + static_cast<long long>(W) * 3;
+  const long long row0 = static_cast<long long>(blockIdx.x) * HROWS;
+  const int rows = static_cast<int>(n_rows - row0 < HROWS ? n_rows - row0 : HROWS);
+  const long long r0 = row0 * W * 3;                 // first byte of this CTA's span
+  const long long r1 = r0 + static_cast<long long>(rows) * W * 3;
   const long long a0 = r0 & ~15ll;
   const int skew = static_cast<int>(r0 - a0);
   const int n_chunks = static_cast<int>((r1 - a0 + 15) >> 4);
@@ -94,22 +96,22 @@ resample_horizontal_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict_
     }
   }
   __syncthreads();
-  const uint8_t* in = row_smem + skew;
-  uint8_t* out = dst + row * S * 3;
-  for (int xo = threadIdx.x; xo < S; xo += blockDim.x) {
+  uint8_t* out = dst + row0 * S * 3;
+  for (int o = threadIdx.x; o < rows * S; o += blockDim.x) {
+    const int r = o / S, xo = o - r * S;
     const int xmin = bounds[2 * xo], n = bounds[2 * xo + 1];
     const int32_t* k = kk + static_cast<size_t>(xo) * ksize;
     int32_t s0 = 1 << (RESAMPLE_PRECISION_BITS - 1), s1 = s0, s2 = s0;
-    const uint8_t* p = in + xmin * 3;
+    const uint8_t* p = row_smem + skew + (static_cast<size_t>(r) * W + xmin) * 3;
     for (int x = 0; x < n; ++x) {
       const int32_t w = k[x];
       s0 += p[3 * x + 0] * w;
       s1 += p[3 * x + 1] * w;
       s2 += p[3 * x + 2] * w;
     }
-    out[3 * xo + 0] = clip8_fixed(s0);
-    out[3 * xo + 1] = clip8_fixed(s1);
-    out[3 * xo + 2] = clip8_fixed(s2);
+    out[3 * o + 0] = clip8_fixed(s0);
+    out[3 * o + 1] = clip8_fixed(s1);
+    out[3 * o + 2] = clip8_fixed(s2);
   }
 }
 
@@ -119,9 +121,10 @@ __global__ void __launch_bounds__(128)
 resample_vertical_normalize_kernel(const uint8_t* __restrict__ tmp, float* __restrict__ out, int H, int S,
                                    const int32_t* __restrict__ bounds, const int32_t* __restrict__ kk, int ksize,
                                    float m0, float m1, float m2, float d0, float d1, float d2) {
-  const int xo = blockIdx.x * blockDim.x + threadIdx.x;
-  const int yo = blockIdx.y, b = blockIdx.z;
-  if (xo >= S) return;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // (yo, xo) flattened: no idle lanes at the row ends
+  const int b = blockIdx.y;
+  if (idx >= S * S) return;
+  const int yo = idx / S, xo = idx - yo * S;
   const int ymin = bounds[2 * yo], n = bounds[2 * yo + 1];
   const int32_t* k = kk + static_cast<size_t>(yo) * ksize;
   const uint8_t* p = tmp + ((static_cast<size_t>(b) * H + ymin) * S + xo) * 3;
