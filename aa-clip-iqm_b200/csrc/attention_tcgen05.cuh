@@ -503,7 +503,11 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, uint16_t*
                 p0 = ex2_approx(x0);
                 p1 = ex2_approx(x1);
               }
+#ifdef AACLIP_ATTN_DBG_NOSUM      // what-if (timing only, wrong results): no row sum in the loop
+              if (i == 0) rs2[0] = add_f32x2(rs2[0], pack_f32x2(p0, p1));
+#else
               rs2[i & 1] = add_f32x2(rs2[i & 1], pack_f32x2(p0, p1));
+#endif
               w[c * (COLS / 4) + i] = ptx::pack16<BF16>(p0, p1);
             }
             if (c == 0) ATTN_STAMP(4);

@@ -24,15 +24,15 @@ from aaclip_b200 import forward_utils as fu  # noqa: E402
 from aaclip_b200 import weights  # noqa: E402
 from aaclip_b200.model import AdaptedCLIP, create_model  # noqa: E402
 
-CLIP_MEAN, CLIP_STD = (0.48145466, 0.4578275, 0.40821073), (0.26862954, 0.26130258, 0.27577711)
+from aaclip_b200 import preprocess  # noqa: E402
 
 
-def load_image(path: str, size: int) -> torch.Tensor:
-    """dataset/__init__.py:150-159: bicubic resize to size x size, ToTensor, CLIP mean/std normalisation."""
+def load_image(path: str, size: int, device: str) -> torch.Tensor:
+    """dataset/__init__.py:86,150-159: decode to RGB on the host; bicubic resize to size x size, ToTensor and the CLIP
+    mean/std normalisation run on the device (aaclip_preprocess_u8, bit-exact with PIL + torchvision)."""
     from PIL import Image
-    img = Image.open(path).convert("RGB").resize((size, size), Image.BICUBIC)
-    x = torch.from_numpy(np.asarray(img, dtype=np.float32) / 255.0).permute(2, 0, 1)
-    return ((x - torch.tensor(CLIP_MEAN)[:, None, None]) / torch.tensor(CLIP_STD)[:, None, None]).unsqueeze(0)
+    rgb = np.asarray(Image.open(path).convert("RGB"))
+    return preprocess.ImagePreprocessor(size, device=device)(rgb)
 
 
 def main():
@@ -69,7 +69,7 @@ def main():
         if not files:
             raise SystemExit(f"no image_adapter_*.pth under {args.save_path}")
         model.image_adapter.load_state_dict(torch.load(files[-1])["image_adapter"])
-        image = load_image(args.image, S)
+        image = load_image(args.image, S, dev)
         with torch.no_grad():
             text = fu.get_adapted_single_class_text_embedding(model, args.dataset, args.class_name, dev)
     with torch.no_grad():
