@@ -220,15 +220,22 @@ def run_ours(args):
             pending.pop(0).synchronize()
         stream_api.drain()
 
-    def timed(fn, steps, finish=None):
+    clock_box = {}
+
+    def timed(fn, steps, finish=None, sampler=None):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
+        if sampler:
+            sampler.start()                   # sample only while this rank's GPU is inside the timed region
         e0.record()
         for i in range(steps):
             fn(i)
         if finish is not None:
             finish()                          # host-side wait for everything still in flight on side streams
         e1.record()
+        if sampler:
+            torch.cuda.synchronize()
+            clock_box["clocks"] = sampler.stop()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
         if world > 1:
@@ -238,10 +245,8 @@ def run_ours(args):
     for i in range(max(Wm, 3)):
         step_device(i)
     sampler = ClockSampler(physical_gpu_index(local_rank)) if rank == 0 else None
-    if sampler:
-        sampler.start()
-    ms_total = timed(step_device, K)
-    clocks = sampler.stop() if sampler else None
+    ms_total = timed(step_device, K, sampler=sampler)
+    clocks = clock_box.get("clocks")
     launches = pred.launches_per_batch * K
     ips = world * B * K / (ms_total * 1e-3)
 
