@@ -55,15 +55,33 @@ struct GemmEpi {
 };
 
 
-// erf-GELU, x * Phi(x), with erf from Abramowitz & Stegun 7.1.26 (|abs err| <= 1.5e-7, far below the 16-bit store):
-//   erf(z) = 1 - (a1 t + ... + a5 t^5) exp(-z^2),  t = 1/(1 + p z),  z = |x|/sqrt(2) >= 0.
-// Written for the instruction count (this epilogue runs 128 times per thread per tile and bounds the c_fc GEMM):
-//   u = |x| sqrt(log2(e)/2)  so that  exp(-z^2) = ex2(-u^2)  and  1 + p z = 1 + (p / sqrt(log2 e)) u;
-//   q = Phi(-|x|) = (poly t) e / 2 (the 1/2 folded into the coefficients);
-//   x Phi(x) = max(x, 0) - |x| q   (x >= 0: x - x q;  x < 0: x q)   -- no compare / select.
-// 11 FMA-pipe instructions + 2 MUFU (rcp, ex2) per element.
+// erf-GELU, x * Phi(x) = max(x, 0) - |x| Phi(-|x|)  (x >= 0: x - x q;  x < 0: x q -- no compare / select, and no
+// cancellation on the negative side). This epilogue runs 128 times per thread per tile and bounds the c_fc GEMM; its
+// MUFUs share the MIO queue with the epilogue's TMEM loads and shared-memory transpose. Measured on B200 (c_fc in the
+// step, tools/variant_check.sh; map error against the reference's golden vectors unchanged unless noted):
+//   form 0  Abramowitz & Stegun 7.1.26 (|abs err| <= 1.5e-7): rcp + ex2, 11 FMA-pipe + 2 MUFU            7.9 ms
+//   form 5  Phi(-a) = 2^P(a), P = degree-5 fit of log2 Phi(-a) weighted by the GELU error
+//           a |2^P - Phi(-a)| (max 4.6e-6 abs, far below the 16-bit store): ONE MUFU on a short chain,
+//           6 FMA-pipe + 1 FMNMX + 1 MUFU; leading coefficient negative, so P -> -inf for large |x|       7.5 ms  (default)
+//   not kept: tanh.approx of a fitted odd polynomial (7.0 ms, but MUFU.TANH's 2^-11 error doubles the map error on the
+//   negative side), the same fit as x * sigmoid on ex2 + rcp (no gain), A&S 7.1.28 with one rcp and a 16th power
+//   (slower: 10 dependent FMA-pipe operations before the MUFU).
+#ifndef AACLIP_GELU_FORM
+#define AACLIP_GELU_FORM 5
+#endif
 __device__ __forceinline__ float gelu_erf(float x) {
   const float ax = fabsf(x);
+#if AACLIP_GELU_FORM == 5
+  float p = fmaf(-0.000417569448472932f, ax, 0.006652015261352062f);
+  p = fmaf(p, ax, -0.05059274658560753f);
+  p = fmaf(p, ax, -0.46160048246383667f);
+  p = fmaf(p, ax, -1.1498371362686157f);
+  p = fmaf(p, ax, -1.0002421140670776f);
+  float q;                                                         // = Phi(-|x|)
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(q) : "f"(p));
+#else
+  //   u = |x| sqrt(log2(e)/2)  so that  exp(-z^2) = ex2(-u^2)  and  1 + p z = 1 + (p / sqrt(log2 e)) u;
+  //   q = Phi(-|x|) = (poly t) e / 2 (the 1/2 folded into the coefficients)
   const float u = ax * 0.84932180028801904f;                       // sqrt(log2(e) / 2)
   float t;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.27273748f, u, 1.0f)));   // p / sqrt(log2 e), p = 0.3275911
@@ -74,6 +92,7 @@ __device__ __forceinline__ float gelu_erf(float x) {
   float e;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-u * u));
   const float q = (poly * t) * e;                                  // = (1 - erf(z)) / 2 = Phi(-|x|)
+#endif
   return fmaf(-ax, q, fmaxf(x, 0.0f));
 }
 __device__ __forceinline__ float quick_gelu(float x) { return x / (1.0f + __expf(-1.702f * x)); }
