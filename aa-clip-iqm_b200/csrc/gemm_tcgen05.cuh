@@ -179,6 +179,9 @@ struct GemmPairCfg {
 #ifndef AACLIP_GEMM_RESID_PREFETCH
 #define AACLIP_GEMM_RESID_PREFETCH 1
 #endif
+#ifndef AACLIP_GEMM_RESID_PREFETCH_MAXKB
+#define AACLIP_GEMM_RESID_PREFETCH_MAXKB 32   // K / 64 up to which the residual rows are L2-prefetched at tile start
+#endif
 #ifndef AACLIP_GEMM_EPI_WARPS
 #define AACLIP_GEMM_EPI_WARPS 8
 #endif
@@ -316,22 +319,16 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         // now, while the MMAs of this tile are still running, so that the loads in the chunk loop below are L2 hits
         // (out-proj 3.39 -> 3.18 ms/step; skipped for long-K tiles, whose 20 us main loop outlives the prefetch).
         // lane l: row row0 + l, COLS_PER_WARP fp32 = COLS_PER_WARP / 32 lines of 128 B.
-        if (num_kb <= 32 && row0 + lane < M) {
+        if (num_kb <= AACLIP_GEMM_RESID_PREFETCH_MAXKB && row0 + lane < M) {
           const float* rp = epi.out_f32 + static_cast<size_t>(row0 + lane) * epi.ldo + n_blk * BN + cg * COLS_PER_WARP;
 #pragma unroll
           for (int i = 0; i < COLS_PER_WARP / 32; ++i) ptx::prefetch_l2(rp + i * 32);
         }
-      ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
-      ptx::tc_fence_after();
-      const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + cg * COLS_PER_WARP;
-      const int sub = lane >> 3, unit = lane & 7;
-      // coalesced domain: this thread handles rows row0 + j*4 + sub (j < 8) in every 32-column chunk
-      float mean_j[8], rstd_j[8];   // EPI_LN_*: LayerNorm statistics of its 8 rows
-      float st_s[8], st_q[8];       // EPI_BIAS_RESID_F32 + stats_out: running sum / sum of squares of the new rows
+      // EPI_LN_*: lane l finishes the LayerNorm statistics of row row0 + l from its partials (contiguous, fixed order)
+      // BEFORE waiting for the accumulator -- the loads' latency (the statistics were written by the previous kernel:
+      // an L2 or HBM round trip) runs under this tile's MMAs instead of on the epilogue's critical path.
+      float mean = 0.f, rstd = 0.f;
       if constexpr (epi_is_ln<EPI>()) {
-        // lane l finishes the statistics of row row0 + l from its partials (contiguous, fixed order), then the
-        // coalesced-domain owners of that row pick them up with one shuffle each
-        float mean = 0.f, rstd = 0.f;
         if (row0 + lane < M) {
           const float4* sp = reinterpret_cast<const float4*>(epi.stats + static_cast<size_t>(row0 + lane) * epi.n_partials * 2);
           float sx = 0.f, sq = 0.f;
@@ -347,6 +344,16 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           mean = sx * epi.inv_width;
           rstd = rsqrtf(fmaxf(sq * epi.inv_width - mean * mean, 0.f) + epi.eps);
         }
+      }
+      ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + cg * COLS_PER_WARP;
+      const int sub = lane >> 3, unit = lane & 7;
+      // coalesced domain: this thread handles rows row0 + j*4 + sub (j < 8) in every 32-column chunk
+      float mean_j[8], rstd_j[8];   // EPI_LN_*: LayerNorm statistics of its 8 rows
+      float st_s[8], st_q[8];       // EPI_BIAS_RESID_F32 + stats_out: running sum / sum of squares of the new rows
+      if constexpr (epi_is_ln<EPI>()) {
+        // the coalesced-domain owners of a row pick its statistics up with one shuffle each
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           mean_j[j] = __shfl_sync(0xffffffffu, mean, j * 4 + sub);
