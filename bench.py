@@ -280,9 +280,9 @@ def run_ours(args):
         roof = {"bound": "tensor", "kernel": "gemm_pair_kernel (tcgen05 cta_group::2, all epilogues)", "achieved": achieved, "peak": peak,
                 "unit": "TFLOP/s", "frac": achieved / peak,
                 # dram__bytes_read + dram__bytes_write per launch, launch-weighted mean over one step's 108 GEMM launches
-                # (ncu --set full capture of the same kernels, profiles/r01b_prof_gemm_r01b.txt: qkv 319 MB, c_fc 413 MB,
-                # c_proj 826 MB, out-proj 488 MB, adapter 216 MB); only meaningful for the B=32 @518 workload
-                "traffic": 4.67e8 if (S == 518 and B == 32 and args.dtype != "fp32") else None,
+                # (ncu --set full capture of the same kernels, profiles/r01d_prof_gemm_r01d.txt: qkv 320 MB, c_fc 413 MB,
+                # c_proj 824 MB, out-proj 488 MB, adapter 218 MB, heads ~150 MB); only meaningful for the B=32 @518 workload
+                "traffic": 4.75e8 if (S == 518 and B == 32 and args.dtype != "fp32") else None,
                 "peak_source": f"{pk['source']} (sustained cuBLAS bf16; burst {pk['bf16_tflops']})",
                 "avg_launch_ms": g["ms"] / max(1, g["launches"]), "launches_per_step": g["launches"] // n_prof,
                 "share_of_step": (g["ms"] / n_prof) / (ms_total / K)}
