@@ -1329,22 +1329,35 @@ int aaclip_preprocess_u8(const uint8_t* src, int32_t B, int32_t H, int32_t W, in
   const size_t row_smem = static_cast<size_t>(HROWS) * W * 3 + 32;
   if (row_smem > 200 * 1024) return fail(AACLIP_EINVAL, "aaclip_preprocess_u8: rows wider than 17 000 pixels are not supported");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  static size_t smem_set = 48 * 1024;
-  if (row_smem > smem_set) {
-    CUDA_TRY(cudaFuncSetAttribute(resample_horizontal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>(row_smem)));
-    smem_set = row_smem;
-  }
   uint8_t* tmp = reinterpret_cast<uint8_t*>(workspace);
   const long long rows = static_cast<long long>(B) * H;
   if (rows > 2147483647ll) return fail(AACLIP_EINVAL, "aaclip_preprocess_u8: too many rows");
-  resample_horizontal_kernel<<<static_cast<unsigned>((rows + HROWS - 1) / HROWS), 256, row_smem, st>>>(
-      src, tmp, W, S, xbounds, xkk, resample_ksize_host(W, S), rows, rows * W * 3);
+  const int xks = resample_ksize_host(W, S), yks = resample_ksize_host(H, S);
+  const unsigned hgrid = static_cast<unsigned>((rows + HROWS - 1) / HROWS);
+  const dim3 vgrid((S * S + 127) / 128, B);
+  // tap loops unrolled for the usual scale factors (ksize = 5 up-scaling / same size, 9 for 2x, 13 for 3x down-scaling)
+#define AACLIP_RESAMPLE_H(KS)                                                                                          \
+  do {                                                                                                                 \
+    if (row_smem > 48 * 1024)                                                                                          \
+      CUDA_TRY(cudaFuncSetAttribute(resample_horizontal_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                    static_cast<int>(row_smem)));                                                      \
+    resample_horizontal_kernel<KS><<<hgrid, 256, row_smem, st>>>(src, tmp, W, S, xbounds, xkk, xks, rows, rows * W * 3); \
+  } while (0)
+  if (xks <= 5) AACLIP_RESAMPLE_H(5);
+  else if (xks <= 9) AACLIP_RESAMPLE_H(9);
+  else if (xks <= 13) AACLIP_RESAMPLE_H(13);
+  else AACLIP_RESAMPLE_H(0);
+#undef AACLIP_RESAMPLE_H
   LAUNCH_CHECK("resample_horizontal_kernel");
-  dim3 grid((S * S + 127) / 128, B);
-  resample_vertical_normalize_kernel<<<grid, 128, 0, st>>>(tmp, out, H, S, ybounds, ykk, resample_ksize_host(H, S),
-                                                           mean_host[0], mean_host[1], mean_host[2], std_host[0],
-                                                           std_host[1], std_host[2]);
+#define AACLIP_RESAMPLE_V(KS)                                                                                          \
+  resample_vertical_normalize_kernel<KS><<<vgrid, 128, 0, st>>>(tmp, out, H, S, ybounds, ykk, yks, mean_host[0],      \
+                                                                 mean_host[1], mean_host[2], std_host[0], std_host[1], \
+                                                                 std_host[2])
+  if (yks <= 5) AACLIP_RESAMPLE_V(5);
+  else if (yks <= 9) AACLIP_RESAMPLE_V(9);
+  else if (yks <= 13) AACLIP_RESAMPLE_V(13);
+  else AACLIP_RESAMPLE_V(0);
+#undef AACLIP_RESAMPLE_V
   LAUNCH_CHECK("resample_vertical_normalize_kernel");
   return AACLIP_OK;
 }

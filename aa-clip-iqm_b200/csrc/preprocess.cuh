@@ -75,6 +75,9 @@ __device__ __forceinline__ uint8_t clip8_fixed(int32_t acc) {
 // bytes (one contiguous span) are staged in shared memory with 16-byte loads (rows start at arbitrary byte offsets:
 // W * 3 is rarely a multiple of 16), then the CTA's threads share the HROWS * S output pixels (all three channels each).
 constexpr int HROWS = 4;
+// KS > 0: the tap loop is fully unrolled over KS >= ksize taps (weights first, then the pixels: every load of an output
+// pixel is in flight at once); KS == 0: runtime loop for very large down-scaling factors.
+template <int KS>
 __global__ void __launch_bounds__(256)
 resample_horizontal_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int W, int S,
                            const int32_t* __restrict__ bounds, const int32_t* __restrict__ kk, int ksize,
@@ -103,11 +106,25 @@ resample_horizontal_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict_
     const int32_t* k = kk + static_cast<size_t>(xo) * ksize;
     int32_t s0 = 1 << (RESAMPLE_PRECISION_BITS - 1), s1 = s0, s2 = s0;
     const uint8_t* p = row_smem + skew + (static_cast<size_t>(r) * W + xmin) * 3;
-    for (int x = 0; x < n; ++x) {
-      const int32_t w = k[x];
-      s0 += p[3 * x + 0] * w;
-      s1 += p[3 * x + 1] * w;
-      s2 += p[3 * x + 2] * w;
+    if constexpr (KS > 0) {
+      int32_t w[KS];
+#pragma unroll
+      for (int x = 0; x < KS; ++x) w[x] = (x < n) ? k[x] : 0;      // taps beyond n multiply in-row garbage by zero
+      const int lim = 3 * (n - 1);                                  // clamp the byte offset of unused taps into the window
+#pragma unroll
+      for (int x = 0; x < KS; ++x) {
+        const int off = min(3 * x, lim);
+        s0 += p[off + 0] * w[x];
+        s1 += p[off + 1] * w[x];
+        s2 += p[off + 2] * w[x];
+      }
+    } else {
+      for (int x = 0; x < n; ++x) {
+        const int32_t w = k[x];
+        s0 += p[3 * x + 0] * w;
+        s1 += p[3 * x + 1] * w;
+        s2 += p[3 * x + 2] * w;
+      }
     }
     out[3 * o + 0] = clip8_fixed(s0);
     out[3 * o + 1] = clip8_fixed(s1);
@@ -117,6 +134,7 @@ resample_horizontal_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict_
 
 // Vertical pass fused with ToTensor + Normalize: tmp [B, H, S, 3] uint8 -> out [B, 3, S, S] fp32.
 // A warp reads 96 contiguous bytes per tap row and writes three 128-byte runs (one per channel plane).
+template <int KS>
 __global__ void __launch_bounds__(128)
 resample_vertical_normalize_kernel(const uint8_t* __restrict__ tmp, float* __restrict__ out, int H, int S,
                                    const int32_t* __restrict__ bounds, const int32_t* __restrict__ kk, int ksize,
@@ -130,12 +148,25 @@ resample_vertical_normalize_kernel(const uint8_t* __restrict__ tmp, float* __res
   const uint8_t* p = tmp + ((static_cast<size_t>(b) * H + ymin) * S + xo) * 3;
   const size_t stride = static_cast<size_t>(S) * 3;
   int32_t s0 = 1 << (RESAMPLE_PRECISION_BITS - 1), s1 = s0, s2 = s0;
-  for (int y = 0; y < n; ++y) {
-    const int32_t w = k[y];
-    s0 += p[0] * w;
-    s1 += p[1] * w;
-    s2 += p[2] * w;
-    p += stride;
+  if constexpr (KS > 0) {
+    int32_t w[KS];
+#pragma unroll
+    for (int y = 0; y < KS; ++y) w[y] = (y < n) ? k[y] : 0;
+#pragma unroll
+    for (int y = 0; y < KS; ++y) {
+      const uint8_t* py = p + static_cast<size_t>(min(y, n - 1)) * stride;   // unused taps re-read the last row (x 0)
+      s0 += py[0] * w[y];
+      s1 += py[1] * w[y];
+      s2 += py[2] * w[y];
+    }
+  } else {
+    for (int y = 0; y < n; ++y) {
+      const int32_t w = k[y];
+      s0 += p[0] * w;
+      s1 += p[1] * w;
+      s2 += p[2] * w;
+      p += stride;
+    }
   }
   // ToTensor: u8 -> float, / 255; Normalize: (x - mean) / std. IEEE round-to-nearest division on purpose (bit parity
   // with torch); never compiled with -use_fast_math.
