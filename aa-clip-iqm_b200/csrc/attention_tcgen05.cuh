@@ -212,8 +212,8 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, uint16_t*
   uint64_t* o_full = p_full + QT;                 // [QT] MMA -> softmax : O_t += P_t(j) V_j complete
   uint64_t* stagger = o_full + QT;                // softmax tile 0 -> tile 1, once: start half an exp phase later
   uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(stagger + 1);
-  float* xmax = reinterpret_cast<float*>(smem + OFF_X);        // [2 (tile parity)][QT][2 (half)][128]
-  float* xsum = xmax + 2 * QT * 2 * 128;                       // [QT][2][128]
+  [[maybe_unused]] float* xmax = reinterpret_cast<float*>(smem + OFF_X);   // [2 (tile parity)][QT][2 (half)][128]
+  [[maybe_unused]] float* xsum = xmax + 2 * QT * 2 * 128;                  // [QT][2][128]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -369,7 +369,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, uint16_t*
       const uint32_t s_tmem = tmem_base + lane_off + TM_S + t * BKV + half * COLS;
       const uint32_t o_tmem = tmem_base + lane_off + TM_O + t * HD + half * OCOLS;
       const uint32_t p_tmem = tmem_base + lane_off + TM_P + t * (BKV / 2) + half * (COLS / 2);
-      const int pair_bar = 1 + t * 4 + q;       // named barrier of the two warps that share these 32 rows
+      [[maybe_unused]] const int pair_bar = 1 + t * 4 + q;   // named barrier of the two warps sharing these 32 rows
 
       float m_used = -1e30f;   // the maximum the exponentials are taken against (log2 domain, scaled)
       float l = 0.f;           // running row sum of P (this thread's columns)
