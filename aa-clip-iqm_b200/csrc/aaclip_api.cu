@@ -823,7 +823,7 @@ static int forward_f32(AaclipHandle* h, const float* images, int B, uint8_t* wsb
           if ((rc = run.gemm(proj_epi, tok_out, h->w_det, MP, E, W, e))) return rc; }
         if ((rc = l2norm(detbuf, MP))) return rc;
         ProfScope ps(h, AACLIP_PROF_OTHER, 0.0, st);
-        mean_over_patches_kernel<<<dim3((E + 127) / 128, B), 128, 0, st>>>(detbuf, det_out, P, E);
+        mean_over_patches_kernel<<<dim3((E + MEAN_COLS - 1) / MEAN_COLS, B), dim3(MEAN_COLS, MEAN_SEGS), 0, st>>>(detbuf, det_out, P, E);
         LAUNCH_CHECK("mean_over_patches_kernel");
         ++launches;
       }
@@ -900,8 +900,15 @@ int aaclip_forward(AaclipHandle* h, const float* images, int32_t B, void* worksp
   // ---- patch embedding + CLS + positional embedding + ln_pre (model/adapter.py:139-156)
   {
     ProfScope ps(h, AACLIP_PROF_OTHER, 0.0, st);
-    if (bf) patch_gather_kernel<true><<<dim3(h->G, B), 256, 0, st>>>(images, patchA, c.img_size, h->G, c.patch, h->KP);
-    else patch_gather_kernel<false><<<dim3(h->G, B), 256, 0, st>>>(images, patchA, c.img_size, h->G, c.patch, h->KP);
+    const size_t gsmem = static_cast<size_t>(3) * c.patch * h->G * c.patch * 2;
+    if (c.patch % 2 == 0 && c.img_size % 2 == 0 && h->KP % 2 == 0 && gsmem <= 48 * 1024 &&
+        (reinterpret_cast<uintptr_t>(images) & 7) == 0) {
+      if (bf) patch_gather_kernel<true><<<dim3(h->G, B), 256, gsmem, st>>>(images, patchA, c.img_size, h->G, c.patch, h->KP);
+      else patch_gather_kernel<false><<<dim3(h->G, B), 256, gsmem, st>>>(images, patchA, c.img_size, h->G, c.patch, h->KP);
+    } else {
+      if (bf) patch_gather_simple_kernel<true><<<dim3(h->G, B), 256, 0, st>>>(images, patchA, c.img_size, h->G, c.patch, h->KP);
+      else patch_gather_simple_kernel<false><<<dim3(h->G, B), 256, 0, st>>>(images, patchA, c.img_size, h->G, c.patch, h->KP);
+    }
     LAUNCH_CHECK("patch_gather_kernel"); ++launches;
   }
   {
@@ -932,7 +939,7 @@ int aaclip_forward(AaclipHandle* h, const float* images, int32_t B, void* worksp
           if ((rc = run.gemm(proj_epi, tok, h->w_det, MP, E, W, e))) return rc; }
         if ((rc = l2norm(detbuf, MP))) return rc;
         ProfScope ps(h, AACLIP_PROF_OTHER, 0.0, st);
-        mean_over_patches_kernel<<<dim3((E + 127) / 128, B), 128, 0, st>>>(detbuf, det_out, P, E);
+        mean_over_patches_kernel<<<dim3((E + MEAN_COLS - 1) / MEAN_COLS, B), dim3(MEAN_COLS, MEAN_SEGS), 0, st>>>(detbuf, det_out, P, E);
         LAUNCH_CHECK("mean_over_patches_kernel");
         ++launches;
       }

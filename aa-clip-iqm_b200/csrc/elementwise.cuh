@@ -21,12 +21,52 @@ __device__ __forceinline__ float warp_sum(float v) {
 // Patch gather ("im2col") for the 14x14/stride-14 patch-embedding conv (model/adapter.py:139,
 // model/transformer.py:359-365):  images fp32 NCHW [B,3,S,S]  ->  A bf16 [B*G*G, KP]  with
 // k = c*ps*ps + ky*ps + kx (the flattening order of conv1.weight[1024,3,14,14]); columns >= 3*ps*ps stay 0.
-// grid = (G, B), block = 256: one CTA per row of patches; reads are fully coalesced image rows.
+// grid = (G, B), block = 256: one CTA per row of patches. The 3*ps image rows of the patch row are converted into
+// shared memory with coalesced reads, then written out as 32-bit pairs in the order of A: consecutive threads store
+// consecutive words (the direct scatter wrote 28-byte runs 2 bytes at a time: 22 % of the HBM rate).
+// Needs an even patch size and image size (pairs never straddle a run of kx; 8-byte aligned image rows) and
+// 3*ps*W*2 bytes of shared memory.
 template <bool BF16>
-__global__ void patch_gather_kernel(const float* __restrict__ img, uint16_t* __restrict__ A, int S, int G,
-                                    int ps, int KP) {
+__global__ void __launch_bounds__(256)
+patch_gather_kernel(const float* __restrict__ img, uint16_t* __restrict__ A, int S, int G, int ps, int KP) {
+  extern __shared__ __align__(16) uint32_t rows32[];   // [3*ps][W/2] packed 16-bit pairs
   const int py = blockIdx.x, b = blockIdx.y;
   const int W = G * ps;  // pixels actually covered by patches (== S when S % ps == 0)
+  const int wp = W / 2, n_rows = 3 * ps;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // phase 1: a warp per image row (no integer division in the inner loop), 8-byte loads, one packed store per pair
+  for (int cr = warp; cr < n_rows; cr += 8) {
+    const int c = cr / ps, ky = cr - c * ps;
+    const float2* src = reinterpret_cast<const float2*>(img + ((static_cast<size_t>(b) * 3 + c) * S + (py * ps + ky)) * S);
+    uint32_t* dst = rows32 + cr * wp;
+    for (int i = lane; i < wp; i += 32) {
+      const float2 v = src[i];
+      dst[i] = ptx::pack16<BF16>(v.x, v.y);
+    }
+  }
+  __syncthreads();
+  // phase 2: thread = one 32-bit word position of an A row (its source offset is fixed: computed once), loop over patches
+  const int k_raw = 3 * ps * ps, wpr = KP / 2;         // 32-bit words per row of A
+  uint32_t* out = reinterpret_cast<uint32_t*>(A + (static_cast<size_t>(b) * G + py) * G * KP);
+  for (int w = threadIdx.x; w < wpr; w += blockDim.x) {
+    const int k = 2 * w;
+    if (k < k_raw) {
+      const int cr = k / ps, kx = k - cr * ps;
+      const uint32_t* src = rows32 + cr * wp + (kx >> 1);
+      const int step = ps >> 1;
+      for (int px = 0; px < G; ++px) out[px * wpr + w] = src[px * step];
+    } else {
+      for (int px = 0; px < G; ++px) out[px * wpr + w] = 0;   // K padding (the workspace may hold anything)
+    }
+  }
+}
+
+// general form of the same gather (odd patch size / width, or rows too large for shared memory)
+template <bool BF16>
+__global__ void patch_gather_simple_kernel(const float* __restrict__ img, uint16_t* __restrict__ A, int S, int G,
+                                           int ps, int KP) {
+  const int py = blockIdx.x, b = blockIdx.y;
+  const int W = G * ps;
   for (int cr = 0; cr < 3 * ps; ++cr) {
     const int c = cr / ps, ky = cr - c * ps;
     const float* src = img + ((static_cast<size_t>(b) * 3 + c) * S + (py * ps + ky)) * S;
@@ -36,7 +76,6 @@ __global__ void patch_gather_kernel(const float* __restrict__ img, uint16_t* __r
       A[row * KP + (c * ps + ky) * ps + kx] = ptx::cvt16<BF16>(src[x]);
     }
   }
-  // zero the K padding (the workspace is caller-owned and may hold anything)
   const int k_raw = 3 * ps * ps, pad = KP - k_raw;
   for (int i = threadIdx.x; i < G * pad; i += blockDim.x) {
     const int px = i / pad, k = k_raw + (i - px * pad);
@@ -252,15 +291,37 @@ __global__ void l2norm_rows_kernel(float* __restrict__ t, int rows) {
   }
 }
 
-// det_token = normalized_rows.mean(dim=1): [B,P,E] -> [B,E]   (model/adapter.py:184). Fixed summation order.
-__global__ void mean_over_patches_kernel(const float* __restrict__ t, float* __restrict__ out, int P, int E) {
+// det_token = normalized_rows.mean(dim=1): [B,P,E] -> [B,E]   (model/adapter.py:184).
+// block = (MEAN_COLS columns, MEAN_SEGS patch segments): every thread sums one contiguous segment of patches with eight
+// independent accumulators, the segments are combined through shared memory in a fixed order. The summation order
+// depends on (P, MEAN_SEGS) alone: bit-reproducible and independent of the batch.
+constexpr int MEAN_SEGS = 16, MEAN_COLS = 64;
+__global__ void __launch_bounds__(MEAN_COLS * MEAN_SEGS)
+mean_over_patches_kernel(const float* __restrict__ t, float* __restrict__ out, int P, int E) {
+  __shared__ float part[MEAN_SEGS][MEAN_COLS];
   const int b = blockIdx.y;
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= E) return;
-  const float* src = t + static_cast<size_t>(b) * P * E + e;
-  float s = 0.f;
-  for (int p = 0; p < P; ++p) s += src[static_cast<size_t>(p) * E];
-  out[static_cast<size_t>(b) * E + e] = s / static_cast<float>(P);
+  const int e = blockIdx.x * MEAN_COLS + threadIdx.x;
+  const int seg = threadIdx.y;
+  const int per = (P + MEAN_SEGS - 1) / MEAN_SEGS;
+  const int p0 = seg * per, p1 = min(P, p0 + per);
+  float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (e < E) {
+    const float* src = t + static_cast<size_t>(b) * P * E + e;
+    int p = p0;
+    for (; p + 8 <= p1; p += 8) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) a[u] += src[static_cast<size_t>(p + u) * E];
+    }
+    for (; p < p1; ++p) a[0] += src[static_cast<size_t>(p) * E];
+  }
+  part[seg][threadIdx.x] = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+  __syncthreads();
+  if (seg == 0 && e < E) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < MEAN_SEGS; ++k) s += part[k][threadIdx.x];
+    out[static_cast<size_t>(b) * E + e] = s / static_cast<float>(P);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -268,6 +329,29 @@ __global__ void mean_over_patches_kernel(const float* __restrict__ t, float* __r
 // One warp per patch row, both anchors in one pass over the row. text_bstride = 0 for a shared [E,2] anchor,
 // E*2 for per-image anchors [B,E,2].
 struct SegPtrs { const float* p[4]; };
+
+// NCH 16-byte feature loads per lane (issued before the first FMA) against the anchor pair [E,2], read as two float4
+// per feature float4 (6 KB, L1-resident)
+template <int NCH>
+__device__ __forceinline__ void similarity_row(const float* f, const float* t, int lane, int i0, float& s0, float& s1) {
+  const float4* f4 = reinterpret_cast<const float4*>(f);
+  const float4* t4 = reinterpret_cast<const float4*>(t);
+  float4 fv[NCH];
+#pragma unroll
+  for (int j = 0; j < NCH; ++j) fv[j] = f4[i0 + lane + 32 * j];
+  float u0 = 0.f, u1 = 0.f;
+#pragma unroll
+  for (int j = 0; j < NCH; ++j) {
+    const int i = i0 + lane + 32 * j;
+    const float4 ta = __ldg(t4 + 2 * i), tb = __ldg(t4 + 2 * i + 1);   // (x0 y0 x1 y1) (x2 y2 x3 y3)
+    s0 = fmaf(fv[j].x, ta.x, s0); s1 = fmaf(fv[j].x, ta.y, s1);
+    u0 = fmaf(fv[j].y, ta.z, u0); u1 = fmaf(fv[j].y, ta.w, u1);
+    s0 = fmaf(fv[j].z, tb.x, s0); s1 = fmaf(fv[j].z, tb.y, s1);
+    u0 = fmaf(fv[j].w, tb.z, u0); u1 = fmaf(fv[j].w, tb.w, u1);
+  }
+  s0 += u0;
+  s1 += u1;
+}
 
 __global__ void similarity_kernel(SegPtrs seg, const float* __restrict__ text, long long text_bstride,
                                   float* __restrict__ s, int B, int L, int P, int E) {
@@ -281,11 +365,17 @@ __global__ void similarity_kernel(SegPtrs seg, const float* __restrict__ text, l
   const float* f = seg.p[l] + (static_cast<size_t>(b) * P + p) * E;
   const float* t = text + static_cast<size_t>(b) * text_bstride;
   float s0 = 0.f, s1 = 0.f;
-  for (int i = lane; i < E; i += 32) {
-    const float fv = f[i];
-    const float2 tv = __ldg(reinterpret_cast<const float2*>(t) + i);
-    s0 = fmaf(fv, tv.x, s0);
-    s1 = fmaf(fv, tv.y, s1);
+  if (E == 768) {
+    similarity_row<6>(f, t, lane, 0, s0, s1);      // all six 16-byte loads of the lane in flight at once
+  } else if ((E & 127) == 0) {
+    for (int i0 = 0; i0 < E / 4; i0 += 32) similarity_row<1>(f, t, lane, i0, s0, s1);
+  } else {
+    for (int i = lane; i < E; i += 32) {
+      const float fv = f[i];
+      const float2 tv = __ldg(reinterpret_cast<const float2*>(t) + i);
+      s0 = fmaf(fv, tv.x, s0);
+      s1 = fmaf(fv, tv.y, s1);
+    }
   }
   s0 = warp_sum(s0);
   s1 = warp_sum(s1);
@@ -339,17 +429,29 @@ __global__ void anomaly_map_kernel(const float* __restrict__ s, float* __restric
   const int b = blockIdx.y;
   const float* sb = s + static_cast<size_t>(b) * L * 2 * P;
 
+  // bilinear, align_corners=True (ATen upsample_bilinear2d index/lambda arithmetic)
+  const float scale = (S > 1) ? static_cast<float>(G - 1) / static_cast<float>(S - 1) : 0.f;
+  const int y_begin = blockIdx.x * MAP_ROWS;
+  const int y_end = min(S, y_begin + MAP_ROWS);
+
   if (test_mode) {
-    for (int i = threadIdx.x; i < P; i += blockDim.x) g0[i] = 0.f;
-    __syncthreads();
+    // Only the grid rows this CTA's MAP_ROWS output rows interpolate between are blurred (3 of 37 at 518 px), from
+    // the horizontally blurred rows within the kernel radius of them: every CTA used to rebuild the whole grid.
+    // Same operations in the same order per element: bit-identical maps.
     const int r = ksize / 2;
+    const int gy_lo = static_cast<int>(scale * y_begin);
+    const int gy_hi = min(G - 1, static_cast<int>(scale * (y_end - 1)) + 1);
+    const int h_lo = max(0, gy_lo - r), h_hi = min(G - 1, gy_hi + r);   // reflected indices stay inside [h_lo, h_hi]
+    const int nh = (h_hi - h_lo + 1) * G, nv = (gy_hi - gy_lo + 1) * G;
+    for (int i = threadIdx.x; i < nv; i += blockDim.x) g0[gy_lo * G + i] = 0.f;
+    __syncthreads();
     for (int l = 0; l < L; ++l) {
       const float* s0 = sb + static_cast<size_t>(l) * 2 * P;
       const float* s1 = s0 + P;
-      for (int i = threadIdx.x; i < P; i += blockDim.x) g1[i] = (s1[i] + 1.0f - s0[i]) / 2.0f;
+      for (int i = h_lo * G + threadIdx.x; i < h_lo * G + nh; i += blockDim.x) g1[i] = (s1[i] + 1.0f - s0[i]) / 2.0f;
       __syncthreads();
       // horizontal pass
-      for (int i = threadIdx.x; i < P; i += blockDim.x) {
+      for (int i = h_lo * G + threadIdx.x; i < h_lo * G + nh; i += blockDim.x) {
         const int y = i / G, x = i - y * G;
         float acc = 0.f;
         for (int k = 0; k < ksize; ++k) acc = fmaf(taps.w[k], g1[y * G + reflect_idx(x + k - r, G)], acc);
@@ -357,7 +459,7 @@ __global__ void anomaly_map_kernel(const float* __restrict__ s, float* __restric
       }
       __syncthreads();
       // vertical pass, accumulated over levels
-      for (int i = threadIdx.x; i < P; i += blockDim.x) {
+      for (int i = gy_lo * G + threadIdx.x; i < gy_lo * G + nv; i += blockDim.x) {
         const int y = i / G, x = i - y * G;
         float acc = 0.f;
         for (int k = 0; k < ksize; ++k) acc = fmaf(taps.w[k], g2[reflect_idx(y + k - r, G) * G + x], acc);
@@ -373,10 +475,6 @@ __global__ void anomaly_map_kernel(const float* __restrict__ s, float* __restric
     __syncthreads();
   }
 
-  // bilinear, align_corners=True (ATen upsample_bilinear2d index/lambda arithmetic)
-  const float scale = (S > 1) ? static_cast<float>(G - 1) / static_cast<float>(S - 1) : 0.f;
-  const int y_begin = blockIdx.x * MAP_ROWS;
-  const int y_end = min(S, y_begin + MAP_ROWS);
   for (int y = y_begin; y < y_end; ++y) {
     const float fy = scale * y;
     const int y0 = static_cast<int>(fy);
