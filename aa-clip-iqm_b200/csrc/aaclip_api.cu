@@ -1319,7 +1319,8 @@ int aaclip_resample_coeffs_host(int32_t in_size, int32_t out_size, int32_t* boun
 
 size_t aaclip_preprocess_workspace_bytes(int32_t B, int32_t H, int32_t S) {
   if (B <= 0 || H <= 0 || S <= 0) return 0;
-  return (static_cast<size_t>(B) * H * S * 3 + 255) & ~static_cast<size_t>(255);
+  // [B, H, S, 3] uint8 intermediate + the 3 x 256 fp32 normalisation table
+  return ((static_cast<size_t>(B) * H * S * 3 + 255) & ~static_cast<size_t>(255)) + 4096;
 }
 
 int aaclip_preprocess_u8(const uint8_t* src, int32_t B, int32_t H, int32_t W, int32_t S, const int32_t* xbounds,
@@ -1333,33 +1334,49 @@ int aaclip_preprocess_u8(const uint8_t* src, int32_t B, int32_t H, int32_t W, in
   if (!workspace || workspace_bytes < aaclip_preprocess_workspace_bytes(B, H, S))
     return fail(AACLIP_EINVAL, "aaclip_preprocess_u8: workspace too small (%zu < %zu)", workspace_bytes,
                 aaclip_preprocess_workspace_bytes(B, H, S));
-  const size_t row_smem = static_cast<size_t>(HROWS) * W * 3 + 32;
-  if (row_smem > 200 * 1024) return fail(AACLIP_EINVAL, "aaclip_preprocess_u8: rows wider than 17 000 pixels are not supported");
+  if (reinterpret_cast<uintptr_t>(workspace) & 255) return fail(AACLIP_EINVAL, "aaclip_preprocess_u8: workspace must be 256-byte aligned");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   uint8_t* tmp = reinterpret_cast<uint8_t*>(workspace);
+  float* lut = reinterpret_cast<float*>(tmp + ((static_cast<size_t>(B) * H * S * 3 + 255) & ~static_cast<size_t>(255)));
   const long long rows = static_cast<long long>(B) * H;
   if (rows > 2147483647ll) return fail(AACLIP_EINVAL, "aaclip_preprocess_u8: too many rows");
   const int xks = resample_ksize_host(W, S), yks = resample_ksize_host(H, S);
-  const unsigned hgrid = static_cast<unsigned>((rows + HROWS - 1) / HROWS);
-  const dim3 vgrid((S * S + 127) / 128, B);
-  // tap loops unrolled for the usual scale factors (ksize = 5 up-scaling / same size, 9 for 2x, 13 for 3x down-scaling)
+
+  resample_lut_kernel<<<3, 256, 0, st>>>(lut, mean_host[0], mean_host[1], mean_host[2], std_host[0], std_host[1], std_host[2]);
+  LAUNCH_CHECK("resample_lut_kernel");
+
+  // horizontal pass: unrolled kernel for the usual scale factors (ksize 5: up-scaling / same size, 9: ~2x, 13: ~3x
+  // down-scaling) when the output row fits two columns per thread and 8 rows fit shared memory; generic kernel otherwise
+  const size_t smem_x = static_cast<size_t>(HROWS_X) * W * 3 + 16 + 64;
+  const int half = (S + 1) / 2, threads_x = ((half + 31) / 32) * 32;
+  if (xks <= 13 && threads_x <= 1024 && smem_x <= 200 * 1024) {
+    const unsigned grid = static_cast<unsigned>((rows + HROWS_X - 1) / HROWS_X);
 #define AACLIP_RESAMPLE_H(KS)                                                                                          \
   do {                                                                                                                 \
-    if (row_smem > 48 * 1024)                                                                                          \
-      CUDA_TRY(cudaFuncSetAttribute(resample_horizontal_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
-                                    static_cast<int>(row_smem)));                                                      \
-    resample_horizontal_kernel<KS><<<hgrid, 256, row_smem, st>>>(src, tmp, W, S, xbounds, xkk, xks, rows, rows * W * 3); \
+    if (smem_x > 48 * 1024)                                                                                            \
+      CUDA_TRY(cudaFuncSetAttribute(resample_horizontal_x_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                    static_cast<int>(smem_x)));                                                        \
+    resample_horizontal_x_kernel<KS><<<grid, threads_x, smem_x, st>>>(src, tmp, W, S, xbounds, xkk, xks, rows,         \
+                                                                      rows * W * 3);                                  \
   } while (0)
-  if (xks <= 5) AACLIP_RESAMPLE_H(5);
-  else if (xks <= 9) AACLIP_RESAMPLE_H(9);
-  else if (xks <= 13) AACLIP_RESAMPLE_H(13);
-  else AACLIP_RESAMPLE_H(0);
+    if (xks <= 5) AACLIP_RESAMPLE_H(5);
+    else if (xks <= 9) AACLIP_RESAMPLE_H(9);
+    else AACLIP_RESAMPLE_H(13);
 #undef AACLIP_RESAMPLE_H
+  } else {
+    const size_t smem_g = static_cast<size_t>(HROWS) * W * 3 + 32;
+    if (smem_g > 200 * 1024) return fail(AACLIP_EINVAL, "aaclip_preprocess_u8: rows wider than 17 000 pixels are not supported");
+    if (smem_g > 48 * 1024)
+      CUDA_TRY(cudaFuncSetAttribute(resample_horizontal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(smem_g)));
+    resample_horizontal_kernel<<<static_cast<unsigned>((rows + HROWS - 1) / HROWS), 256, smem_g, st>>>(
+        src, tmp, W, S, xbounds, xkk, xks, rows, rows * W * 3);
+  }
   LAUNCH_CHECK("resample_horizontal_kernel");
-#define AACLIP_RESAMPLE_V(KS)                                                                                          \
-  resample_vertical_normalize_kernel<KS><<<vgrid, 128, 0, st>>>(tmp, out, H, S, ybounds, ykk, yks, mean_host[0],      \
-                                                                 mean_host[1], mean_host[2], std_host[0], std_host[1], \
-                                                                 std_host[2])
+
+  const dim3 vgrid((S * S + 127) / 128, B);
+#define AACLIP_RESAMPLE_V(KS) \
+  resample_vertical_normalize_kernel<KS><<<vgrid, 128, 0, st>>>(tmp, out, H, S, ybounds, ykk, yks, lut)
   if (yks <= 5) AACLIP_RESAMPLE_V(5);
   else if (yks <= 9) AACLIP_RESAMPLE_V(9);
   else if (yks <= 13) AACLIP_RESAMPLE_V(13);
