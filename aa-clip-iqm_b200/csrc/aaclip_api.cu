@@ -901,8 +901,14 @@ int aaclip_forward(AaclipHandle* h, const float* images, int32_t B, void* worksp
   {
     ProfScope ps(h, AACLIP_PROF_OTHER, 0.0, st);
     const size_t gsmem = static_cast<size_t>(3) * c.patch * h->G * c.patch * 2;
-    if (c.patch % 2 == 0 && c.img_size % 2 == 0 && h->KP % 2 == 0 && gsmem <= 48 * 1024 &&
+    // AACLIP_PATCH_GATHER_SIMPLE=1 forces the general kernel (tests compare the two paths bit for bit)
+    static const bool force_simple = getenv("AACLIP_PATCH_GATHER_SIMPLE") != nullptr;
+    if (!force_simple && c.patch % 2 == 0 && c.img_size % 2 == 0 && h->KP % 2 == 0 && gsmem <= 160 * 1024 &&
         (reinterpret_cast<uintptr_t>(images) & 7) == 0) {
+      if (gsmem > 48 * 1024) {
+        if (bf) CUDA_TRY(cudaFuncSetAttribute(patch_gather_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(gsmem)));
+        else CUDA_TRY(cudaFuncSetAttribute(patch_gather_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(gsmem)));
+      }
       if (bf) patch_gather_kernel<true><<<dim3(h->G, B), 256, gsmem, st>>>(images, patchA, c.img_size, h->G, c.patch, h->KP);
       else patch_gather_kernel<false><<<dim3(h->G, B), 256, gsmem, st>>>(images, patchA, c.img_size, h->G, c.patch, h->KP);
     } else {

@@ -97,6 +97,35 @@ def test_forward_matches_cpu_oracle_on_the_box_and_exports_iqm_inputs():
     assert (cls.cpu() - o["cls"]).abs().max().item() < 5e-2
 
 
+def test_patch_gather_fast_and_general_kernels_agree():
+    """The shared-memory patch gather (even patch / image size) and the general kernel write the same operand bytes:
+    forward outputs are bit-identical. The general path is selected by an environment switch read at first use, so it
+    runs in a child process."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "import torch, aaclip_b200\n"
+        "from aaclip_b200 import engine, weights\n"
+        "sd = weights.make_visual_state_dict(seed=5, img_size=224)\n"
+        "eng = engine.AaclipEngine('cuda', img_size=224, max_batch=2); eng.load_state_dict(sd)\n"
+        "seg, det, _, _ = eng.forward(weights.make_images(5, 2, 224).cuda())\n"
+        "torch.cuda.synchronize()\n"
+        "print(float(seg[0].double().sum()), float(seg[3].double().sum()), float(det.double().sum()))\n"
+    ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for simple in (False, True):
+        env = dict(os.environ)
+        env.pop("AACLIP_PATCH_GATHER_SIMPLE", None)
+        if simple:
+            env["AACLIP_PATCH_GATHER_SIMPLE"] = "1"
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(r.stdout.strip().splitlines()[-1])
+    assert outs[0] == outs[1], outs
+
+
 def test_batch_invariance_and_determinism():
     """Data-parallel sharding must not change per-image results: image 0 alone == image 0 inside a batch, bit for bit."""
     import aaclip_b200  # noqa: F401
