@@ -39,7 +39,7 @@ def test_baseline_size_checksum_equals_pil(pre):
 
 
 @pytest.mark.parametrize("H,W,S", [(1, 1, 8), (2, 3, 5), (17, 301, 37), (301, 17, 37), (518, 518, 518), (64, 100, 64),
-                                   (100, 64, 64), (999, 1001, 336), (13, 4099, 24)])
+                                   (100, 64, 64), (999, 1001, 336), (13, 4099, 24), (200, 40, 24), (40, 200, 24)])
 def test_ragged_sizes_equal_the_oracle(pre, H, W, S):
     rng = np.random.default_rng(H * 7919 + W)
     img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
