@@ -129,6 +129,41 @@ def test_massive_activation_channels_stay_within_tolerance():
     assert (score.cpu() - o["score"]).abs().max().item() < SCORE_TOL
 
 
+def test_auroc_and_ap_agree_with_the_fp32_oracle_to_three_decimals():
+    """north_star: "AUROC ... identical to 3 decimals". Eight seeded images through the sm_100a path (fp16 operands) and
+    through the fp32 oracle, scored against the same synthetic ground truth (a noisy threshold of the oracle's own maps,
+    so the curves are neither trivial nor random) with the reference's metrics_eval semantics (forward_utils.py:233-308).
+    Image AUROC on 8 images moves in steps of 1/16, so it must be identical; the pixel metrics may differ by < 1e-3."""
+    import aaclip_b200  # noqa: F401
+    from aaclip_b200 import engine, forward_utils as fu, weights
+    from oracle import aaclip_oracle as orc
+    S, B, seed = 224, 8, 33
+    sd = weights.make_visual_state_dict(seed=seed, img_size=S)
+    eng = engine.AaclipEngine("cuda", img_size=S, max_batch=B)
+    eng.load_state_dict(sd)
+    images = weights.make_images(seed, B, S)
+    text = weights.make_text_anchor(seed)
+    seg, det, _, _ = eng.forward(images.cuda())
+    maps, score = engine.score_maps(seg, text.cuda(), S, test=True, ksize=7, sigma=1.0, det=det)
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        o = orc.predict(sd, images, text, S, domain="Industrial")
+    ref_maps, ref_score = o["maps"].numpy(), o["score"].numpy()
+    rng = np.random.default_rng(seed)
+    noisy = ref_maps + rng.normal(0, ref_maps.std(), ref_maps.shape)
+    pixel_label = (noisy > np.quantile(noisy, 0.93)).astype(np.int64)
+    image_label = (ref_score + rng.normal(0, ref_score.std(), B) > np.median(ref_score)).astype(np.int64)
+    assert 0 < image_label.sum() < B
+    ours = fu.metrics_eval(pixel_label, image_label, maps.cpu().numpy(), score.cpu().numpy(), "synthetic", "Industrial")
+    ref = fu.metrics_eval(pixel_label, image_label, ref_maps, ref_score, "synthetic", "Industrial")
+    print("ours", ours, "\nref ", ref)
+    assert 55.0 < ref["pixel AUC"] < 99.5                      # a non-trivial curve
+    for k in ("pixel AUC", "pixel AP"):
+        assert abs(ours[k] - ref[k]) < 0.1, (k, ours[k], ref[k])   # percent units: 0.1 = 1e-3 of the [0, 1] metric
+    for k in ("image AUC", "image AP"):
+        assert abs(ours[k] - ref[k]) < 1e-9, (k, ours[k], ref[k])
+
+
 def test_patch_gather_fast_and_general_kernels_agree():
     """The shared-memory patch gather (even patch / image size) and the general kernel write the same operand bytes:
     forward outputs are bit-identical. The general path is selected by an environment switch read at first use, so it
