@@ -213,6 +213,36 @@ def test_batch_invariance_and_determinism():
     assert torch.equal(det5[2:3], det1) and torch.equal(m5[2:3], m1) and torch.equal(s5[2:3], s1)
 
 
+def test_full_size_batch_properties():
+    """BASELINE config 2 at full size (B = 32 @518), through properties that need no oracle run: two passes are
+    bit-identical; images 0, 13 and 31 alone equal their rows in the batch (what data-parallel sharding relies on); a
+    16 + 16 split equals the whole batch; patch features are unit-norm; maps are finite and bounded by the level count
+    (each level map is (s1 + 1 - s0) / 2 with |s| <= 100 |cos| blurred and interpolated, i.e. within [-99.5, 100.5])."""
+    import aaclip_b200  # noqa: F401
+    from aaclip_b200 import pipeline, weights
+    S, B = 518, 32
+    pred = pipeline.AnomalyPredictor(weights.make_visual_state_dict(seed=0, img_size=S), weights.make_text_anchor(0),
+                                     img_size=S, max_batch=B)
+    images = weights.make_images(0, B, S).cuda()
+    m_a, s_a = pred.predict_device(images)
+    m_a, s_a = m_a.clone(), s_a.clone()
+    m_b, s_b = pred.predict_device(images)
+    assert torch.equal(m_a, m_b) and torch.equal(s_a, s_b)
+    for i in (0, 13, 31):
+        m1, s1 = pred.predict_device(images[i:i + 1])
+        assert torch.equal(m1[0], m_a[i]) and torch.equal(s1[0], s_a[i]), i
+    halves = [pred.predict_device(images[k:k + 16]) for k in (0, 16)]
+    halves = [(m.clone(), s.clone()) for m, s in halves]
+    assert torch.equal(torch.cat([h[0] for h in halves]), m_a) and torch.equal(torch.cat([h[1] for h in halves]), s_a)
+    seg, det, _, _ = pred.engine.forward(images)
+    for f in seg:
+        n = f.norm(dim=-1)
+        assert torch.allclose(n, torch.ones_like(n), atol=1e-5)
+    assert torch.isfinite(m_a).all() and m_a.abs().max().item() <= 4 * 100.5
+    assert ((s_a >= 0) & (s_a <= 1)).all()
+    assert pred.launches_per_batch == 154      # 151 tower launches + similarity, anomaly-map and image-score kernels
+
+
 def test_argument_errors():
     import aaclip_b200  # noqa: F401
     from aaclip_b200 import engine
