@@ -315,9 +315,10 @@ def run_ours(args):
     # ---- CPU baseline: bounded sample on the box's host cores (rank 0, N=1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        t = cpu_reference_time(S, args.seed, n_timed=2, warm=1)
+        n_cpu = 10 if S >= 500 else 20          # ~10 s of CPU work on the box's 16 cores
+        t = cpu_reference_time(S, args.seed, n_timed=n_cpu, warm=1)
         cpu = {"value": len(t) / sum(t), "unit": "images/s", "cores": os.cpu_count() or 1, "kind": "port",
-               "sample": f"2 timed single-image passes @{S}px after 1 warm-up, fp32 torch CPU oracle port, all host threads"}
+               "sample": f"{n_cpu} timed single-image passes @{S}px after 1 warm-up, fp32 torch CPU oracle port, all host threads"}
 
     if rank == 0:
         fpi = flop_per_image(S)
