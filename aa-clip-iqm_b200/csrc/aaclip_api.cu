@@ -8,6 +8,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
 #include <string>
 #include <vector>
 
@@ -83,17 +84,74 @@ int make_tmap_16(CUtensorMap* map, const void* base, int rank, const uint64_t* d
   return AACLIP_OK;
 }
 
-int g_num_sms = 0;
-int ensure_device() {
-  if (g_num_sms > 0) return AACLIP_OK;
+// Per-device state. Function attributes (the > 48 KiB dynamic shared-memory opt-in) and the SM count belong to the
+// CURRENT device's context: a process that drives several GPUs (AaclipEngine(device="cuda:1")) must see them set on
+// each. Everything is keyed by device ordinal; the flags are atomics, so first calls from several threads may both set
+// an attribute (idempotent) but never skip it.
+constexpr int kMaxDevices = 64;
+std::atomic<int> g_sms[kMaxDevices];
+
+int current_device() {
   int dev = 0;
-  CUDA_TRY(cudaGetDevice(&dev));
-  cudaDeviceProp prop;
-  CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
-  if (prop.major != 10) return fail(AACLIP_ENOSYS, "device '%s' is sm_%d%d; this library is sm_100a only", prop.name,
-                                    prop.major, prop.minor);
-  g_num_sms = prop.multiProcessorCount;
+  cudaGetDevice(&dev);
+  return dev;
+}
+
+int ensure_device(int* num_sms = nullptr) {
+  const int dev = current_device();
+  if (dev < 0 || dev >= kMaxDevices) return fail(AACLIP_EINVAL, "device ordinal %d outside 0..%d", dev, kMaxDevices - 1);
+  int sms = g_sms[dev].load(std::memory_order_relaxed);
+  if (sms == 0) {
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10) return fail(AACLIP_ENOSYS, "device '%s' is sm_%d%d; this library is sm_100a only", prop.name,
+                                      prop.major, prop.minor);
+    sms = prop.multiProcessorCount;
+    g_sms[dev].store(sms, std::memory_order_relaxed);
+  }
+  if (num_sms) *num_sms = sms;
   return AACLIP_OK;
+}
+
+// One flag word per kernel instantiation: bit d set = cudaFuncSetAttribute has run on device d.
+struct PerDeviceOnce {
+  std::atomic<uint64_t> mask{0};
+  bool needed() const { return (mask.load(std::memory_order_acquire) >> (current_device() & 63) & 1ull) == 0; }
+  void done() { mask.fetch_or(1ull << (current_device() & 63), std::memory_order_release); }
+};
+
+template <typename K>
+int opt_in_smem(PerDeviceOnce& once, K kernel, size_t bytes) {
+  if (bytes <= 48 * 1024 || !once.needed()) return AACLIP_OK;
+  CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)));
+  once.done();
+  return AACLIP_OK;
+}
+
+// Programmatic dependent launch (ptx.cuh: pdl_wait / pdl_trigger). AACLIP_PDL=0 turns the attribute off (plain stream
+// order), e.g. to A/B the overlap.
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("AACLIP_PDL");
+    return !(e != nullptr && e[0] == '0');
+  }();
+  return on;
+}
+
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
 // ------------------------------------------------------------------------------------------ kernel launchers
@@ -101,17 +159,15 @@ template <int EPI, bool BF16>
 int launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const GemmEpi& epi,
                   cudaStream_t st) {
   using C = GemmPairCfg<256>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(gemm_pair_kernel<EPI, BF16, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  C::SMEM_BYTES));
-    attr_set = true;
-  }
+  static PerDeviceOnce once;
+  if (int rc = opt_in_smem(once, gemm_pair_kernel<EPI, BF16, 256>, C::SMEM_BYTES)) return rc;
+  int sms = 0;
+  if (int rc = ensure_device(&sms)) return rc;
   // persistent: one CTA pair (cluster of 2) per two SMs, each looping over 256 x 256 output tiles
   const int tiles = ((M + 2 * C::BM - 1) / (2 * C::BM)) * (N / C::BN);
-  const int pairs = tiles < g_num_sms / 2 ? tiles : g_num_sms / 2;
-  gemm_pair_kernel<EPI, BF16, 256><<<2 * pairs, C::THREADS, C::SMEM_BYTES, st>>>(ta, tb, M, N, K, epi);
-  LAUNCH_CHECK("gemm_pair_kernel");
+  const int pairs = tiles < sms / 2 ? tiles : sms / 2;
+  CUDA_TRY(launch_pdl(gemm_pair_kernel<EPI, BF16, 256>, dim3(2 * pairs), dim3(C::THREADS), C::SMEM_BYTES, st, ta, tb, M, N,
+                      K, epi));
   return AACLIP_OK;
 }
 
@@ -158,17 +214,12 @@ int launch_gemm(int epi_mode, bool bf16, const void* A, const void* W, int M, in
 
 template <bool BF16>
 int launch_attention_t(const CUtensorMap& tq, void* out, int B, int N, int D, int causal, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(attention_tcgen05_kernel<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  attn_cfg::SMEM_BYTES));
-    attr_set = true;
-  }
+  static PerDeviceOnce once;
+  if (int rc = opt_in_smem(once, attention_tcgen05_kernel<BF16>, attn_cfg::SMEM_BYTES)) return rc;
   dim3 grid((N + attn_cfg::BQ * attn_cfg::QT - 1) / (attn_cfg::BQ * attn_cfg::QT), D / 64, B);
   const float scale_log2 = 0.125f * 1.4426950408889634f;  // head_dim^-0.5 * log2(e)
-  attention_tcgen05_kernel<BF16><<<grid, attn_cfg::THREADS, attn_cfg::SMEM_BYTES, st>>>(
-      tq, reinterpret_cast<uint16_t*>(out), N, D, causal, scale_log2);
-  LAUNCH_CHECK("attention_tcgen05_kernel");
+  CUDA_TRY(launch_pdl(attention_tcgen05_kernel<BF16>, grid, dim3(attn_cfg::THREADS), attn_cfg::SMEM_BYTES, st, tq,
+                      reinterpret_cast<uint16_t*>(out), N, D, causal, scale_log2));
   return AACLIP_OK;
 }
 
@@ -188,8 +239,8 @@ void launch_layernorm_t(const float* x, const float* g, const float* b, void* ou
                         int skipP, bool normalize, cudaStream_t st, float* stats_out, int np) {
   const int threads = 256, grid = (rows + 7) / 8;
   uint16_t* o = reinterpret_cast<uint16_t*>(out16);
-  if (normalize) layernorm_kernel<D, true, BF16><<<grid, threads, 0, st>>>(x, g, b, o, out_f32, rows, skipP, 1e-5f, stats_out, np);
-  else layernorm_kernel<D, false, BF16><<<grid, threads, 0, st>>>(x, g, b, o, out_f32, rows, skipP, 1e-5f, stats_out, np);
+  if (normalize) launch_pdl(layernorm_kernel<D, true, BF16>, dim3(grid), dim3(threads), 0, st, x, g, b, o, out_f32, rows, skipP, 1e-5f, stats_out, np);
+  else launch_pdl(layernorm_kernel<D, false, BF16>, dim3(grid), dim3(threads), 0, st, x, g, b, o, out_f32, rows, skipP, 1e-5f, stats_out, np);
 }
 
 int launch_layernorm(bool bf16, const float* x, const float* g, const float* b, void* out16, float* out_f32, int rows,
@@ -218,6 +269,8 @@ __global__ void pack16_kernel(const float* __restrict__ src, uint16_t* __restric
 }
 
 __global__ void gather_cls_kernel(const float* __restrict__ x, float* __restrict__ out, int tokens, int D) {
+  ptx::pdl_trigger();
+  ptx::pdl_wait();
   const int b = blockIdx.x;
   for (int i = threadIdx.x; i < D; i += blockDim.x) out[static_cast<size_t>(b) * D + i] = x[static_cast<size_t>(b) * tokens * D + i];
 }
@@ -528,11 +581,11 @@ struct BlockRun {
       const int grid = (M + 7) / 8;
       const float w = adapt_weight, w1 = 1.0f - adapt_weight;
       if (W == 1024) {
-        if (bf16) adapter_blend_kernel<1024, true><<<grid, 256, 0, st>>>(x, abuf, M, w, w1, x16, stats, np);
-        else adapter_blend_kernel<1024, false><<<grid, 256, 0, st>>>(x, abuf, M, w, w1, x16, stats, np);
+        if (bf16) launch_pdl(adapter_blend_kernel<1024, true>, dim3(grid), dim3(256), 0, st, x, static_cast<const float*>(abuf), M, w, w1, x16, stats, np);
+        else launch_pdl(adapter_blend_kernel<1024, false>, dim3(grid), dim3(256), 0, st, x, static_cast<const float*>(abuf), M, w, w1, x16, stats, np);
       } else {
-        if (bf16) adapter_blend_kernel<768, true><<<grid, 256, 0, st>>>(x, abuf, M, w, w1, x16, stats, np);
-        else adapter_blend_kernel<768, false><<<grid, 256, 0, st>>>(x, abuf, M, w, w1, x16, stats, np);
+        if (bf16) launch_pdl(adapter_blend_kernel<768, true>, dim3(grid), dim3(256), 0, st, x, static_cast<const float*>(abuf), M, w, w1, x16, stats, np);
+        else launch_pdl(adapter_blend_kernel<768, false>, dim3(grid), dim3(256), 0, st, x, static_cast<const float*>(abuf), M, w, w1, x16, stats, np);
       }
       LAUNCH_CHECK("adapter_blend_kernel");
       ++launches;
@@ -891,8 +944,8 @@ int aaclip_forward(AaclipHandle* h, const float* images, int32_t B, void* worksp
     ProfScope ps(h, AACLIP_PROF_OTHER, 0.0, st);
     ++launches;
     const int grid = (rows + 7) / 8;
-    if (E == 768) l2norm_rows_kernel<768><<<grid, 256, 0, st>>>(t, rows);
-    else l2norm_rows_kernel<1024><<<grid, 256, 0, st>>>(t, rows);
+    if (E == 768) launch_pdl(l2norm_rows_kernel<768>, dim3(grid), dim3(256), 0, st, t, rows);
+    else launch_pdl(l2norm_rows_kernel<1024>, dim3(grid), dim3(256), 0, st, t, rows);
     LAUNCH_CHECK("l2norm_rows_kernel");
     return AACLIP_OK;
   };
@@ -905,15 +958,16 @@ int aaclip_forward(AaclipHandle* h, const float* images, int32_t B, void* worksp
     static const bool force_simple = getenv("AACLIP_PATCH_GATHER_SIMPLE") != nullptr;
     if (!force_simple && c.patch % 2 == 0 && c.img_size % 2 == 0 && h->KP % 2 == 0 && gsmem <= 160 * 1024 &&
         (reinterpret_cast<uintptr_t>(images) & 7) == 0) {
+      // (the opt-in is per image geometry, so it is simply repeated: one host call per forward)
       if (gsmem > 48 * 1024) {
         if (bf) CUDA_TRY(cudaFuncSetAttribute(patch_gather_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(gsmem)));
         else CUDA_TRY(cudaFuncSetAttribute(patch_gather_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(gsmem)));
       }
-      if (bf) patch_gather_kernel<true><<<dim3(h->G, B), 256, gsmem, st>>>(images, patchA, c.img_size, h->G, c.patch, h->KP);
-      else patch_gather_kernel<false><<<dim3(h->G, B), 256, gsmem, st>>>(images, patchA, c.img_size, h->G, c.patch, h->KP);
+      if (bf) launch_pdl(patch_gather_kernel<true>, dim3(h->G, B), dim3(256), gsmem, st, images, patchA, c.img_size, h->G, c.patch, h->KP);
+      else launch_pdl(patch_gather_kernel<false>, dim3(h->G, B), dim3(256), gsmem, st, images, patchA, c.img_size, h->G, c.patch, h->KP);
     } else {
-      if (bf) patch_gather_simple_kernel<true><<<dim3(h->G, B), 256, 0, st>>>(images, patchA, c.img_size, h->G, c.patch, h->KP);
-      else patch_gather_simple_kernel<false><<<dim3(h->G, B), 256, 0, st>>>(images, patchA, c.img_size, h->G, c.patch, h->KP);
+      if (bf) launch_pdl(patch_gather_simple_kernel<true>, dim3(h->G, B), dim3(256), 0, st, images, patchA, c.img_size, h->G, c.patch, h->KP);
+      else launch_pdl(patch_gather_simple_kernel<false>, dim3(h->G, B), dim3(256), 0, st, images, patchA, c.img_size, h->G, c.patch, h->KP);
     }
     LAUNCH_CHECK("patch_gather_kernel"); ++launches;
   }
@@ -923,7 +977,7 @@ int aaclip_forward(AaclipHandle* h, const float* images, int32_t B, void* worksp
   }
   {
     ProfScope ps(h, AACLIP_PROF_OTHER, 0.0, st);
-    cls_row_kernel<<<B, 256, 0, st>>>(x, h->cls, h->pos, N, W);
+    launch_pdl(cls_row_kernel, dim3(B), dim3(256), 0, st, x, static_cast<const float*>(h->cls), static_cast<const float*>(h->pos), N, W);
     LAUNCH_CHECK("cls_row_kernel"); ++launches;
   }
   // ln_pre in place; also emits the 16-bit copy and the LayerNorm partials block 0's folded ln_1 needs
@@ -945,7 +999,7 @@ int aaclip_forward(AaclipHandle* h, const float* images, int32_t B, void* worksp
           if ((rc = run.gemm(proj_epi, tok, h->w_det, MP, E, W, e))) return rc; }
         if ((rc = l2norm(detbuf, MP))) return rc;
         ProfScope ps(h, AACLIP_PROF_OTHER, 0.0, st);
-        mean_over_patches_kernel<<<dim3((E + MEAN_COLS - 1) / MEAN_COLS, B), dim3(MEAN_COLS, MEAN_SEGS), 0, st>>>(detbuf, det_out, P, E);
+        launch_pdl(mean_over_patches_kernel, dim3((E + MEAN_COLS - 1) / MEAN_COLS, B), dim3(MEAN_COLS, MEAN_SEGS), 0, st, static_cast<const float*>(detbuf), det_out, P, E);
         LAUNCH_CHECK("mean_over_patches_kernel");
         ++launches;
       }
@@ -954,7 +1008,7 @@ int aaclip_forward(AaclipHandle* h, const float* images, int32_t B, void* worksp
   }
   if (cls_out != nullptr) {
     ProfScope ps(h, AACLIP_PROF_OTHER, 0.0, st);
-    gather_cls_kernel<<<B, 256, 0, st>>>(x, cls_out, N, W);
+    launch_pdl(gather_cls_kernel, dim3(B), dim3(256), 0, st, static_cast<const float*>(x), cls_out, N, W);
     LAUNCH_CHECK("gather_cls_kernel"); ++launches;
   }
   h->last_launches = launches;
@@ -1017,7 +1071,7 @@ int aaclip_score_maps(const float* const* seg, int32_t n_levels, const float* te
   {
     const long long rows = (long long)B * n_levels * P;
     const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
-    similarity_kernel<<<grid, 256, 0, st>>>(sp, text, tstride, s, B, n_levels, P, E);
+    launch_pdl(similarity_kernel, dim3(grid), dim3(256), 0, st, sp, text, tstride, s, B, n_levels, P, E);
     LAUNCH_CHECK("similarity_kernel");
   }
   MapTaps taps;
@@ -1033,19 +1087,16 @@ int aaclip_score_maps(const float* const* seg, int32_t n_levels, const float* te
     for (int k = 0; k < ksize; ++k) taps.w[k] /= sum;
   }
   {
-    static bool attr_set = false;
+    static PerDeviceOnce once;
     const size_t smem = 3 * (size_t)P * sizeof(float);
     if (smem > 200 * 1024) return fail(AACLIP_EINVAL, "aaclip_score_maps: grid %dx%d too large", G, G);
-    if (!attr_set) {
-      CUDA_TRY(cudaFuncSetAttribute(anomaly_map_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      attr_set = true;
-    }
+    if (int rc = opt_in_smem(once, anomaly_map_kernel, 200 * 1024)) return rc;
     dim3 grid((S + MAP_ROWS - 1) / MAP_ROWS, B);
-    anomaly_map_kernel<<<grid, 256, smem, st>>>(s, maps_out, n_levels, G, S, test_mode, ksize, taps);
+    launch_pdl(anomaly_map_kernel, grid, dim3(256), smem, st, static_cast<const float*>(s), maps_out, n_levels, G, S, test_mode, ksize, taps);
     LAUNCH_CHECK("anomaly_map_kernel");
   }
   if (det != nullptr && score_out != nullptr) {
-    image_score_kernel<<<(B + 7) / 8, 256, 0, st>>>(det, text, tstride, score_out, B, E);
+    launch_pdl(image_score_kernel, dim3((B + 7) / 8), dim3(256), 0, st, det, text, tstride, score_out, B, E);
     LAUNCH_CHECK("image_score_kernel");
   }
   return AACLIP_OK;
@@ -1237,14 +1288,14 @@ int aaclip_encode_text(AaclipTextHandle* h, const int32_t* tokens, int32_t n, vo
 
   // token + positional embedding (model/adapter.py:277-281); an identity-LayerNorm pass (NORMALIZE=false) then
   // produces the raw 16-bit copy and the LayerNorm partials block 0's folded ln_1 needs
-  text_embed_kernel<<<M, 192, 0, st>>>(tokens, h->tok_emb, h->pos, run.x, T, W, c.vocab);
+  launch_pdl(text_embed_kernel, dim3(M), dim3(192), 0, st, tokens, static_cast<const float*>(h->tok_emb), static_cast<const float*>(h->pos), run.x, T, W, c.vocab);
   LAUNCH_CHECK("text_embed_kernel");
   if ((rc = launch_layernorm(bf, run.x, nullptr, nullptr, run.x16, nullptr, M, W, 0, /*normalize=*/false, st, run.stats, kStatPartials(W)))) return rc;
   // 12 causal residual attention blocks + adapters (model/adapter.py:284-295)
   for (int i = 0; i < c.layers; ++i)
     if ((rc = run.run(h->blk[i], i < c.adapt_until ? h->w_adapter[i] : nullptr, c.adapt_weight))) return rc;
   // EOT row -> ln_final -> SimpleProj + LeakyReLU (model/adapter.py:296-298)
-  text_gather_eot_kernel<<<n, 192, 0, st>>>(tokens, run.x, eot, T, W);
+  launch_pdl(text_gather_eot_kernel, dim3(n), dim3(192), 0, st, tokens, static_cast<const float*>(run.x), eot, T, W);
   LAUNCH_CHECK("text_gather_eot_kernel");
   if ((rc = launch_layernorm(bf, eot, h->lnf_g, h->lnf_b, eot16, nullptr, n, W, 0, true, st))) return rc;
   { GemmEpi e; e.out_f32 = out; e.ldo = E;

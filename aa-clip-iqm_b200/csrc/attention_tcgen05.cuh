@@ -248,6 +248,8 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, uint16_t*
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
+  ptx::pdl_trigger();      // programmatic dependent launch (ptx.cuh): no global access above this line
+  ptx::pdl_wait();
 
   // The softmax warpgroups need a whole S row in registers: warpgroup 2 (TMA, MMA, 2 idle warps) hands its
   // registers over with setmaxnreg (issued inside each role's branch so ptxas allocates per role).

@@ -30,6 +30,8 @@ template <bool BF16>
 __global__ void __launch_bounds__(256)
 patch_gather_kernel(const float* __restrict__ img, uint16_t* __restrict__ A, int S, int G, int ps, int KP) {
   extern __shared__ __align__(16) uint32_t rows32[];   // [3*ps][W/2] packed 16-bit pairs
+  ptx::pdl_trigger();
+  ptx::pdl_wait();
   const int py = blockIdx.x, b = blockIdx.y;
   const int W = G * ps;  // pixels actually covered by patches (== S when S % ps == 0)
   const int wp = W / 2, n_rows = 3 * ps;
@@ -65,6 +67,8 @@ patch_gather_kernel(const float* __restrict__ img, uint16_t* __restrict__ A, int
 template <bool BF16>
 __global__ void patch_gather_simple_kernel(const float* __restrict__ img, uint16_t* __restrict__ A, int S, int G,
                                            int ps, int KP) {
+  ptx::pdl_trigger();
+  ptx::pdl_wait();
   const int py = blockIdx.x, b = blockIdx.y;
   const int W = G * ps;
   for (int cr = 0; cr < 3 * ps; ++cr) {
@@ -106,6 +110,8 @@ __global__ void patch_gather_f32_kernel(const float* __restrict__ img, float* __
 // x[b*(P+1), :] = class_embedding + positional_embedding[0, :]      (model/adapter.py:143-153)
 __global__ void cls_row_kernel(float* __restrict__ x, const float* __restrict__ cls, const float* __restrict__ pos,
                                int tokens, int D) {
+  ptx::pdl_trigger();
+  ptx::pdl_wait();
   const int b = blockIdx.x;
   for (int i = threadIdx.x; i < D; i += blockDim.x) x[static_cast<size_t>(b) * tokens * D + i] = cls[i] + pos[i];
 }
@@ -118,11 +124,15 @@ __global__ void cls_row_kernel(float* __restrict__ x, const float* __restrict__ 
 // stats_out != nullptr additionally emits (sum, sum of squares) of the OUTPUT row as partial 0 of stats_out[row][np][2]
 // (partials 1..np-1 zeroed): the LayerNorm statistics the next GEMM's folded-LN epilogue needs when this kernel
 // produces the residual stream (ln_pre).
+// x and out_f32 may be the same buffer (ln_pre runs in place: each warp loads its whole row before it stores), so
+// neither is declared __restrict__.
 template <int D, bool NORMALIZE, bool BF16>
-__global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+__global__ void layernorm_kernel(const float* x, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, uint16_t* __restrict__ out_bf16,
-                                 float* __restrict__ out_f32, int rows, int skipP, float eps,
+                                 float* out_f32, int rows, int skipP, float eps,
                                  float* __restrict__ stats_out = nullptr, int np = 0) {
+  ptx::pdl_trigger();
+  ptx::pdl_wait();
   constexpr int V = D / 128;  // float4 per lane
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -194,6 +204,8 @@ template <int D, bool BF16>
 __global__ void adapter_blend_kernel(float* __restrict__ x, const float* __restrict__ a, int rows, float w,
                                      float one_minus_w, uint16_t* __restrict__ x16 = nullptr,
                                      float* __restrict__ stats_out = nullptr, int np = 0) {
+  ptx::pdl_trigger();
+  ptx::pdl_wait();
   constexpr int V = D / 128;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -271,6 +283,8 @@ __global__ void ln_fold_kernel(const float* __restrict__ W, const float* __restr
 // F.normalize(t, dim=-1) in place: t / max(||t||_2, 1e-12)   (model/adapter.py:182-184). One warp per row.
 template <int D>
 __global__ void l2norm_rows_kernel(float* __restrict__ t, int rows) {
+  ptx::pdl_trigger();
+  ptx::pdl_wait();
   constexpr int V = D / 128;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -298,6 +312,8 @@ __global__ void l2norm_rows_kernel(float* __restrict__ t, int rows) {
 constexpr int MEAN_SEGS = 16, MEAN_COLS = 64;
 __global__ void __launch_bounds__(MEAN_COLS * MEAN_SEGS)
 mean_over_patches_kernel(const float* __restrict__ t, float* __restrict__ out, int P, int E) {
+  ptx::pdl_trigger();
+  ptx::pdl_wait();
   __shared__ float part[MEAN_SEGS][MEAN_COLS];
   const int b = blockIdx.y;
   const int e = blockIdx.x * MEAN_COLS + threadIdx.x;
@@ -355,6 +371,8 @@ __device__ __forceinline__ void similarity_row(const float* f, const float* t, i
 
 __global__ void similarity_kernel(SegPtrs seg, const float* __restrict__ text, long long text_bstride,
                                   float* __restrict__ s, int B, int L, int P, int E) {
+  ptx::pdl_trigger();
+  ptx::pdl_wait();
   const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const long long total = static_cast<long long>(B) * L * P;
@@ -389,6 +407,8 @@ __global__ void similarity_kernel(SegPtrs seg, const float* __restrict__ text, l
 // image score, test_last.py:90-92 at the well-posed level: ((det[b,:] @ text[(b),:,1]) + 1) / 2
 __global__ void image_score_kernel(const float* __restrict__ det, const float* __restrict__ text,
                                    long long text_bstride, float* __restrict__ score, int B, int E) {
+  ptx::pdl_trigger();
+  ptx::pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= B) return;
@@ -421,6 +441,8 @@ __device__ __forceinline__ int reflect_idx(int i, int n) {
 
 __global__ void anomaly_map_kernel(const float* __restrict__ s, float* __restrict__ out, int L, int G, int S,
                                    int test_mode, int ksize, MapTaps taps) {
+  ptx::pdl_trigger();
+  ptx::pdl_wait();
   extern __shared__ float sm[];
   const int P = G * G;
   float* g0 = sm;            // test: summed blurred grid ; train: channel 0
@@ -511,6 +533,8 @@ namespace aaclip {
 // grid = n_sent * ctx rows, block = D/4 threads (float4 each). Out-of-vocabulary ids are clamped.
 __global__ void text_embed_kernel(const int32_t* __restrict__ ids, const float* __restrict__ tok_emb,
                                   const float* __restrict__ pos, float* __restrict__ x, int ctx, int D, int vocab) {
+  ptx::pdl_trigger();
+  ptx::pdl_wait();
   const int row = blockIdx.x;
   const int t = row % ctx;
   const int id = min(max(ids[row], 0), vocab - 1);
@@ -527,6 +551,8 @@ __global__ void text_embed_kernel(const int32_t* __restrict__ ids, const float* 
 // maximum), model/adapter.py:298. ln_final is row-wise, so it is applied after this gather on n_sent rows only.
 __global__ void text_gather_eot_kernel(const int32_t* __restrict__ ids, const float* __restrict__ x,
                                        float* __restrict__ out, int ctx, int D) {
+  ptx::pdl_trigger();
+  ptx::pdl_wait();
   const int s = blockIdx.x;
   __shared__ int s_best;
   if (threadIdx.x < 32) {

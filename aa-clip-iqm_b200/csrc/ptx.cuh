@@ -38,6 +38,20 @@ __device__ __forceinline__ void prefetch_l2(const void* p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
+// ------------------------------------------------------------------ programmatic dependent launch
+// Every kernel of the step is launched with cudaLaunchAttributeProgrammaticStreamSerialization (launch_pdl in
+// aaclip_api.cu): its CTAs may become resident while the previous kernel of the stream is still draining, run their
+// prologue (barrier init, TMEM allocation, tensor-map prefetch) and then block in pdl_wait() until every CTA of the
+// previous kernel has exited and its memory is visible. pdl_trigger() lets the NEXT kernel do the same once every CTA
+// of this grid has issued it. Both are no-ops in a kernel launched without the attribute.
+// Rule: no global-memory access (read OR write) before pdl_wait().
+__device__ __forceinline__ void pdl_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_trigger() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 // ------------------------------------------------------------------ mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));

@@ -1,24 +1,35 @@
-"""Mirror of the reference's ``AdaptedCLIP`` (model/adapter.py:10-304) for inference: same constructor arguments,
-sub-module names and state_dict keys (``image_adapter.{layer_adapters,seg_proj,det_proj}``, ``text_adapter``,
-``clipmodel``, ``image_encoder``), same ``forward`` / ``encode_text`` signatures and return values -- so that the
-reference's evaluation loop (test_last.get_predictions, test_last.py:53-158) and its checkpoint loading
-(test_last.py:231-247) run unchanged against this class -- with every tensor-core contraction and fused op executed
-by libaaclip_b200.so (sm_100a) through the C ABI.
+"""Mirror of the reference's ``AdaptedCLIP`` (model/adapter.py:10-304): same constructor arguments, sub-module names
+and state_dict keys (``image_adapter.{layer_adapters,seg_proj,det_proj}``, ``text_adapter``, ``iqm``,
+``class_query_mlp``, ``query_adapters``, ``clipmodel``, ``image_encoder`` ...), same ``forward`` / ``encode_text`` /
+``forward_original`` signatures and return values -- so that the reference's evaluation loop
+(test_last.get_predictions, test_last.py:53-158), its checkpoint loading (test_last.py:231-247) and its training steps
+(train.py:150,219) run against this class.
 
-What is NOT here: the IQM Q-Former branch (random, un-checkpointed weights at test time) -- its two
-inputs are exported instead and an optional user callable ``iqm_branch`` may consume them -- and the training path.
-There is no PyTorch / CPU fallback: without a CUDA sm_100a device or the built library, forward raises.
+Where the work happens:
+  * inference (``torch.no_grad()``, or nothing requires grad): the adapted visual tower, the adapted text tower and
+    every fused op run in libaaclip_b200.so (sm_100a) through the C ABI. There is NO PyTorch / CPU fallback on this
+    route: without a CUDA sm_100a device or the built library it raises.
+  * the fork's IQM branch (model/adapter.py:186-269) is host-side PyTorch on the tensors the
+    engine exports (ln_post'ed tokens of the four levels, the final CLS row). Its weights are random at test time in
+    the reference too (they are never checkpointed).
+  * training (autograd enabled and some parameter requires grad): plain PyTorch ops on the same parameters
+    (model/torch_path.py) -- the route train.py needs; section 8f rank 4 lists native training kernels as future work.
 """
 from __future__ import annotations
 
-from typing import Callable, List, Optional
+import math
+from types import SimpleNamespace
+from typing import List, Optional
 
 import torch
+import torch.nn.functional as F
 from torch import nn
 
 from .. import _lib
 from .. import engine as _engine
+from . import torch_path as _tp
 from .adapter_modules import SimpleAdapter, SimpleProj
+from .iqm import IQM, IQMConfig
 
 
 class AdaptedCLIP(nn.Module):
@@ -45,56 +56,82 @@ class AdaptedCLIP(nn.Module):
         })
         self.text_adapter = nn.ModuleList([SimpleAdapter(Wt, Wt) for _ in range(text_adapt_until)]
                                           + [SimpleProj(Wt, Wt, relu=True)])
-        for mod in (self.image_adapter, self.text_adapter):          # model/adapter.py:107-113
-            for p in mod.parameters():
+        # ---- IQM branch (model/adapter.py:56-96)
+        self.iqm_config = IQMConfig(hidden_size=iqm_hidden_size, num_hidden_layers=iqm_num_layers,
+                                    num_attention_heads=iqm_num_heads, encoder_hidden_size=iqm_hidden_size,
+                                    text_encoder_hidden_size=768)
+        self.iqm = IQM(self.iqm_config)
+        self.class_query_mlp = nn.Sequential(nn.Linear(W, iqm_hidden_size), nn.ReLU(),
+                                             nn.Linear(iqm_hidden_size, iqm_hidden_size))
+        self.query_adapters = nn.ModuleList([SimpleProj(W, iqm_hidden_size, relu) for _ in range(len(levels))])
+        self.iqm_hidden_size = iqm_hidden_size
+        self.visual_feature_proj = None       # created on first use, like the reference (model/adapter.py:215-218)
+        self.text_feature_proj = None         # (model/adapter.py:242-243)
+        self.pos_embedding = nn.Parameter(_sinusoid(512, iqm_hidden_size))
+        self.visual_weight = nn.Parameter(torch.tensor(0.6))    # held for the key set; the reference computes the
+        self.text_weight = nn.Parameter(torch.tensor(0.4))      # normalised pair and never uses it (adapter.py:236-244)
+        self.iqm_dropout = nn.Dropout(0.1)
+        self.iqm_layer_norm = nn.LayerNorm(iqm_hidden_size)
+        for mod in (self.image_adapter, self.text_adapter, self.iqm, self.class_query_mlp, self.query_adapters):
+            for p in mod.parameters():                                # model/adapter.py:107-123
                 if p.dim() > 1:
                     nn.init.xavier_uniform_(p)
-        # IQM branch: hyper-parameters kept for signature compatibility; see module docstring
-        self.iqm_hidden_size = iqm_hidden_size
-        self.iqm_num_layers, self.iqm_num_heads = iqm_num_layers, iqm_num_heads
-        self.iqm_branch: Optional[Callable] = None   # callable(tokens[4x[B,P,W]], cls[B,W], text_embeddings) -> outputs
         self._operand_dtype, self._max_batch = operand_dtype, max_batch
         self._vis: Optional[_engine.AaclipEngine] = None
         self._txt: Optional[_engine.AaclipTextEngine] = None
         self._vis_stamp = self._txt_stamp = None
+        self._vis_list = self._txt_list = None      # cached (key, tensor) lists the stamps are taken over
 
     # ------------------------------------------------------------------------------------------ engine plumbing
     def _device(self) -> torch.device:
         return self.image_encoder.conv1.weight.device
 
-    @staticmethod
-    def _stamp(tensors):
-        return tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in tensors)
+    def _training_route(self) -> bool:
+        """True when the call must be differentiable: autograd on and at least one parameter wants a gradient."""
+        return torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
 
-    def _check_inference(self):
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise RuntimeError("AdaptedCLIP (aaclip_b200) is the inference hot path: call it under torch.no_grad(). "
-                               "The training path (train.py) is outside this build (SURVEY.md section 8f rank 4).")
+    def _need_cuda(self):
         if self._device().type != "cuda":
-            raise RuntimeError("AdaptedCLIP (aaclip_b200) needs its parameters on a CUDA sm_100a device "
+            raise RuntimeError("AdaptedCLIP (aaclip_b200) inference needs its parameters on a CUDA sm_100a device "
                                "(model.to('cuda')); there is no CPU path")
 
-    def _visual_tensors(self):
-        sd = {"image_encoder." + k: v for k, v in self.image_encoder.state_dict().items()
-              if k != "proj" and "attn_pool" not in k}
-        sd.update({"image_adapter." + k: v for k, v in self.image_adapter.state_dict().items()})
-        return sd
+    @staticmethod
+    def _stamp(pairs):
+        return tuple((t.data_ptr(), t._version) for _, t in pairs)
 
-    def _text_tensors(self):
-        keep = ("token_embedding.", "positional_embedding", "transformer.", "ln_final.")
-        sd = {"clipmodel." + k: v for k, v in self.clipmodel.state_dict().items() if k.startswith(keep)}
-        sd.update({"text_adapter." + k: v for k, v in self.text_adapter.state_dict().items()})
-        return sd
+    def _visual_pairs(self):
+        owner = (id(self.image_encoder), id(self.image_adapter))
+        if self._vis_list is None or self._vis_list[0] != owner:
+            sd = {"image_encoder." + k: v for k, v in _tp.named(self.image_encoder).items()
+                  if k != "proj" and "attn_pool" not in k}
+            sd.update({"image_adapter." + k: v for k, v in _tp.named(self.image_adapter).items()})
+            self._vis_list = (owner, list(sd.items()))
+        return self._vis_list[1]
+
+    def _text_pairs(self):
+        owner = (id(self.clipmodel), id(self.text_adapter))
+        if self._txt_list is None or self._txt_list[0] != owner:
+            keep = ("token_embedding.", "positional_embedding", "transformer.", "ln_final.")
+            sd = {"clipmodel." + k: v for k, v in _tp.named(self.clipmodel).items() if k.startswith(keep)}
+            sd.update({"text_adapter." + k: v for k, v in _tp.named(self.text_adapter).items()})
+            self._txt_list = (owner, list(sd.items()))
+        return self._txt_list[1]
+
+    def refresh_engines(self):
+        """Forget the packed copies (call after replacing a sub-module object; in-place updates -- load_state_dict,
+        .to(), optimizer steps -- are noticed automatically through the tensors' version counters)."""
+        self._vis_list = self._txt_list = self._vis_stamp = self._txt_stamp = None
 
     def _visual_engine(self) -> _engine.AaclipEngine:
-        sd = self._visual_tensors()
-        stamp = self._stamp(sd.values())
+        pairs = self._visual_pairs()
+        stamp = self._stamp(pairs)
         if self._vis is None or stamp != self._vis_stamp:     # first call, or weights were (re)loaded / moved
+            sd = dict(pairs)
             W = self.image_encoder.conv1.weight.shape[0]
             ps = self.image_encoder.conv1.weight.shape[-1]
             n_tok = self.image_encoder.positional_embedding.shape[0]
             grid = int(round((n_tok - 1) ** 0.5))
-            layers = 1 + max(int(k.split(".")[3]) for k in sd if k.startswith("image_encoder.transformer.resblocks."))
+            layers = _tp.n_blocks(sd, "image_encoder.transformer.resblocks.")
             if self._vis is not None:
                 self._vis.close()
             self._vis = _engine.AaclipEngine(
@@ -111,11 +148,12 @@ class AdaptedCLIP(nn.Module):
         return self._vis
 
     def _text_engine(self) -> _engine.AaclipTextEngine:
-        sd = self._text_tensors()
-        stamp = self._stamp(sd.values())
+        pairs = self._text_pairs()
+        stamp = self._stamp(pairs)
         if self._txt is None or stamp != self._txt_stamp:
+            sd = dict(pairs)
             vocab, Wt = sd["clipmodel.token_embedding.weight"].shape
-            layers = 1 + max(int(k.split(".")[3]) for k in sd if k.startswith("clipmodel.transformer.resblocks."))
+            layers = _tp.n_blocks(sd, "clipmodel.transformer.resblocks.")
             if self._txt is not None:
                 self._txt.close()
             self._txt = _engine.AaclipTextEngine(
@@ -130,36 +168,95 @@ class AdaptedCLIP(nn.Module):
             self._txt_stamp = stamp
         return self._txt
 
+    # ------------------------------------------------------------------------------------------ the two routes
+    def _tower_engine(self, x: torch.Tensor, want_iqm: bool):
+        self._need_cuda()
+        eng = self._visual_engine()
+        chunks = [eng.forward(x[i:i + self._max_batch], want_tokens=want_iqm, want_cls=want_iqm)
+                  for i in range(0, x.shape[0], self._max_batch)]      # larger batches run in max_batch chunks
+        if len(chunks) == 1:
+            return chunks[0]
+        L = len(self.levels)
+        seg = [torch.cat([c[0][l] for c in chunks]) for l in range(L)]
+        det = torch.cat([c[1] for c in chunks])
+        tokens = [torch.cat([c[2][l] for c in chunks]) for l in range(L)] if want_iqm else None
+        cls = torch.cat([c[3] for c in chunks]) if want_iqm else None
+        return seg, det, tokens, cls
+
+    def _tower_autograd(self, x: torch.Tensor):
+        P = _tp.named(self.image_encoder)
+        tokens, cls = _tp.visual_tower(x, P, self.image_adapter["layer_adapters"], self.i_w, self.levels,
+                                       bool(getattr(self.clipmodel, "quick_gelu", False)))
+        seg = [F.normalize(self.image_adapter["seg_proj"][i](t), dim=-1) for i, t in enumerate(tokens)]
+        det = F.normalize(self.image_adapter["det_proj"](tokens[-1]), dim=-1).mean(1)
+        return seg, det, tokens, cls
+
+    # ------------------------------------------------------------------------------------------ IQM branch
+    def _iqm_branch(self, tokens: List[torch.Tensor], cls_feature: torch.Tensor, text_embeddings: torch.Tensor):
+        """model/adapter.py:186-269 on the tower's exports. tokens: ln_post'ed [B,P,W] per level; cls_feature: the
+        final block's CLS row [B,W] (no ln_post)."""
+        B = cls_feature.shape[0]
+        class_query = self.class_query_mlp(cls_feature).unsqueeze(1).repeat(1, 2, 1)      # normal / abnormal query
+        query_embeds = class_query + self.pos_embedding[:, :2, :].repeat(B, 1, 1)
+        visual = torch.cat([self.query_adapters[i](t) for i, t in enumerate(tokens)], dim=1)   # [B, L*P, hidden]
+        if self.visual_feature_proj is None or self.visual_feature_proj.in_features != visual.shape[-1]:
+            self.visual_feature_proj = nn.Linear(int(visual.shape[-1]), self.iqm_hidden_size).to(visual.device)
+        visual = self.visual_feature_proj(visual)
+        te = text_embeddings
+        if te.dim() == 2:                                   # [E,2] -> [B,2,E]
+            te = te.transpose(0, 1).unsqueeze(0).repeat(B, 1, 1)
+        elif te.dim() != 3:
+            te = te.unsqueeze(0).repeat(B, 1, 1)
+        # (a [B,E,2] stack, what test_last / train pass, goes in as is: 768 "tokens" of width 2 -- adapter.py:228-243)
+        if self.text_feature_proj is None or self.text_feature_proj.in_features != te.shape[-1]:
+            self.text_feature_proj = nn.Linear(int(te.shape[-1]), 768).to(te.device)
+        out = self.iqm(query_embeds=query_embeds, query_length=query_embeds.shape[1], encoder_hidden_states=visual,
+                       text_encoder_hidden_states=self.text_feature_proj(te))
+        out.last_hidden_state = self.iqm_dropout(self.iqm_layer_norm(out.last_hidden_state))
+        return out
+
     # ------------------------------------------------------------------------------------------ reference surface
     def forward(self, x, text_embeddings=None, iqm_hidden_size=None):
         """x [B,3,S,S] fp32 -> (seg_tokens: list of len(levels) x [B,P,768] unit-norm, det_token [B,768],
-        iqm_outputs). model/adapter.py:137-271. iqm_outputs is None unless `self.iqm_branch` is set (then it receives
-        the two tensors the reference's IQM branch consumes: ln_post'ed tokens per level and the final CLS row)."""
-        self._check_inference()
-        eng = self._visual_engine()
-        want_iqm = text_embeddings is not None and self.iqm_branch is not None
-        outs_seg, outs_det, outs_tok, outs_cls = [], [], [], []
-        for i in range(0, x.shape[0], self._max_batch):              # larger batches run in max_batch chunks
-            seg, det, tokens, cls = eng.forward(x[i:i + self._max_batch], want_tokens=want_iqm, want_cls=want_iqm)
-            outs_seg.append(seg), outs_det.append(det), outs_tok.append(tokens), outs_cls.append(cls)
-        if len(outs_seg) == 1:
-            seg, det, tokens, cls = outs_seg[0], outs_det[0], outs_tok[0], outs_cls[0]
+        iqm_outputs | None). model/adapter.py:137-271. ``iqm_outputs.last_hidden_state`` is [B,2,iqm_hidden_size]."""
+        want_iqm = text_embeddings is not None
+        if self._training_route():
+            seg, det, tokens, cls = self._tower_autograd(x)
         else:
-            seg = [torch.cat([s[l] for s in outs_seg]) for l in range(len(self.levels))]
-            det = torch.cat(outs_det)
-            tokens = [torch.cat([t[l] for t in outs_tok]) for l in range(len(self.levels))] if want_iqm else None
-            cls = torch.cat(outs_cls) if want_iqm else None
-        iqm_outputs = self.iqm_branch(tokens, cls, text_embeddings) if want_iqm else None
+            seg, det, tokens, cls = self._tower_engine(x, want_iqm)
+        iqm_outputs = self._iqm_branch(tokens, cls, text_embeddings) if want_iqm else None
         return seg, det, iqm_outputs
 
     def encode_text(self, text, adapt_text=True):
         """int token ids [n,77] -> [n,768] (un-normalised), model/adapter.py:273-304."""
         if not adapt_text:
-            raise NotImplementedError("encode_text(adapt_text=False) = the plain CLIP text tower with text_projection "
-                                      "(model/model.py:190-201): not on the AA-CLIP hot path")
-        self._check_inference()
+            return self.clipmodel.encode_text(text)
+        if self._training_route():
+            P = _tp.named(self.clipmodel)
+            eot = _tp.text_tower(text, P, list(self.text_adapter)[:self.text_adapt_until], self.t_w,
+                                 bool(getattr(self.clipmodel, "quick_gelu", False)))
+            return self.text_adapter[-1](eot)
+        self._need_cuda()
         return self._text_engine().encode_text(text)
 
     def forward_original(self, x, modality="visual"):
-        raise NotImplementedError("forward_original (un-adapted CLIP features, model/adapter.py:125-135) is only used "
-                                  "by the training script and is outside the inference hot path")
+        """Un-adapted CLIP features (model/adapter.py:125-135; training script only)."""
+        if modality != "visual":
+            raise ValueError("modality must be visual")
+        cls_features, patch_features = self.clipmodel.encode_image(x, [24])
+        patch_features = [t[:, 1:] for t in patch_features]
+        ln = self.clipmodel.visual
+        W = patch_features[0].shape[-1]
+        patch_features = [F.layer_norm(t, (W,), ln.ln_post.weight, ln.ln_post.bias, 1e-5) @ ln.proj
+                          for t in patch_features]
+        return patch_features, cls_features
+
+
+def _sinusoid(max_len: int, d_model: int) -> torch.Tensor:
+    """[1, max_len, d_model] sine / cosine table (model/adapter.py:98-105)."""
+    pos = torch.arange(max_len).unsqueeze(1)
+    freq = torch.exp(torch.arange(0, d_model, 2) * (-math.log(10000.0) / d_model))
+    pe = torch.zeros(max_len, d_model)
+    pe[:, 0::2] = torch.sin(pos * freq)
+    pe[:, 1::2] = torch.cos(pos * freq)
+    return pe.unsqueeze(0)

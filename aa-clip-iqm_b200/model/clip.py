@@ -3,9 +3,10 @@
 ``create_model`` returns a ``ClipWeights`` object: an ``nn.Module`` that HOLDS the CLIP parameters under the
 reference's state_dict keys (``visual.conv1.weight``, ``visual.transformer.resblocks.<i>.attn.in_proj_weight``,
 ``transformer.resblocks.<i>...``, ``token_embedding.weight``, ``ln_final.weight`` ...) and exposes the attributes the
-callers read (``.visual``, ``.visual.image_size / grid_size``, ``.context_length``, ``.vocab_size``). It contains no
-forward code: the towers run inside the sm_100a engine (AdaptedCLIP). A reference ``CLIP`` instance can be passed to
-AdaptedCLIP instead -- only ``state_dict()`` and those attributes are used.
+callers read (``.visual``, ``.visual.image_size / grid_size``, ``.context_length``, ``.vocab_size``). The adapted towers
+run inside the sm_100a engine (AdaptedCLIP); ``encode_image`` / ``encode_text`` (the UN-adapted CLIP towers, used by
+the reference's scripts outside the hot path) are plain PyTorch ops on the held parameters. A reference ``CLIP``
+instance can be passed to AdaptedCLIP instead -- only its parameters and those attributes are used.
 """
 from __future__ import annotations
 
@@ -109,10 +110,23 @@ class ClipWeights(nn.Module):
         self.vocab_size = t["vocab_size"]
 
     def forward(self, *a, **k):
-        raise RuntimeError("ClipWeights only holds parameters; wrap it in AdaptedCLIP (sm_100a engine). "
-                           "There is no PyTorch forward.")
+        raise RuntimeError("ClipWeights holds the CLIP parameters for AdaptedCLIP (sm_100a engine); the joint "
+                           "image/text forward of the reference's CLIP class is not part of the hot path.")
 
-    encode_image = encode_text = forward
+    # The two un-adapted CLIP entry points the reference's scripts call OUTSIDE the hot path: train.py stage 1 and
+    # forward_original (encode_image), test_last.py:264-271 without a text-adapter checkpoint (encode_text). Plain
+    # PyTorch ops on these parameters (model/torch_path.py); differentiable.
+    def encode_image(self, image, out_layers, normalize: bool = False):
+        """(ln_post(CLS) @ proj [B,E], [tokens [B,N,W] after block l for l in out_layers]) -- model/model.py:185-188."""
+        from . import torch_path as tp
+        pooled, tokens = tp.clip_encode_image(image, tp.named(self.visual), list(out_layers), self.quick_gelu)
+        return (F.normalize(pooled, dim=-1) if normalize else pooled), tokens
+
+    def encode_text(self, text, normalize: bool = False):
+        """token ids [n,77] -> ln_final(EOT row) @ text_projection [n,E] -- model/model.py:190-201."""
+        from . import torch_path as tp
+        x = tp.text_tower(text, tp.named(self), (), 0.0, self.quick_gelu) @ self.text_projection
+        return F.normalize(x, dim=-1) if normalize else x
 
 
 def resize_pos_embed(state_dict: Dict[str, torch.Tensor], model, interpolation: str = "bicubic",

@@ -119,3 +119,39 @@ def make_images(seed: int, batch: int, img_size: int, first_index: int = 0) -> t
         g.manual_seed(1_000_000 * seed + 1000 + first_index + i)
         out[i] = torch.randn(3, img_size, img_size, generator=g, dtype=torch.float32)
     return out
+
+
+IQM_BRANCH_MODULES = ("iqm", "class_query_mlp", "query_adapters", "iqm_layer_norm", "visual_feature_proj",
+                      "text_feature_proj")
+
+
+def fill_iqm_branch_(model, seed: int = 0, n_levels: int = 4) -> int:
+    """Deterministic weights for the IQM branch of an ``AdaptedCLIP`` -- the reference's class or this repository's
+    mirror: both expose the same sub-modules under the same parameter names (model/adapter.py:56-96). The two layers
+    the reference creates lazily on its first forward (``visual_feature_proj`` Linear(hidden, hidden),
+    ``text_feature_proj`` Linear(2, 768), model/adapter.py:215-218,242-243) are created here, so that both sides run
+    the same tensors. Parameters are filled in sorted-name order from one CPU generator: the same seed gives the same
+    tensors in the build container (golden generation with the reference) and on the GPU box. Returns the count."""
+    import torch.nn as nn
+    hidden = model.iqm_hidden_size
+    dev = next(model.iqm.parameters()).device
+    if model.visual_feature_proj is None:
+        model.visual_feature_proj = nn.Linear(hidden, hidden).to(dev)
+    if model.text_feature_proj is None:
+        model.text_feature_proj = nn.Linear(2, 768).to(dev)
+    g = torch.Generator(device="cpu")
+    g.manual_seed(1000003 * seed + 41)
+    n = 0
+    with torch.no_grad():
+        for mod_name in IQM_BRANCH_MODULES:
+            mod = getattr(model, mod_name)
+            for name, p in sorted(mod.named_parameters(), key=lambda kv: kv[0]):
+                if p.dim() >= 2:
+                    t = torch.randn(p.shape, generator=g) * (p.shape[-1] ** -0.5)
+                elif name.endswith("LayerNorm.weight") or name in ("weight",) or name.endswith("layernorm.weight"):
+                    t = torch.randn(p.shape, generator=g) * 0.1 + 1.0
+                else:
+                    t = torch.randn(p.shape, generator=g) * 0.05
+                p.copy_(t.to(p.device))
+                n += 1
+    return n

@@ -23,6 +23,20 @@ def install():
             sys.path.remove(p)
     sys.path.insert(0, REF_ROOT)
     sys.path.insert(0, SHIM)
+    # the repository root carries shim modules under the reference's import names (model/, dataset/, forward_utils.py,
+    # utils.py): make sure `import model` below resolves to the REFERENCE, also if a shim was imported earlier
+    for name in list(sys.modules):
+        if name.split(".")[0] in ("model", "dataset", "forward_utils", "utils"):
+            f = getattr(sys.modules[name], "__file__", "") or ""
+            if not f.startswith(REF_ROOT):
+                del sys.modules[name]
+    # the reference's model/ directory has no __init__.py (a namespace package), and a REGULAR package of the same name
+    # later on sys.path (our shim) would win over it whatever the path order: bind the name to the reference explicitly
+    if "model" not in sys.modules:
+        import types
+        pkg = types.ModuleType("model")
+        pkg.__path__ = [os.path.join(REF_ROOT, "model")]
+        sys.modules["model"] = pkg
     import transformers.modeling_utils as mu
     import transformers.pytorch_utils as pu
 

@@ -25,7 +25,9 @@ def test_state_dict_keys_and_shapes_match_reference(clip224, relu):
     ref = json.load(open(os.path.join(REPO, "tests", "golden", "ref_state_dict_keys.json")))["relu" if relu else "norelu"]
     m = model.AdaptedCLIP(clip224, relu=relu, iqm_hidden_size=512)
     ours = {k: list(v.shape) for k, v in m.state_dict().items()}
-    # non-persistent buffers / IQM excluded by construction of the fixture; every reference key must exist here
+    # the fixture holds EVERY key of the reference's AdaptedCLIP.state_dict() (CLIP towers, adapters, the IQM branch:
+    # iqm.*, class_query_mlp.*, query_adapters.*, pos_embedding, visual_weight, text_weight, iqm_layer_norm.*)
+    assert len(ref) == 856
     missing = [k for k in ref if k not in ours]
     assert not missing, missing[:5]
     assert all(ours[k] == ref[k] for k in ref), [k for k in ref if ours[k] != ref[k]][:5]
@@ -102,10 +104,14 @@ def test_no_cpu_or_pytorch_fallback(clip224):
             m(x)
         with pytest.raises(RuntimeError, match="CUDA"):
             m.encode_text(torch.zeros(1, 77, dtype=torch.int32))
-    with pytest.raises(RuntimeError, match="weights"):
-        m.image_adapter["det_proj"](torch.zeros(1, 1024))
     with pytest.raises(RuntimeError, match="ClipWeights"):
         clip224(x)
+    from aaclip_b200 import engine, forward_utils as fu
+    with pytest.raises(RuntimeError, match="CUDA"):       # scoring under no_grad = engine route: no torch fallback
+        with torch.no_grad():
+            fu.calculate_similarity_map(torch.zeros(1, 1369, 768), torch.zeros(768, 2), 518, test=True)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        engine.text_anchors(torch.zeros(16, 768), [6, 10])
 
 
 def test_metrics_eval_semantics():

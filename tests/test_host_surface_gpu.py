@@ -37,7 +37,7 @@ def test_get_predictions_style_loop_matches_reference(name):
         # --- the body of test_last.get_predictions (no-IQM branch), verbatim in structure
         epoch_text_feature = class_text_embeddings.unsqueeze(0).repeat(image.size(0), 1, 1)
         patch_features, det_feature, iqm_outputs = model(image, text_embeddings=epoch_text_feature)
-        assert iqm_outputs is None
+        assert tuple(iqm_outputs.last_hidden_state.shape) == (B, 2, 512)      # the IQM branch ran (text given)
         text_anomaly_maps = [fu.calculate_similarity_map(f, epoch_text_feature, S, test=True, domain="Industrial")
                              for f in patch_features]
         final_map = torch.cat(text_anomaly_maps, dim=1).sum(1)
@@ -63,7 +63,10 @@ def test_text_embedding_surface_matches_reference():
     tokens, sizes = torch.from_numpy(fx["tokens"]), fx["sizes"].tolist()
     reals = {"carpet": "gray carpet", "pill": "oval white pill with small red speckles and the letters 'FF' engraved",
              "pcb1": "dual ultrasonic distance sensor pcb module"}   # dataset/constants.py REAL_NAMES of the fixture's classes
-    # stand-in for the reference BPE tokenizer (out of scope): replays the ids the reference tokenizer produced
+    # the built-in BPE tokenizer must reproduce the ids the reference tokenizer produced for these 48 sentences
+    from aaclip_b200 import constants, tokenizer
+    sentences = [s for c in reals.values() for g in constants.class_prompts(c) for s in g]
+    assert torch.equal(tokenizer.tokenize(sentences), tokens.to(torch.int32))
     cursor = {"i": 0}
 
     def replay_tokenize(sentences):
@@ -81,13 +84,81 @@ def test_text_embedding_surface_matches_reference():
         assert list(all_) == list(reals)
         for i, c in enumerate(reals):
             assert np.abs(all_[c].cpu().numpy() - fx["anchors"][i]).max() < 2e-3
-        with pytest.raises(NotImplementedError):
-            model.encode_text(tokens[:1].cuda(), adapt_text=False)
+        # default tokenizer + REAL_NAMES lookup (no overrides): same anchors
+        a1 = fu.get_adapted_single_class_text_embedding(model, "VisA", "pcb1", "cuda")
+        assert np.abs(a1.cpu().numpy() - fx["anchors"][2]).max() < 2e-3
+        # the un-adapted CLIP text tower (test_last.py:264-271 without a text-adapter checkpoint): host PyTorch
+        plain = model.encode_text(tokens[:2].cuda(), adapt_text=False)
+        assert plain.shape == (2, 768) and torch.isfinite(plain).all()
 
 
-def test_grad_mode_is_rejected():
+def test_grad_mode_takes_the_autograd_route():
+    """train.py:150 calls the model with autograd on: the plain-PyTorch route must agree with the engine route
+    (same parameters) and produce gradients for the adapters."""
+    from aaclip_b200 import weights
     model = _model(224, False, 1)
+    x = weights.make_images(1, 1, 224).to("cuda")
+    with torch.no_grad():
+        seg_e, det_e, _ = model(x)
     for p in model.image_adapter.parameters():
         p.requires_grad_(True)
-    with pytest.raises(RuntimeError, match="no_grad"):
-        model(torch.zeros(1, 3, 224, 224, device="cuda"))
+    seg_t, det_t, _ = model(x)
+    assert det_t.requires_grad
+    assert (det_t - det_e).abs().max().item() < 2e-3 and (seg_t[3] - seg_e[3]).abs().max().item() < 2e-2
+    det_t.sum().backward()
+    g = model.image_adapter["layer_adapters"][0].fc[0].weight.grad
+    assert g is not None and torch.isfinite(g).all() and g.abs().max().item() > 0
+
+
+@pytest.mark.parametrize("name", ["iqm_224_h768", "iqm_224_h512"])
+def test_get_predictions_with_iqm_matches_reference(name):
+    """The body of the reference's evaluation loop, test_last.get_predictions (test_last.py:70-151), IQM branch
+    included, against what the unmodified reference produced for the same seeded weights and batch
+    (oracle/gen_golden_iqm.py): the fused 0.6 * text + 0.4 * IQM maps and the fork's [B,2] image predictions."""
+    import torch.nn as nn
+    import torch.nn.functional as F
+    from aaclip_b200 import forward_utils as fu
+    from aaclip_b200 import model as M
+    from aaclip_b200 import weights
+    fx = golden(name)
+    S, B, seed, hidden = int(fx["img_size"]), int(fx["batch"]), int(fx["seed"]), int(fx["hidden"])
+    clip = M.create_model("ViT-L-14-336", S, pretrained=None, force_image_size=S, device="cuda")
+    model = M.AdaptedCLIP(clip_model=clip, relu=False, iqm_hidden_size=hidden, iqm_num_layers=2, iqm_num_heads=8).to("cuda")
+    model.eval()
+    missing, unexpected = model.load_state_dict(weights.make_visual_state_dict(seed=seed, img_size=S), strict=False)
+    assert not unexpected
+    assert weights.fill_iqm_branch_(model, seed) == int(fx["n_iqm_params"])
+    device, img_size = "cuda", S
+    class_text_embeddings = weights.make_text_anchor(seed).to(device)
+    iqm_weight, text_weight = 0.4, 0.6
+    with torch.no_grad():
+        torch.manual_seed(1234)
+        image = weights.make_images(seed, B, S).to(device)
+        epoch_text_feature = class_text_embeddings.unsqueeze(0).repeat(image.size(0), 1, 1)
+        patch_features, det_feature, iqm_outputs = model(image, text_embeddings=epoch_text_feature)
+        pred = det_feature @ epoch_text_feature
+        pred = (pred[:, 1] + 1) / 2
+        text_anomaly_maps = [fu.calculate_similarity_map(f, epoch_text_feature, img_size, test=True, domain="Industrial")
+                             for f in patch_features]
+        iqm_anomaly_maps = []
+        final_query_embedding = iqm_outputs.last_hidden_state
+        norm_query, abnorm_query = final_query_embedding[:, 0, :], final_query_embedding[:, 1, :]
+        for f in patch_features:
+            if norm_query.shape[-1] != f.shape[-1]:
+                proj_layer = nn.Linear(norm_query.shape[-1], f.shape[-1]).to(f.device)   # seeded CPU init, as the reference
+                norm_query, abnorm_query = proj_layer(norm_query), proj_layer(abnorm_query)
+            norm_sim = F.cosine_similarity(f, norm_query.unsqueeze(1), dim=-1)
+            abnorm_sim = F.cosine_similarity(f, abnorm_query.unsqueeze(1), dim=-1)
+            iqm_pred = torch.sigmoid(abnorm_sim - norm_sim)
+            Bq, L = iqm_pred.shape
+            H = int(L ** 0.5)
+            iqm_pred = F.interpolate(iqm_pred.view(Bq, 1, H, H), size=(img_size, img_size), mode="bilinear",
+                                     align_corners=False)
+            iqm_anomaly_maps.append(iqm_pred)
+        text_map = torch.cat(text_anomaly_maps, dim=1).sum(1, keepdim=True)
+        iqm_map = torch.cat(iqm_anomaly_maps, dim=1).sum(1, keepdim=True)
+        final_map = text_map * text_weight + iqm_map * iqm_weight
+    assert final_map.shape == (B, 1, S, S) and pred.shape == (B, 2)
+    assert np.abs(iqm_outputs.last_hidden_state.cpu().numpy() - fx["iqm_last_hidden"]).max() < 2e-2
+    assert np.abs(final_map.cpu().numpy() - fx["preds"]).max() < 1e-2      # north_star map tolerance, fused map
+    assert np.abs(pred.cpu().numpy() - fx["preds_image"]).max() < 1e-3
