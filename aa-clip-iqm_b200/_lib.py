@@ -153,6 +153,14 @@ def _declare(lib):
     lib.aaclip_last_launch_count.argtypes = [vp]
     lib.aaclip_stat_columns.restype = i32
     lib.aaclip_stat_columns.argtypes = []
+    u64p = ctypes.POINTER(ctypes.c_uint64)
+    for pre in ("aaclip_", "aaclip_text_"):
+        f = getattr(lib, pre + "finalize_weights")
+        f.restype, f.argtypes = i32, [vp, vp]
+        f = getattr(lib, pre + "saturation_check")
+        f.restype, f.argtypes = i32, [vp, i32]
+        f = getattr(lib, pre + "saturation_count")
+        f.restype, f.argtypes = i32, [vp, u64p, i32, vp]
     lib.aaclip_profile_enable.restype = i32
     lib.aaclip_profile_enable.argtypes = [vp, i32]
     lib.aaclip_profile_read.restype = i32
@@ -216,6 +224,8 @@ EXPORTED_SYMBOLS = [
     "aaclip_text_create", "aaclip_text_destroy", "aaclip_text_set_weight", "aaclip_text_missing_weights",
     "aaclip_text_workspace_bytes", "aaclip_encode_text", "aaclip_text_anchors",
     "aaclip_resample_ksize", "aaclip_resample_coeffs_host", "aaclip_preprocess_workspace_bytes", "aaclip_preprocess_u8",
+    "aaclip_finalize_weights", "aaclip_saturation_check", "aaclip_saturation_count",
+    "aaclip_text_finalize_weights", "aaclip_text_saturation_check", "aaclip_text_saturation_count",
 ]
 
 

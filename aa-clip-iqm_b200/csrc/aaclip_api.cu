@@ -509,6 +509,8 @@ struct AaclipHandle {
   uint16_t* w_det;                   // [E,W]
   std::vector<std::string> missing;
   int last_launches = 0;
+  unsigned long long* sat_counter = nullptr;   // device counter of aaclip_saturation_check (cudaMalloc'ed at create)
+  bool sat_on = false;
   // optional per-kernel-class device timing (aaclip_profile_*)
   struct ProfRec { int cls; double flops; cudaEvent_t a, b; };
   bool prof_on = false;
@@ -542,8 +544,25 @@ namespace {
 // One residual attention block (+ optional residual adapter), model/transformer.py:239-258 + model/adapter.py:163-170.
 //   x, x16, stats hold the residual stream on entry (fp32, raw 16-bit copy, LayerNorm partials) and on exit.
 // 5 launches (7 with an adapter): LayerNorms live in the GEMM epilogues.
+// aaclip_saturation_check: after every kernel that stores 16-bit activations, count the stored elements that sit at the
+// format's ceiling (elementwise.cuh: count_saturated16_kernel). Off by default: zero cost on the hot path.
+struct SatCheck {
+  unsigned long long* counter = nullptr;   // device counter, nullptr = disabled
+  bool bf16 = false;
+  int launches = 0;
+  void scan(const void* p, size_t n, cudaStream_t st) {
+    if (counter == nullptr || n == 0) return;
+    const size_t n8 = n / 8;
+    const unsigned grid = static_cast<unsigned>(n8 / 256 + 1 < 148 * 8 ? n8 / 256 + 1 : 148 * 8);
+    if (bf16) launch_pdl(count_saturated16_kernel<true>, dim3(grid), dim3(256), 0, st, static_cast<const uint16_t*>(p), n8, counter);
+    else launch_pdl(count_saturated16_kernel<false>, dim3(grid), dim3(256), 0, st, static_cast<const uint16_t*>(p), n8, counter);
+    ++launches;
+  }
+};
+
 struct BlockRun {
   AaclipHandle* prof;     // profiling sink (visual handle) or nullptr
+  SatCheck sat;
   bool bf16;
   int items, tokens, W, F, causal, act;
   float* x; uint16_t* x16; uint16_t* qkv; uint16_t* att; uint16_t* hid; float* abuf; float* stats;
@@ -562,18 +581,23 @@ struct BlockRun {
     { GemmEpi e; e.bias = b.bf_qkv; e.colsum = b.cs_qkv; e.stats = stats; e.n_partials = np; e.inv_width = 1.0f / W;
       e.out_16 = qkv; e.ldo = 3 * W;
       if ((rc = gemm(EPI_LN_BIAS_BF16, x16, b.w_qkv, M, 3 * W, W, e, AACLIP_PROF_GEMM_QKV))) return rc; }
+    sat.scan(qkv, static_cast<size_t>(M) * 3 * W, st);
     {
       ProfScope ps(prof, AACLIP_PROF_ATTENTION, 4.0 * items * (W / 64) * (double)tokens * tokens * 64, st);
       ++launches;
       if ((rc = launch_attention(bf16, qkv, att, items, tokens, W, causal, st))) return rc;
     }
+    sat.scan(att, static_cast<size_t>(M) * W, st);
     { GemmEpi e; e.bias = b.b_out; e.out_f32 = x; e.out_16 = x16; e.stats_out = stats; e.ldo = W;
       if ((rc = gemm(EPI_BIAS_RESID_F32, att, b.w_out, M, W, W, e, AACLIP_PROF_GEMM_OUT))) return rc; }
+    sat.scan(x16, static_cast<size_t>(M) * W, st);
     { GemmEpi e; e.bias = b.bf_fc; e.colsum = b.cs_fc; e.stats = stats; e.n_partials = np; e.inv_width = 1.0f / W;
       e.out_16 = hid; e.ldo = F;
       if ((rc = gemm(act == AACLIP_ACT_QUICK_GELU ? EPI_LN_BIAS_QGELU_BF16 : EPI_LN_BIAS_GELU_BF16, x16, b.w_fc, M, F, W, e, AACLIP_PROF_GEMM_FC))) return rc; }
+    sat.scan(hid, static_cast<size_t>(M) * F, st);
     { GemmEpi e; e.bias = b.b_proj; e.out_f32 = x; e.out_16 = x16; e.stats_out = stats; e.ldo = W;
       if ((rc = gemm(EPI_BIAS_RESID_F32, hid, b.w_proj, M, W, F, e, AACLIP_PROF_GEMM_PROJ))) return rc; }
+    sat.scan(x16, static_cast<size_t>(M) * W, st);
     if (w_adapter != nullptr) {
       { GemmEpi e; e.out_f32 = abuf; e.ldo = W;
         if ((rc = gemm(EPI_LEAKY_F32, x16, w_adapter, M, W, W, e))) return rc; }
@@ -589,6 +613,7 @@ struct BlockRun {
       }
       LAUNCH_CHECK("adapter_blend_kernel");
       ++launches;
+      sat.scan(x16, static_cast<size_t>(M) * W, st);
     }
     return AACLIP_OK;
   }
@@ -701,6 +726,7 @@ int aaclip_create(const AaclipCfg* cfg, AaclipHandle** out) {
   for (int i = 0; i < c.adapt_until; ++i) o_ad[i] = plan.take<uint8_t>(W * W * wb);
   for (int l = 0; l < c.n_levels; ++l) o_seg[l] = plan.take<uint8_t>(E * W * wb);
   const size_t o_det = plan.take<uint8_t>(E * W * wb);
+  const size_t o_sat = plan.take<unsigned long long>(1);
 
   h->arena_bytes = plan.off;
   cudaError_t e = cudaMalloc(&h->arena, h->arena_bytes);
@@ -724,6 +750,7 @@ int aaclip_create(const AaclipCfg* cfg, AaclipHandle** out) {
   for (int i = 0; i < c.adapt_until; ++i) h->w_adapter.push_back((uint16_t*)(a + o_ad[i]));
   for (int l = 0; l < c.n_levels; ++l) h->w_seg.push_back((uint16_t*)(a + o_seg[l]));
   h->w_det = (uint16_t*)(a + o_det);
+  h->sat_counter = (unsigned long long*)(a + o_sat);      // zeroed with the arena
 
   // the set of tensors that must arrive through aaclip_set_weight before forward may run
   auto need = [&](const std::string& k) { h->missing.push_back(k); };
@@ -917,10 +944,10 @@ int aaclip_forward(AaclipHandle* h, const float* images, int32_t B, void* worksp
   const int M = B * N, MP = B * P;
   int rc;
   if (h->f32) return forward_f32(h, images, B, static_cast<uint8_t*>(workspace), ws, seg_out, det_out, tokens_out, cls_out, st);
-  if (!h->folded) {      // first forward: fold ln_1 / ln_2 into the in_proj / c_fc weights (load-time work)
-    if ((rc = fold_blocks(h->blk, h->bf16, W, F, st))) return rc;
-    h->folded = true;
-  }
+  // LayerNorm folding is load-time work (kernels + a synchronisation + cudaFree of the staging copies): callers that
+  // want a capture-safe, non-blocking first forward call aaclip_finalize_weights() after the last aaclip_set_weight();
+  // otherwise it happens here, once.
+  if ((rc = aaclip_finalize_weights(h, stream))) return rc;
   uint8_t* wsb = static_cast<uint8_t*>(workspace);
   uint16_t* patchA = (uint16_t*)(wsb + ws.patchA);
   uint16_t* tok = (uint16_t*)(wsb + ws.tok);
@@ -931,6 +958,7 @@ int aaclip_forward(AaclipHandle* h, const float* images, int32_t B, void* worksp
   run.x = (float*)(wsb + ws.core.x); run.x16 = (uint16_t*)(wsb + ws.core.x16); run.qkv = (uint16_t*)(wsb + ws.core.qkv);
   run.att = (uint16_t*)(wsb + ws.core.att); run.hid = (uint16_t*)(wsb + ws.core.hid);
   run.abuf = (float*)(wsb + ws.core.abuf); run.stats = (float*)(wsb + ws.core.stats); run.st = st;
+  if (h->sat_on) { run.sat.counter = h->sat_counter; run.sat.bf16 = bf; }
   float* x = run.x;
   int& launches = run.launches;
 
@@ -970,6 +998,7 @@ int aaclip_forward(AaclipHandle* h, const float* images, int32_t B, void* worksp
       else launch_pdl(patch_gather_simple_kernel<false>, dim3(h->G, B), dim3(256), 0, st, images, patchA, c.img_size, h->G, c.patch, h->KP);
     }
     LAUNCH_CHECK("patch_gather_kernel"); ++launches;
+    run.sat.scan(patchA, static_cast<size_t>(MP) * h->KP, st);
   }
   {
     GemmEpi e; e.out_f32 = x; e.ldo = W; e.pos = h->pos; e.patches = P;
@@ -982,6 +1011,7 @@ int aaclip_forward(AaclipHandle* h, const float* images, int32_t B, void* worksp
   }
   // ln_pre in place; also emits the 16-bit copy and the LayerNorm partials block 0's folded ln_1 needs
   if ((rc = lnorm(x, h->lnpre_g, h->lnpre_b, run.x16, x, M, 0, run.stats))) return rc;
+  run.sat.scan(run.x16, static_cast<size_t>(M) * W, st);
 
   // ---- residual attention blocks (model/transformer.py:239-258) + adapters (model/adapter.py:161-172)
   int level_idx = 0;
@@ -990,6 +1020,7 @@ int aaclip_forward(AaclipHandle* h, const float* images, int32_t B, void* worksp
     if (level_idx < c.n_levels && c.levels[level_idx] == i + 1) {
       float* tok_f32 = (tokens_out != nullptr) ? tokens_out[level_idx] : nullptr;
       if ((rc = lnorm(x, h->lnpost_g, h->lnpost_b, tok, tok_f32, MP, P, nullptr))) return rc;
+      run.sat.scan(tok, static_cast<size_t>(MP) * W, st);
       const int proj_epi = c.proj_relu ? EPI_LEAKY_F32 : EPI_F32;
       { GemmEpi e; e.out_f32 = seg_out[level_idx]; e.ldo = E;
         if ((rc = run.gemm(proj_epi, tok, h->w_seg[level_idx], MP, E, W, e))) return rc; }
@@ -1011,11 +1042,39 @@ int aaclip_forward(AaclipHandle* h, const float* images, int32_t B, void* worksp
     launch_pdl(gather_cls_kernel, dim3(B), dim3(256), 0, st, static_cast<const float*>(x), cls_out, N, W);
     LAUNCH_CHECK("gather_cls_kernel"); ++launches;
   }
-  h->last_launches = launches;
+  h->last_launches = launches + run.sat.launches;
   return AACLIP_OK;
 }
 
 int aaclip_last_launch_count(AaclipHandle* h) { return h ? h->last_launches : -1; }
+
+int aaclip_finalize_weights(AaclipHandle* h, void* stream) {
+  if (!h) return fail(AACLIP_EINVAL, "aaclip_finalize_weights: null handle");
+  if (h->f32 || h->folded) return AACLIP_OK;
+  if (!h->missing.empty())
+    return fail(AACLIP_ESTATE, "aaclip_finalize_weights: %zu weight tensors not set (first: %s)", h->missing.size(), h->missing[0].c_str());
+  if (int rc = fold_blocks(h->blk, h->bf16, h->cfg.width, h->cfg.mlp_dim, static_cast<cudaStream_t>(stream))) return rc;
+  h->folded = true;
+  return AACLIP_OK;
+}
+
+int aaclip_saturation_check(AaclipHandle* h, int32_t enable) {
+  if (!h) return fail(AACLIP_EINVAL, "aaclip_saturation_check: null handle");
+  if (h->f32 && enable) return fail(AACLIP_EINVAL, "aaclip_saturation_check: fp32-accuracy mode stores no 16-bit activations");
+  h->sat_on = enable != 0;
+  return AACLIP_OK;
+}
+
+int aaclip_saturation_count(AaclipHandle* h, uint64_t* count_host, int32_t reset, void* stream) {
+  if (!h || !count_host) return fail(AACLIP_EINVAL, "aaclip_saturation_count: null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  unsigned long long v = 0;
+  CUDA_TRY(cudaMemcpyAsync(&v, h->sat_counter, sizeof(v), cudaMemcpyDeviceToHost, st));
+  if (reset) CUDA_TRY(cudaMemsetAsync(h->sat_counter, 0, sizeof(v), st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  *count_host = v;
+  return AACLIP_OK;
+}
 
 int aaclip_stat_columns(void) { return kStatCols; }
 
@@ -1114,6 +1173,8 @@ struct AaclipTextHandle {
   float *tok_emb, *pos, *lnf_g, *lnf_b;
   std::vector<BlockW> blk;
   bool folded = false;
+  unsigned long long* sat_counter = nullptr;
+  bool sat_on = false;
   std::vector<uint16_t*> w_adapter;  // [W,W] each (SimpleAdapter)
   uint16_t* w_proj;                  // [E,W] final SimpleProj
   std::vector<std::string> missing;
@@ -1160,6 +1221,7 @@ int aaclip_text_create(const AaclipTextCfg* cfg, AaclipTextHandle** out) {
   std::vector<size_t> o_ad(c.adapt_until);
   for (int i = 0; i < c.adapt_until; ++i) o_ad[i] = plan.take<uint8_t>(W * W * wb);
   const size_t o_proj = plan.take<uint8_t>(E * W * wb);
+  const size_t o_sat = plan.take<unsigned long long>(1);
   h->arena_bytes = plan.off;
   cudaError_t e = cudaMalloc(&h->arena, h->arena_bytes);
   if (e == cudaSuccess) e = cudaMemset(h->arena, 0, h->arena_bytes);
@@ -1175,6 +1237,7 @@ int aaclip_text_create(const AaclipTextCfg* cfg, AaclipTextHandle** out) {
   for (int i = 0; i < c.layers; ++i) bind_block(h->blk[i], a, bo[i]);
   for (int i = 0; i < c.adapt_until; ++i) h->w_adapter.push_back((uint16_t*)(a + o_ad[i]));
   h->w_proj = (uint16_t*)(a + o_proj);
+  h->sat_counter = (unsigned long long*)(a + o_sat);
   auto need = [&](const std::string& k) { h->missing.push_back(k); };
   need("token_embedding.weight"); need("positional_embedding"); need("ln_final.weight"); need("ln_final.bias");
   for (int i = 0; i < c.layers; ++i)
@@ -1274,11 +1337,9 @@ int aaclip_encode_text(AaclipTextHandle* h, const int32_t* tokens, int32_t n, vo
     GemmEpi e; e.out_f32 = out; e.ldo = E;
     return r32.gemm(EPI_LEAKY_F32, eotn, h->w_proj, n, E, W, e);
   }
-  if (!h->folded) {
-    if ((rc = fold_blocks(h->blk, bf, W, F, st))) return rc;
-    h->folded = true;
-  }
+  if ((rc = aaclip_text_finalize_weights(h, stream))) return rc;
   BlockRun run;
+  if (h->sat_on) { run.sat.counter = h->sat_counter; run.sat.bf16 = bf; }
   run.prof = nullptr; run.bf16 = bf; run.items = n; run.tokens = T; run.W = W; run.F = F; run.causal = 1; run.act = c.act;
   run.x = (float*)(wsb + ws.core.x); run.x16 = (uint16_t*)(wsb + ws.core.x16); run.qkv = (uint16_t*)(wsb + ws.core.qkv);
   run.att = (uint16_t*)(wsb + ws.core.att); run.hid = (uint16_t*)(wsb + ws.core.hid);
@@ -1291,6 +1352,7 @@ int aaclip_encode_text(AaclipTextHandle* h, const int32_t* tokens, int32_t n, vo
   launch_pdl(text_embed_kernel, dim3(M), dim3(192), 0, st, tokens, static_cast<const float*>(h->tok_emb), static_cast<const float*>(h->pos), run.x, T, W, c.vocab);
   LAUNCH_CHECK("text_embed_kernel");
   if ((rc = launch_layernorm(bf, run.x, nullptr, nullptr, run.x16, nullptr, M, W, 0, /*normalize=*/false, st, run.stats, kStatPartials(W)))) return rc;
+  run.sat.scan(run.x16, static_cast<size_t>(M) * W, st);
   // 12 causal residual attention blocks + adapters (model/adapter.py:284-295)
   for (int i = 0; i < c.layers; ++i)
     if ((rc = run.run(h->blk[i], i < c.adapt_until ? h->w_adapter[i] : nullptr, c.adapt_weight))) return rc;
@@ -1298,8 +1360,37 @@ int aaclip_encode_text(AaclipTextHandle* h, const int32_t* tokens, int32_t n, vo
   launch_pdl(text_gather_eot_kernel, dim3(n), dim3(192), 0, st, tokens, static_cast<const float*>(run.x), eot, T, W);
   LAUNCH_CHECK("text_gather_eot_kernel");
   if ((rc = launch_layernorm(bf, eot, h->lnf_g, h->lnf_b, eot16, nullptr, n, W, 0, true, st))) return rc;
+  run.sat.scan(eot16, static_cast<size_t>(n) * W, st);
   { GemmEpi e; e.out_f32 = out; e.ldo = E;
     if ((rc = launch_gemm(EPI_LEAKY_F32, bf, eot16, h->w_proj, n, E, W, e, st))) return rc; }
+  return AACLIP_OK;
+}
+
+int aaclip_text_finalize_weights(AaclipTextHandle* h, void* stream) {
+  if (!h) return fail(AACLIP_EINVAL, "aaclip_text_finalize_weights: null handle");
+  if (h->f32 || h->folded) return AACLIP_OK;
+  if (!h->missing.empty())
+    return fail(AACLIP_ESTATE, "aaclip_text_finalize_weights: %zu weight tensors not set (first: %s)", h->missing.size(), h->missing[0].c_str());
+  if (int rc = fold_blocks(h->blk, h->bf16, h->cfg.width, h->cfg.mlp_dim, static_cast<cudaStream_t>(stream))) return rc;
+  h->folded = true;
+  return AACLIP_OK;
+}
+
+int aaclip_text_saturation_check(AaclipTextHandle* h, int32_t enable) {
+  if (!h) return fail(AACLIP_EINVAL, "aaclip_text_saturation_check: null handle");
+  if (h->f32 && enable) return fail(AACLIP_EINVAL, "aaclip_text_saturation_check: fp32-accuracy mode stores no 16-bit activations");
+  h->sat_on = enable != 0;
+  return AACLIP_OK;
+}
+
+int aaclip_text_saturation_count(AaclipTextHandle* h, uint64_t* count_host, int32_t reset, void* stream) {
+  if (!h || !count_host) return fail(AACLIP_EINVAL, "aaclip_text_saturation_count: null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  unsigned long long v = 0;
+  CUDA_TRY(cudaMemcpyAsync(&v, h->sat_counter, sizeof(v), cudaMemcpyDeviceToHost, st));
+  if (reset) CUDA_TRY(cudaMemsetAsync(h->sat_counter, 0, sizeof(v), st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  *count_host = v;
   return AACLIP_OK;
 }
 

@@ -245,6 +245,32 @@ __global__ void adapter_blend_kernel(float* __restrict__ x, const float* __restr
   }
 }
 
+// Validation pass for the 16-bit operand mode (aaclip_saturation_check): counts the elements of a 16-bit activation
+// buffer that hit the format's ceiling -- fp16: +-65504 (what cvt.rn.satfinite stores for anything larger) or a
+// non-finite pattern; bf16: inf / nan (bf16 has fp32's range, so only non-finite inputs get there). n is a multiple of 8
+// (every activation row is), p is 16-byte aligned. Not launched unless the check is enabled.
+template <bool BF16>
+__global__ void count_saturated16_kernel(const uint16_t* __restrict__ p, size_t n8, unsigned long long* counter) {
+  ptx::pdl_trigger();
+  ptx::pdl_wait();
+  const uint4* v = reinterpret_cast<const uint4*>(p);
+  unsigned int local = 0;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const uint4 q = v[i];
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t lo = w[k] & 0x7FFFu, hi = (w[k] >> 16) & 0x7FFFu;
+      constexpr uint32_t kCeil = BF16 ? 0x7F80u : 0x7BFFu;
+      local += (lo >= kCeil) + (hi >= kCeil);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+  if ((threadIdx.x & 31) == 0 && local != 0) atomicAdd(counter, static_cast<unsigned long long>(local));
+}
+
 // LayerNorm folding at weight-load time (model/transformer.py:245-254: LN followed by a Linear):
 //   W'[n,k] = W[n,k] * gamma[k] (rounded to the 16-bit operand type),  colsum[n] = sum_k W'_16[n,k],
 //   bias'[n] = b[n] + sum_k W[n,k] * beta[k].

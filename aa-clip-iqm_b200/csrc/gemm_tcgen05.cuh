@@ -177,13 +177,10 @@ struct GemmPairCfg {
   static constexpr int B_BYTES = (BN / 2) * BK * 2;       // 16 KiB (BN 256) / 8 KiB (BN 128): this CTA's half
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 #ifndef AACLIP_GEMM_RESID_PREFETCH
-#define AACLIP_GEMM_RESID_PREFETCH 1   // 0 off | 1 this tile (K <= MAXKB*64 only) | 2 one tile ahead (measured: no gain, r02_run1)
+#define AACLIP_GEMM_RESID_PREFETCH 1
 #endif
 #ifndef AACLIP_GEMM_RESID_PREFETCH_MAXKB
 #define AACLIP_GEMM_RESID_PREFETCH_MAXKB 32   // K / 64 up to which the residual rows are L2-prefetched at tile start
-#endif
-#ifndef AACLIP_GEMM_RESID_PIPE
-#define AACLIP_GEMM_RESID_PIPE 1   // residual-epilogue: bias + residual rows fetched one 32-column chunk ahead
 #endif
 #ifndef AACLIP_GEMM_EPI_WARPS
 #define AACLIP_GEMM_EPI_WARPS 8
@@ -321,30 +318,19 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
       const int m_pair = tile / n_tiles, n_blk = tile - m_pair * n_tiles;
       const int row0 = (2 * m_pair + static_cast<int>(rank)) * BM + q * 32;
-      if constexpr (EPI == EPI_BIAS_RESID_F32 && AACLIP_GEMM_RESID_PREFETCH != 0) {
-        // The residual rows this warp adds come from HBM (the stream is 180 MB, far beyond L2; last written one or two
-        // kernels ago). An L2 prefetch issued at the start of the SAME tile is too late whenever the epilogue is the
-        // slower side of the pipeline (out-proj: 16 K steps): the accumulator is already waiting, and every 32-column
-        // chunk then pays a full HBM round trip (~1.5 us x 8 chunks per tile against a 4.4 us main loop). So the lines
-        // are requested one TILE ahead -- the rows of tile i + num_pairs while tile i is processed (128 KiB per CTA in
-        // flight, 19 MB over the GPU: L2-resident until used) -- and the chunk loop's loads become L2 hits.
+      if constexpr (EPI == EPI_BIAS_RESID_F32 && AACLIP_GEMM_RESID_PREFETCH)
+        // The residual rows this warp will add come from HBM (the stream is 180 MB, far beyond L2): pull them into L2
+        // now, while the MMAs of this tile are still running, so that the loads in the chunk loop below are L2 hits
+        // (out-proj 3.39 -> 3.18 ms/step; skipped for long-K tiles, whose 20 us main loop outlives the prefetch).
         // lane l: row row0 + l, COLS_PER_WARP fp32 = COLS_PER_WARP / 32 lines of 128 B.
-        auto prefetch_rows = [&](int t) {
-          const int mp = t / n_tiles, nb = t - mp * n_tiles;
-          const int r0 = (2 * mp + static_cast<int>(rank)) * BM + q * 32;
-          if (r0 + lane < M) {
-            const float* rp = epi.out_f32 + static_cast<size_t>(r0 + lane) * epi.ldo + nb * BN + cg * COLS_PER_WARP;
+        // (Round 2: requesting the lines one TILE ahead instead, and fetching bias + residual one chunk ahead into
+        // registers, both measured slower -- tools/experiments/README.md. ncu: the out-projection moves 4.5 TB/s of
+        // DRAM traffic in isolation, 70 % of the measured copy bandwidth; it is bandwidth-, not latency-bound.)
+        if (num_kb <= AACLIP_GEMM_RESID_PREFETCH_MAXKB && row0 + lane < M) {
+          const float* rp = epi.out_f32 + static_cast<size_t>(row0 + lane) * epi.ldo + n_blk * BN + cg * COLS_PER_WARP;
 #pragma unroll
-            for (int i = 0; i < COLS_PER_WARP / 32; ++i) ptx::prefetch_l2(rp + i * 32);
-          }
-        };
-        if (AACLIP_GEMM_RESID_PREFETCH == 1) {          // previous behaviour: this tile only, short-K GEMMs only
-          if (num_kb <= AACLIP_GEMM_RESID_PREFETCH_MAXKB) prefetch_rows(tile);
-        } else {
-          if (tile == pair) prefetch_rows(tile);
-          if (tile + num_pairs < num_tiles) prefetch_rows(tile + num_pairs);
+          for (int i = 0; i < COLS_PER_WARP / 32; ++i) ptx::prefetch_l2(rp + i * 32);
         }
-      }
       // EPI_LN_*: lane l finishes the LayerNorm statistics of row row0 + l from its partials (contiguous, fixed order)
       // BEFORE waiting for the accumulator -- the loads' latency (the statistics were written by the previous kernel:
       // an L2 or HBM round trip) runs under this tile's MMAs instead of on the epilogue's critical path.
@@ -366,30 +352,10 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           rstd = rsqrtf(fmaxf(sq * epi.inv_width - mean * mean, 0.f) + epi.eps);
         }
       }
-      const int sub = lane >> 3, unit = lane & 7;
-      // EPI_BIAS_RESID_F32, pipelined form. ncu's per-instruction samples of the out-projection (K = 1024: the epilogue
-      // is the slower side of the tile pipeline) put 35 % of the epilogue warps' time on the first use of the chunk's
-      // global loads (bias and residual rows issued at the top of the chunk, consumed ~300 instructions later: a full
-      // L2 / HBM round trip per 32-column chunk, behind the previous chunk's 16 stores in the LSU queue). The loads of
-      // chunk c+1 are therefore issued before chunk c is processed (two register buffers, the chunk loop fully
-      // unrolled so that they stay in registers), and chunk 0's before the wait for the accumulator.
-      constexpr bool kResidPipe = (EPI == EPI_BIAS_RESID_F32) && (AACLIP_GEMM_RESID_PIPE != 0);
-      [[maybe_unused]] float4 rbuf[2][8];
-      [[maybe_unused]] float4 bbuf[2];
-      [[maybe_unused]] auto fetch_chunk = [&](int c, float4 (&dst)[8], float4& b) {
-        const int n = n_blk * BN + cg * COLS_PER_WARP + c * 32 + unit * 4;
-        b = __ldg(reinterpret_cast<const float4*>(epi.bias + n));
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int rr = row0 + j * 4 + sub;
-          dst[j] = (rr < M) ? *reinterpret_cast<const float4*>(epi.out_f32 + static_cast<size_t>(rr) * epi.ldo + n)
-                            : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      };
-      if constexpr (kResidPipe) fetch_chunk(0, rbuf[0], bbuf[0]);
       ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
       ptx::tc_fence_after();
       const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + cg * COLS_PER_WARP;
+      const int sub = lane >> 3, unit = lane & 7;
       // coalesced domain: this thread handles rows row0 + j*4 + sub (j < 8) in every 32-column chunk
       float mean_j[8], rstd_j[8];   // EPI_LN_*: LayerNorm statistics of its 8 rows
       float st_s[8], st_q[8];       // EPI_BIAS_RESID_F32 + stats_out: running sum / sum of squares of the new rows
@@ -405,35 +371,6 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
         for (int j = 0; j < 8; ++j) st_s[j] = st_q[j] = 0.f;
       }
-      if constexpr (kResidPipe) {
-#pragma unroll
-        for (int c = 0; c < CHUNKS; ++c) {
-          const int n = n_blk * BN + cg * COLS_PER_WARP + c * 32 + unit * 4;
-          if (c + 1 < CHUNKS) fetch_chunk(c + 1, rbuf[(c + 1) & 1], bbuf[(c + 1) & 1]);
-          uint32_t r[32];
-          ptx::tmem_ld_32x32b_x32(t_base + c * 32, r);
-          ptx::tmem_ld_wait();
-          if (c == CHUNKS - 1) {
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa_u32(ptx::smem_u32(&tmem_empty_bar[acc]), 0));
-          }
-#pragma unroll
-          for (int u = 0; u < 8; ++u)
-            ptx::sts128(stage_u32 + lane * 128 + ((u ^ (lane & 7)) << 4), r[4 * u], r[4 * u + 1], r[4 * u + 2],
-                        r[4 * u + 3]);
-          __syncwarp();
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int rr = j * 4 + sub;
-            const float4 v = ptx::lds128(stage_u32 + rr * 128 + ((unit ^ (rr & 7)) << 4));
-            const float4 x = epilogue_apply<EPI, BF16>(row0 + rr < M, v, row0 + rr, n, epi, bbuf[c & 1], rbuf[c & 1][j]);
-            st_s[j] += (x.x + x.y) + (x.z + x.w);      // rows >= M accumulate garbage that is never stored
-            st_q[j] += (x.x * x.x + x.y * x.y) + (x.z * x.z + x.w * x.w);
-          }
-          __syncwarp();
-        }
-      } else
 #pragma unroll 1
       for (int c = 0; c < CHUNKS; ++c) {
         const int n = n_blk * BN + cg * COLS_PER_WARP + c * 32 + unit * 4;

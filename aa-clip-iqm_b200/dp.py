@@ -71,3 +71,47 @@ def gather_predictions(maps: torch.Tensor, scores: torch.Tensor, n_total: Option
     dist.gather(pm, None, dst=dst, group=group)
     dist.gather(ps, None, dst=dst, group=group)
     return None, None
+
+
+class AsyncGather:
+    """Gather of equal-sized micro-batch results to the sink, overlapped with the next micro-batch's kernels
+    (BASELINE config 5): ``submit`` enqueues NCCL ``gather``s that wait for the producing stream and then run on the
+    communicator's own stream; ``wait`` makes the current stream wait for all of them. On the sink the results land
+    directly in their global positions of ``out_maps`` / ``out_scores`` (rank-major, then micro-batch, then image:
+    the contiguous split of shard_range), so no re-ordering pass is needed.
+    """
+
+    def __init__(self, per_rank: int, micro: int, map_shape, device, dst: int = 0, group=None):
+        if per_rank % micro:
+            raise ValueError(f"per-rank share {per_rank} is not a multiple of the micro-batch {micro}")
+        self.group, self.dst = group, dst
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.per_rank, self.micro = per_rank, micro
+        self.out_maps = self.out_scores = None
+        if self.rank == dst:
+            self.out_maps = torch.empty((self.world * per_rank, *map_shape), dtype=torch.float32, device=device)
+            self.out_scores = torch.empty((self.world * per_rank,), dtype=torch.float32, device=device)
+        self._pending = []
+
+    def submit(self, m: int, maps: torch.Tensor, scores: torch.Tensor) -> None:
+        """Results of this rank's micro-batch m (images [m*micro, (m+1)*micro) of its shard)."""
+        if self.world == 1:
+            self.out_maps[m * self.micro:(m + 1) * self.micro].copy_(maps)
+            self.out_scores[m * self.micro:(m + 1) * self.micro].copy_(scores)
+            return
+        lists = (None, None)
+        if self.rank == self.dst:
+            sl = [slice(r * self.per_rank + m * self.micro, r * self.per_rank + (m + 1) * self.micro)
+                  for r in range(self.world)]
+            lists = ([self.out_maps[s] for s in sl], [self.out_scores[s] for s in sl])
+        maps, scores = maps.contiguous(), scores.contiguous()
+        w1 = dist.gather(maps, lists[0], dst=self.dst, group=self.group, async_op=True)
+        w2 = dist.gather(scores, lists[1], dst=self.dst, group=self.group, async_op=True)
+        self._pending.append((w1, w2, maps, scores))     # the sources stay alive until the collective has run
+
+    def wait(self) -> None:
+        for w1, w2, _, _ in self._pending:
+            w1.wait()
+            w2.wait()
+        self._pending.clear()

@@ -237,8 +237,9 @@ class AaclipEngine:
         with torch.cuda.device(self.device):
             _lib.check(self._lib.aaclip_set_weight(self._h, name.encode(), _ptr(t), shape, t.dim(), _stream()),
                        f"aaclip_set_weight({name})")
-            # the engine copies on the current stream; keep `t` alive until the copy has been enqueued and done
-            torch.cuda.current_stream().synchronize()
+            # The engine's copy / pack kernel is enqueued on the current stream, the stream a temporary `t` was
+            # allocated on: PyTorch's caching allocator is stream-ordered, so releasing `t` here cannot hand its
+            # memory to anything that runs before that copy. No per-tensor synchronisation (there are ~400 tensors).
 
     def load_state_dict(self, sd: Dict[str, torch.Tensor], prefixes=("image_encoder.", "image_adapter.")):
         """Feed every tensor of an AdaptedCLIP state_dict whose key starts with one of `prefixes`."""
@@ -247,7 +248,24 @@ class AaclipEngine:
             if k.startswith(prefixes) and not k.endswith("proj") and ".attn_pool" not in k:
                 self.set_weight(k, v)
                 n += 1
+        with torch.cuda.device(self.device):
+            if self.missing == 0:
+                # load-time work (LayerNorm folding) now, so that forward never allocates or blocks (aaclip.h)
+                _lib.check(self._lib.aaclip_finalize_weights(self._h, _stream()), "aaclip_finalize_weights")
+            torch.cuda.current_stream().synchronize()      # one synchronisation per load: errors surface here
         return n
+
+    # -- 16-bit range validation (aaclip_saturation_check)
+    def saturation_check(self, on: bool = True):
+        """While on, every forward also counts stored 16-bit activations that hit the format's ceiling."""
+        _lib.check(self._lib.aaclip_saturation_check(self._h, int(on)), "aaclip_saturation_check")
+
+    def saturation_count(self, reset: bool = True) -> int:
+        v = ctypes.c_uint64(0)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.aaclip_saturation_count(self._h, ctypes.byref(v), int(reset), _stream()),
+                       "aaclip_saturation_count")
+        return int(v.value)
 
     @property
     def missing(self) -> int:
@@ -343,8 +361,7 @@ class AaclipTextEngine:
         shape = (ctypes.c_int64 * t.dim())(*t.shape)
         with torch.cuda.device(self.device):
             _lib.check(self._lib.aaclip_text_set_weight(self._h, name.encode(), _ptr(t), shape, t.dim(), _stream()),
-                       f"aaclip_text_set_weight({name})")
-            torch.cuda.current_stream().synchronize()
+                       f"aaclip_text_set_weight({name})")       # stream-ordered, see AaclipEngine.set_weight
 
     TEXT_KEYS = ("clipmodel.token_embedding.", "clipmodel.positional_embedding", "clipmodel.transformer.",
                  "clipmodel.ln_final.", "text_adapter.")
@@ -356,7 +373,21 @@ class AaclipTextEngine:
             if k.startswith(self.TEXT_KEYS):
                 self.set_weight(k, v)
                 n += 1
+        with torch.cuda.device(self.device):
+            if self.missing == 0:
+                _lib.check(self._lib.aaclip_text_finalize_weights(self._h, _stream()), "aaclip_text_finalize_weights")
+            torch.cuda.current_stream().synchronize()
         return n
+
+    def saturation_check(self, on: bool = True):
+        _lib.check(self._lib.aaclip_text_saturation_check(self._h, int(on)), "aaclip_text_saturation_check")
+
+    def saturation_count(self, reset: bool = True) -> int:
+        v = ctypes.c_uint64(0)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.aaclip_text_saturation_count(self._h, ctypes.byref(v), int(reset), _stream()),
+                       "aaclip_text_saturation_count")
+        return int(v.value)
 
     @property
     def missing(self) -> int:

@@ -38,9 +38,32 @@ def minmax(chunks: Sequence[torch.Tensor]) -> torch.Tensor:
     return out
 
 
+def _multi_rank(group=None) -> bool:
+    """True when torch.distributed is initialised with more than one rank in `group` (None = the default group). The
+    ONE predicate every reduction / gather below uses, so that pixel-level and image-level statistics are always
+    reduced over the same set of ranks."""
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+
+
+def gather_concat(t: torch.Tensor, group=None) -> torch.Tensor:
+    """All-gather 1-D tensors of (possibly) different lengths and concatenate them in rank order on every rank
+    (identity in a single process)."""
+    if not _multi_rank(group):
+        return t
+    world = dist.get_world_size(group)
+    sizes = [torch.zeros(1, dtype=torch.int64, device=t.device) for _ in range(world)]
+    dist.all_gather(sizes, torch.tensor([t.numel()], dtype=torch.int64, device=t.device), group=group)
+    mx = int(max(s.item() for s in sizes))
+    buf = torch.zeros(mx, dtype=t.dtype, device=t.device)
+    buf[: t.numel()] = t
+    outs = [torch.empty_like(buf) for _ in sizes]
+    dist.all_gather(outs, buf, group=group)
+    return torch.cat([o[: int(s.item())] for o, s in zip(outs, sizes)])
+
+
 def reduce_minmax(mm: torch.Tensor, group=None) -> torch.Tensor:
     """All-reduce a (min, max) pair over the data-parallel ranks (identity without a process group)."""
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+    if _multi_rank(group):
         lo, hi = mm[0:1].clone(), mm[1:2].clone()
         dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
         dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
@@ -50,7 +73,7 @@ def reduce_minmax(mm: torch.Tensor, group=None) -> torch.Tensor:
 
 def reduce_histogram(hist: torch.Tensor, group=None) -> torch.Tensor:
     """All-reduce (sum) the [2, n_bins] count histograms over the ranks. Counts travel as int64."""
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+    if _multi_rank(group):
         h = hist.to(torch.int64)
         dist.all_reduce(h, op=dist.ReduceOp.SUM, group=group)
         return h
@@ -109,8 +132,9 @@ def roc_auc_ap(scores: torch.Tensor, labels: torch.Tensor, normalize: bool = Fal
 def metrics_eval_device(pixel_label: Sequence[torch.Tensor], image_label: torch.Tensor,
                         pixel_preds: Sequence[torch.Tensor], image_preds: torch.Tensor, class_names: str, domain: str,
                         group=None) -> dict:
-    """forward_utils.metrics_eval (forward_utils.py:233-308) on device tensors; with a process group each rank passes
-    ITS shard and every rank gets the global result.
+    """forward_utils.metrics_eval (forward_utils.py:233-308) on device tensors. When torch.distributed is initialised
+    with more than one rank (in `group`, or in the default group when group is None) each rank passes ITS shard and
+    every rank gets the global result.
 
     pixel_label / pixel_preds: per-batch lists of [b,(1,)S,S] masks ({0,1}) and fp32 maps; image_label [n] {0,1};
     image_preds [n] (or the fork's [n,2], column 0 is used -- forward_utils.py:269-270).
@@ -131,17 +155,9 @@ def metrics_eval_device(pixel_label: Sequence[torch.Tensor], image_label: torch.
         ip = ip[:, 0]
     ip = ip.reshape(-1)
     il = image_label.reshape(-1).to(pmax.device)
-    if group is not None and dist.is_initialized() and dist.get_world_size(group) > 1:
-        def gather(t):
-            sizes = [torch.zeros(1, dtype=torch.int64, device=t.device) for _ in range(dist.get_world_size(group))]
-            dist.all_gather(sizes, torch.tensor([t.numel()], dtype=torch.int64, device=t.device), group=group)
-            mx = int(max(s.item() for s in sizes))
-            buf = torch.zeros(mx, dtype=t.dtype, device=t.device)
-            buf[: t.numel()] = t
-            outs = [torch.empty_like(buf) for _ in sizes]
-            dist.all_gather(outs, buf, group=group)
-            return torch.cat([o[: int(s.item())] for o, s in zip(outs, sizes)])
-        pmax, ip, il = gather(pmax), gather(ip.to(pmax.device)), gather(il.float())
+    # image-level statistics over ALL ranks' images -- same predicate as the pixel-level reductions above (with the
+    # default process group and group=None the pixel metrics used to be global and these shard-local)
+    pmax, ip, il = gather_concat(pmax, group), gather_concat(ip.to(pmax.device), group), gather_concat(il.float(), group)
     ip = ip.to(pmax.device)
     if float(ip.max()) != 1:                              # :250-253
         ip = (ip - ip.min()) / (ip.max() - ip.min())

@@ -6,9 +6,14 @@
         bench.py --gpus N --steps K --warmup W
 
 One "step" = one pass of the hot path over one batch of synthetic 518x518 images on every rank: adapted visual tower
-(aaclip_forward) + patch-text similarity / blur / upsample / level-sum maps + image scores (aaclip_score_maps); with
-N > 1 also the NCCL gather of maps and scores to rank 0 (the only collective on the path). Weak scaling: every rank
-processes its own `--batch` images (global image index = rank*batch + i, so inputs do not depend on the sharding).
+(aaclip_forward) + patch-text similarity / blur / upsample / level-sum maps + image scores (aaclip_score_maps).
+N = 1 is BASELINE config 2: one batch of 32 per step. N > 1 is BASELINE config 5: every rank processes its contiguous
+share of the global batch -- 128 images = 4 micro-batches of 32 (global 1024 at N = 8) -- and the NCCL gather of
+micro-batch i's maps and scores to rank 0 (the only collective on the path) overlaps the kernels of micro-batch i+1.
+Weak scaling: per-GPU work is the same at every N > 1 and the per-image rate is what `value` reports; the global image
+index of (rank r, micro-batch m, image i) is r*128 + m*32 + i, so inputs do not depend on the sharding. After the timed
+region rank 0 recomputes one FOREIGN shard's micro-batch on its own GPU and checks the gathered rows bit for bit
+(`dp_parity`).
 
 Printed JSON line (rank 0): value = whole-job images/s with inputs resident in HBM; e2e = same metric through the
 host API (pinned host images -> pinned host maps, copies inside the timed region); roofline = the tcgen05 GEMM kernel
@@ -39,6 +44,16 @@ def flop_per_image(S: int) -> float:
     P, N, W, F, E = G * G, G * G + 1, 1024, 4096, 768
     blocks = 24 * (2 * N * W * 3 * W + 4 * N * N * W + 2 * N * W * W + 4 * N * W * F)
     return 2 * P * 588 * W + blocks + 6 * 2 * N * W * W + 5 * 2 * P * W * E + 4 * 2 * P * E * 2
+
+
+def gemm_traffic(S, B, dtype):
+    """Measured DRAM bytes per GEMM launch for this workload from the committed ncu capture, or None."""
+    path = os.path.join(REPO, "profiles", "gemm_traffic.json")
+    if not os.path.exists(path):
+        return None
+    t = json.load(open(path))
+    key = f"S{S}_B{B}_{dtype}"
+    return t.get(key, {}).get("dram_bytes_per_gemm_launch")
 
 
 def peaks():
@@ -183,10 +198,16 @@ def run_ours(args):
     pred = pipeline.AnomalyPredictor(sd, text, img_size=S, device=dev, domain="Industrial", max_batch=B,
                                      operand_dtype={"bf16": _lib.DT_BF16, "fp16": _lib.DT_F16, "fp32": _lib.DT_F32}[args.dtype])
     del sd
-    # two resident input batches, alternated (2 x 103 MB > 126 MB L2; the step's own working set is > 1 GB anyway)
-    n_in = 2
-    host_imgs = [weights.make_images(args.seed, B, S, first_index=rank * B + 7919 * j).pin_memory() for j in range(n_in)]
+    # micro-batches per step and per rank: 1 at N = 1 (config 2), 4 at N > 1 (config 5: 128 images per GPU)
+    MB = args.micro_batches or (1 if world == 1 else 4)
+    per_rank = MB * B
+    # resident inputs: at least two distinct batches, alternated (2 x 103 MB > 126 MB L2; the step's own working set is
+    # > 1 GB anyway); input j of rank r holds global images r*per_rank + j*B ...
+    n_in = max(2, MB)
+    host_imgs = [weights.make_images(args.seed, B, S, first_index=rank * per_rank + j * B + (0 if j < MB else 7919 * j)).pin_memory()
+                 for j in range(n_in)]
     dev_imgs = [h.to(dev) for h in host_imgs]
+    gather = dp.AsyncGather(per_rank, B, (S, S), dev, dst=0) if world > 1 else None
 
     def barrier():
         torch.cuda.synchronize()
@@ -195,14 +216,17 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def step_device(i):
-        maps, scores = pred.predict_device(dev_imgs[i % n_in])
-        if world > 1:
-            dp.gather_predictions(maps, scores, n_total=world * B, dst=0)
+        for m in range(MB):
+            maps, scores = pred.predict_device(dev_imgs[(i * MB + m) % n_in])
+            if gather is not None:
+                gather.submit(m, maps, scores)          # overlaps the next micro-batch's kernels
+        if gather is not None:
+            gather.wait()
         return maps, scores
 
     # end to end: pinned host images -> pinned host maps + scores through the host API. Batches are pipelined the way a
     # real evaluation loop would run them (pipeline.HostStream): the H2D copy of batch i+1 and the D2H copy of batch
-    # i-1 overlap the kernels of batch i; every batch's result is read on the host (its event is awaited) one step
+    # i-1 overlap the kernels of batch i; every batch's result is read on the host (its event is awaited) one batch
     # later, and the timed region ends only when the last result has landed.
     stream_api = pipeline.HostStream(pred, slots=2)
     host_out = [(torch.empty((B, S, S), dtype=torch.float32).pin_memory(), torch.empty((B,), dtype=torch.float32).pin_memory())
@@ -210,10 +234,12 @@ def run_ours(args):
     pending = []
 
     def step_host(i):
-        ev = stream_api.submit(host_imgs[i % n_in], *host_out[i % 2])
-        pending.append(ev)
-        if len(pending) > 1:
-            pending.pop(0).synchronize()      # the previous batch's maps / scores are now readable on the host
+        for m in range(MB):
+            j = i * MB + m
+            ev = stream_api.submit(host_imgs[j % n_in], *host_out[j % 2])
+            pending.append(ev)
+            if len(pending) > 1:
+                pending.pop(0).synchronize()      # the previous batch's maps / scores are now readable on the host
 
     def drain_host():
         while pending:
@@ -247,15 +273,39 @@ def run_ours(args):
     sampler = ClockSampler(physical_gpu_index(local_rank)) if rank == 0 else None
     ms_total = timed(step_device, K, sampler=sampler)
     clocks = clock_box.get("clocks")
-    launches = pred.launches_per_batch * K
-    ips = world * B * K / (ms_total * 1e-3)
+    launches = pred.launches_per_batch * MB * K
+    ips = world * per_rank * K / (ms_total * 1e-3)
+
+    # ---- data-parallel parity on the hardware (outside the timed region): one more step on the canonical inputs, then
+    # rank 0 recomputes a FOREIGN rank's last micro-batch on its own GPU; the gathered rows must be bit-identical
+    # (kernels are batch-invariant with fixed reduction orders, weights are replicated)
+    dp_parity = None
+    if world > 1:
+        for m in range(MB):
+            maps, scores = pred.predict_device(dev_imgs[m])
+            gather.submit(m, maps, scores)
+        gather.wait()
+        torch.cuda.synchronize()
+        if rank == 0:
+            src = world - 1
+            first = src * per_rank + (MB - 1) * B
+            foreign = weights.make_images(args.seed, B, S, first_index=first).to(dev)
+            fm, fs = pred.predict_device(foreign)
+            ok = (torch.equal(fm, gather.out_maps[first:first + B]) and torch.equal(fs, gather.out_scores[first:first + B])
+                  and torch.equal(maps, gather.out_maps[(MB - 1) * B:MB * B]))
+            if not ok:
+                raise RuntimeError(f"data-parallel parity failed: rows gathered from rank {src} differ from rank 0's "
+                                   f"own computation of the same images")
+            dp_parity = {"result": "bit-exact", "checked": f"rank {src} micro-batch {MB - 1} ({B} maps + scores) recomputed on rank 0",
+                         "global_images": world * per_rank}
+            del foreign, fm, fs
 
     # ---- end to end through the host API (pinned host buffers, copies inside the timed region)
     for i in range(max(Wm, 3) + 1):             # the same warm-up as the device path (+1 to fill the two-slot pipeline):
         step_host(i)                            # pinned-buffer first touches and copy-stream start-up stay outside
     drain_host()
     ms_e2e = timed(step_host, K, finish=drain_host)
-    ips_e2e = world * B * K / (ms_e2e * 1e-3)
+    ips_e2e = world * per_rank * K / (ms_e2e * 1e-3)
 
     # ---- per-kernel-class timing, live, CUDA events on the launch stream (same step, same inputs)
     pk = peaks()
@@ -279,10 +329,10 @@ def run_ours(args):
         peak = pk["bf16_tflops_sustained"] or pk["bf16_tflops"]
         roof = {"bound": "tensor", "kernel": "gemm_pair_kernel (tcgen05 cta_group::2, all epilogues)", "achieved": achieved, "peak": peak,
                 "unit": "TFLOP/s", "frac": achieved / peak,
-                # dram__bytes_read + dram__bytes_write per launch, launch-weighted mean over one step's 108 GEMM launches
-                # (ncu --set full capture of the same kernels, profiles/r01d_prof_gemm_r01d.txt: qkv 320 MB, c_fc 413 MB,
-                # c_proj 824 MB, out-proj 488 MB, adapter 218 MB, heads ~150 MB); only meaningful for the B=32 @518 workload
-                "traffic": 4.75e8 if (S == 518 and B == 32 and args.dtype != "fp32") else None,
+                # dram__bytes_read + dram__bytes_write per GEMM launch (launch-weighted mean over one step), read from the
+                # committed ncu capture of this workload (profiles/gemm_traffic.json, written by tools/ncu_traffic.py from
+                # the per-launch CSV); null for any other workload
+                "traffic": gemm_traffic(S, B, args.dtype),
                 "peak_source": f"{pk['source']} (sustained cuBLAS bf16; burst {pk['bf16_tflops']})",
                 "avg_launch_ms": g["ms"] / max(1, g["launches"]), "launches_per_step": g["launches"] // n_prof,
                 "share_of_step": (g["ms"] / n_prof) / (ms_total / K)}
@@ -312,6 +362,37 @@ def run_ours(args):
                 "peak_GBs": pk["hbm_gbs"], "frac": alg_bytes / (ms * 1e-3) / 1e9 / pk["hbm_gbs"], "launches_per_batch": 2}
         del src, dst
 
+    # ---- BASELINE config 3: the text-anchor build for all 27 MVTec + VisA classes from their real prompt strings
+    # (16 sentences per class = 432): BPE tokenisation on the host, adapted text tower + prompt ensembling on the device
+    cfg3 = None
+    if rank == 0 and world == 1 and args.dtype != "fp32":
+        from aaclip_b200 import constants, engine as _eng, tokenizer
+        reals = [constants.REAL_NAMES[d][c] for d in ("MVTec", "VisA") for c in constants.CLASS_NAMES[d]]
+        groups = [g for r in reals for g in constants.class_prompts(r)]
+        sentences = [s_ for g in groups for s_ in g]
+        t0 = time.perf_counter()
+        tok = tokenizer.tokenize(sentences)
+        tok_ms = (time.perf_counter() - t0) * 1e3
+        teng = _eng.AaclipTextEngine(dev, operand_dtype={"bf16": _lib.DT_BF16, "fp16": _lib.DT_F16}[args.dtype])
+        teng.load_state_dict(weights.make_text_state_dict(seed=args.seed))
+        tok_dev = tok.to(dev)
+        sizes = [len(g) for g in groups]
+        for _ in range(2):
+            anchors = _eng.text_anchors(teng.encode_text(tok_dev), sizes)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(5):
+            anchors = _eng.text_anchors(teng.encode_text(tok_dev), sizes)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        cfg3 = {"workload": f"{len(reals)} classes x 16 prompts = {len(sentences)} sentences x 77 tokens -> {len(reals)} anchors [768,2]",
+                "tokenize_ms_host": tok_ms, "device_ms": ms, "sentences_per_s": len(sentences) / (ms * 1e-3),
+                "anchor_shape": list(anchors.shape), "unit_norm_err": float((anchors.norm(dim=1) - 1).abs().max())}
+        teng.close()
+        del teng, tok_dev, anchors
+
     # ---- CPU baseline: bounded sample on the box's host cores (rank 0, N=1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -326,8 +407,11 @@ def run_ours(args):
             "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": max(Wm, 3),
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {"fp16": "f16", "bf16": "bf16", "fp32": "f32"}[args.dtype], "data": "synthetic",
-            "config": {"workload": f"ViT-L-14-336 @{S} batch {B} per GPU (visual tower + adapters + similarity maps)",
-                       "img_size": S, "batch_per_gpu": B, "global_batch": world * B, "parallelism": f"dp{world}",
+            "config": {"workload": (f"ViT-L-14-336 @{S} batch {B} on one GPU (visual tower + adapters + similarity maps)" if world == 1 else
+                                    f"ViT-L-14-336 @{S} global batch {world * per_rank} data-parallel over {world} GPUs, {per_rank} images "
+                                    f"per GPU in micro-batches of {B}, NCCL gather of maps + scores overlapped with compute"),
+                       "img_size": S, "batch_per_gpu": per_rank, "micro_batch": B, "micro_batches_per_step": MB,
+                       "global_batch": world * per_rank, "parallelism": f"dp{world}",
                        "weights": "random-init (seeded), reference architecture",
                        "operands": {"fp16": "fp16 tensor-core operands, fp32 accumulate/residual/LN/softmax",
                                     "bf16": "bf16 tensor-core operands, fp32 accumulate",
@@ -338,13 +422,16 @@ def run_ours(args):
             "tensor_frac_of_sustained_peak": ips / world * fpi / ((pk["bf16_tflops_sustained"] or pk["bf16_tflops"]) * 1e12),
             "flop_per_image": fpi,
             "e2e": {"value": ips_e2e, "unit": "images/s", "ms_per_step": ms_e2e / K,
-                    "h2d_bytes_per_step": world * B * 3 * S * S * 4, "d2h_bytes_per_step": world * (B * S * S * 4 + B * 4)},
+                    "h2d_bytes_per_step": world * per_rank * 3 * S * S * 4,
+                    "d2h_bytes_per_step": world * (per_rank * S * S * 4 + per_rank * 4)},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": roof,
             "kernel_classes": classes,
             "cpu_baseline": cpu,
             "preprocess": prep,
+            "dp_parity": dp_parity,
+            "config3_text_anchors": cfg3,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -359,7 +446,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--batch", type=int, default=32, help="images per GPU per step (BASELINE configs[1]: 32)")
+    ap.add_argument("--batch", type=int, default=32, help="images per micro-batch (BASELINE configs[1]: 32)")
+    ap.add_argument("--micro-batches", type=int, default=0,
+                    help="micro-batches per rank per step; default 1 at N=1 (config 2), 4 at N>1 (config 5: 128 images per GPU)")
     ap.add_argument("--img-size", type=int, default=518)
     ap.add_argument("--dtype", choices=["fp16", "bf16", "fp32"], default="fp16",
                     help="tensor-core operand type; fp32 = the fp32-accuracy verification mode (BASELINE config 4)")

@@ -146,6 +146,23 @@ int aaclip_stat_columns(void);
 /* Kernel launches enqueued by the last aaclip_forward on this handle (for bench.py's gpu_launches). */
 int aaclip_last_launch_count(AaclipHandle* h);
 
+/* Load-time finalisation: folds ln_1 / ln_2 (model/transformer.py:245,252) into the in_proj / c_fc GEMM weights
+ * (kernels on `stream`, one stream synchronisation, release of the fp32 staging copies). Call it after the last
+ * aaclip_set_weight(); aaclip_forward() then allocates nothing, never blocks the host, and can be stream-captured.
+ * If it was not called, the first aaclip_forward() does it. Idempotent; AACLIP_ESTATE while tensors are missing.
+ * After it the LayerNorm / in_proj / c_fc tensors of the blocks are frozen (aaclip_set_weight refuses them). */
+int aaclip_finalize_weights(AaclipHandle* h, void* stream);
+
+/* Run-time validation of the 16-bit operand range (there is no such check in the fp32 reference: this guards the
+ * one thing the tensor-core path adds). While enabled, aaclip_forward follows every kernel that stores 16-bit
+ * activations (patch operand, the raw residual copy x16, q|k|v, attention output, GELU output, ln_post tokens) with a
+ * scan that counts stored elements sitting at the format's ceiling: fp16 +-65504 -- what the saturating stores write
+ * for anything larger -- or non-finite; bf16: non-finite. A count of 0 proves that no activation of the run was clipped.
+ * Off by default (the scans re-read every activation: ~1.5x the step time). aaclip_saturation_count copies the
+ * accumulated count to the host (synchronises `stream`) and optionally resets it. */
+int aaclip_saturation_check(AaclipHandle* h, int32_t enable);
+int aaclip_saturation_count(AaclipHandle* h, uint64_t* count_host, int32_t reset, void* stream);
+
 /* Per-kernel-class device timing of aaclip_forward, for bench.py's roofline: while enabled, every launch is bracketed
  * by a CUDA-event pair on the launch stream. aaclip_profile_read waits for the recorded events, returns the
  * accumulated milliseconds / launch counts / algorithmic FLOPs (2*M*N*K per GEMM, 4*B*H*N*N*64 per attention) per
@@ -196,6 +213,10 @@ int aaclip_text_set_weight(AaclipTextHandle* h, const char* name, const float* d
                            int32_t ndim, void* stream);
 int aaclip_text_missing_weights(AaclipTextHandle* h);
 size_t aaclip_text_workspace_bytes(AaclipTextHandle* h, int32_t n_sentences);
+/* Text-tower counterparts of aaclip_finalize_weights / aaclip_saturation_check / aaclip_saturation_count. */
+int aaclip_text_finalize_weights(AaclipTextHandle* h, void* stream);
+int aaclip_text_saturation_check(AaclipTextHandle* h, int32_t enable);
+int aaclip_text_saturation_count(AaclipTextHandle* h, uint64_t* count_host, int32_t reset, void* stream);
 
 /* Adapted text encoder. Replaces AdaptedCLIP.encode_text(text, adapt_text=True), model/adapter.py:273-304:
  * token + positional embedding, 12 causal pre-LN residual attention blocks with residual adapters on the first

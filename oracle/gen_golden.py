@@ -29,6 +29,7 @@ CASES = [
     ("vitl_518_b1", 518, 1, 2, False),
     ("vitl_224_b1_relu", 224, 1, 3, True),
     ("vitl_336_b2", 336, 2, 4, False),      # BASELINE config 4 (fp32-accuracy mode @336)
+    ("vitl_518_b2", 518, 2, 5, False),      # a second and third reference-pinned image at the headline size
 ]
 
 

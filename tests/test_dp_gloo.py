@@ -98,10 +98,18 @@ def _metrics_worker(rank, world, port, q):
         hist[rank, rank + 3] = 5 + rank
         hist[0, 0] = 1
         total = metrics.reduce_histogram(hist)
+        # image-level statistics: ragged per-rank vectors, DEFAULT process group with group=None (the case that used
+        # to stay shard-local), concatenated in rank order on every rank
+        mine = torch.arange(3 + 2 * rank, dtype=torch.float32) + 10 * rank
+        everyone = metrics.gather_concat(mine)
+        want_all = torch.cat([torch.arange(3, dtype=torch.float32), torch.arange(5, dtype=torch.float32) + 10])
+        ok_gather = torch.equal(everyone, want_all)
+        flags = [torch.zeros(1) for _ in range(world)]
+        dist.all_gather(flags, torch.tensor([float(ok_gather)]))
         if rank == 0:
             want = torch.zeros(2, 16, dtype=torch.int64)
             want[0, 3], want[1, 4], want[0, 0] = 5, 6, 2
-            q.put((mm.tolist() == [-2.0, 5.0], torch.equal(total, want)))
+            q.put((mm.tolist() == [-2.0, 5.0], torch.equal(total, want) and all(f.item() == 1.0 for f in flags)))
     finally:
         dist.barrier()
         dist.destroy_process_group()
@@ -118,3 +126,44 @@ def test_metric_statistics_reduce_world2():
         p.join(timeout=120)
         assert p.exitcode == 0
     assert q.get(timeout=5) == (True, True)
+
+
+def _async_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import aaclip_b200  # noqa: F401
+        from aaclip_b200 import dp
+        per_rank, micro, S = 6, 2, 3                      # 3 micro-batches of 2 images per rank (config-5 shape, tiny)
+        g = dp.AsyncGather(per_rank, micro, (S, S), "cpu", dst=0)
+        for m in range(per_rank // micro):
+            idx = torch.arange(rank * per_rank + m * micro, rank * per_rank + (m + 1) * micro, dtype=torch.float32)
+            g.submit(m, idx[:, None, None].expand(micro, S, S).contiguous(), idx * 2)
+        g.wait()
+        if rank == 0:
+            want = torch.arange(world * per_rank, dtype=torch.float32)
+            q.put(bool(torch.equal(g.out_scores, want * 2) and torch.equal(g.out_maps[:, 0, 0], want)
+                       and torch.equal(g.out_maps[:, 2, 1], want)))
+        else:
+            assert g.out_maps is None
+    finally:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def test_async_microbatch_gather_world2():
+    """bench.py's N > 1 path (BASELINE config 5): micro-batch results gathered to the sink in global image order."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_async_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) is True
+    with pytest.raises(ValueError):
+        import aaclip_b200  # noqa: F401
+        from aaclip_b200 import dp
+        dp.AsyncGather(7, 2, (3, 3), "cpu")

@@ -25,16 +25,19 @@ def _engine_outputs(name, domain="Industrial", operand_dtype=0):
                               operand_dtype=operand_dtype)
     eng.load_state_dict(sd)
     assert eng.missing == 0
+    eng.saturation_check(True)            # every parity run also proves that no 16-bit store was clipped
     images = weights.make_images(seed, B, S).cuda()
     text = weights.make_text_anchor(seed).cuda()
     seg, det, tokens, cls = eng.forward(images, want_tokens=True, want_cls=True)
     ks, sg = (7, 1.0) if domain == "Industrial" else (9, 1.5)
     maps, score = engine.score_maps(seg, text, S, test=True, ksize=ks, sigma=sg, det=det)
     torch.cuda.synchronize()
+    assert eng.saturation_count() == 0, "a 16-bit activation store saturated"
+    eng.saturation_check(False)
     return fx, eng, sd, images, text, seg, det, tokens, cls, maps, score
 
 
-@pytest.mark.parametrize("name", ["vitl_224_b2", "vitl_224_b1_relu", "vitl_518_b1"])
+@pytest.mark.parametrize("name", ["vitl_224_b2", "vitl_224_b1_relu", "vitl_518_b1", "vitl_518_b2"])
 def test_forward_matches_reference_golden(name):
     fx, eng, sd, images, text, seg, det, tokens, cls, maps, score = _engine_outputs(name)
     rows = torch.as_tensor(fx["rows"]).cuda()
@@ -114,11 +117,13 @@ def test_massive_activation_channels_stay_within_tolerance():
         sd[k + "weight"][ch] *= 25.0
     eng = engine.AaclipEngine("cuda", img_size=S, max_batch=B)
     eng.load_state_dict(sd)
+    eng.saturation_check(True)
     images = weights.make_images(seed, B, S)
     text = weights.make_text_anchor(seed)
     seg, det, _, cls = eng.forward(images.cuda(), want_cls=True)
     maps, score = engine.score_maps(seg, text.cuda(), S, test=True, ksize=7, sigma=1.0, det=det)
     torch.cuda.synchronize()
+    assert eng.saturation_count() == 0        # |x| ~ 275 is far inside fp16's range
     with torch.no_grad():
         o = orc.predict(sd, images, text, S, domain="Industrial")
     assert o["cls"].abs().max().item() > 100.0          # the outlier channels really are in the residual stream
@@ -127,6 +132,33 @@ def test_massive_activation_channels_stay_within_tolerance():
     print(f"massive activations: |x|max {o['cls'].abs().max().item():.0f}, map max abs err {merr:.3e}")
     assert merr < MAP_TOL
     assert (score.cpu() - o["score"]).abs().max().item() < SCORE_TOL
+
+
+def test_saturation_counter_reports_clipped_stores():
+    """aaclip_saturation_check: activations pushed beyond fp16's range must be COUNTED (the stores clamp to +-65504
+    instead of producing inf), and the same weights in bf16 operand mode must count none."""
+    import aaclip_b200  # noqa: F401
+    from aaclip_b200 import _lib, engine, weights
+    S, B, seed = 224, 1, 23
+    sd = weights.make_visual_state_dict(seed=seed, img_size=S)
+    sd["image_encoder.transformer.resblocks.2.mlp.c_proj.bias"][7] += 1.0e5      # residual channel 7 ~ 1e5 from block 2 on
+    images = weights.make_images(seed, B, S).cuda()
+    counts = {}
+    for name, dt in (("fp16", _lib.DT_F16), ("bf16", _lib.DT_BF16)):
+        eng = engine.AaclipEngine("cuda", img_size=S, max_batch=B, operand_dtype=dt)
+        eng.load_state_dict(sd)
+        eng.forward(images)
+        torch.cuda.synchronize()
+        assert eng.saturation_count() == 0                # disabled: nothing is counted
+        eng.saturation_check(True)
+        seg, det, _, _ = eng.forward(images)
+        torch.cuda.synchronize()
+        counts[name] = eng.saturation_count(reset=True)
+        assert eng.saturation_count() == 0                # reset
+        assert torch.isfinite(seg[0]).all()
+        eng.close()
+    print("saturated stores:", counts)
+    assert counts["fp16"] >= 257 and counts["bf16"] == 0     # at least one x16 element per token row of one block
 
 
 def test_auroc_and_ap_agree_with_the_fp32_oracle_to_three_decimals():

@@ -27,7 +27,7 @@ def _run(name):
     return fx, out
 
 
-@pytest.mark.parametrize("name", ["vitl_224_b2", "vitl_224_b1_relu", "vitl_518_b1", "vitl_336_b2"])
+@pytest.mark.parametrize("name", ["vitl_224_b2", "vitl_224_b1_relu", "vitl_518_b1", "vitl_336_b2", "vitl_518_b2"])
 def test_oracle_matches_reference_golden(name):
     fx, out = _run(name)
     rows = fx["rows"]

@@ -29,8 +29,11 @@ def test_encode_text_matches_reference_golden(text_engine):
     from aaclip_b200 import engine
     fx, eng, sd = text_engine
     tokens = torch.from_numpy(fx["tokens"]).cuda()
+    eng.saturation_check(True)
     emb = eng.encode_text(tokens)
     torch.cuda.synchronize()
+    assert eng.saturation_count() == 0
+    eng.saturation_check(False)
     err = np.abs(emb.cpu().numpy() - fx["emb"]).max()
     scale = np.abs(fx["emb"]).max()
     print(f"sentence embeddings: max abs err {err:.3e} (|max| {scale:.2f})")
