@@ -68,6 +68,7 @@ class AaclipCfg(ctypes.Structure):
         ("adapt_weight", ctypes.c_float),
         ("max_batch", ctypes.c_int32),
         ("operand_dtype", ctypes.c_int32),
+        ("query_dim", ctypes.c_int32),
     ]
 
 
@@ -143,7 +144,7 @@ def _declare(lib):
     lib.aaclip_workspace_bytes.restype = sz
     lib.aaclip_workspace_bytes.argtypes = [vp, i32]
     lib.aaclip_forward.restype = i32
-    lib.aaclip_forward.argtypes = [vp, vp, i32, vp, sz, _c_void_pp, vp, _c_void_pp, vp, vp]
+    lib.aaclip_forward.argtypes = [vp, vp, i32, vp, sz, _c_void_pp, vp, _c_void_pp, vp, _c_void_pp, vp]
     lib.aaclip_score_workspace_bytes.restype = sz
     lib.aaclip_score_workspace_bytes.argtypes = [i32, i32, i32]
     lib.aaclip_score_maps.restype = i32

@@ -507,6 +507,8 @@ struct AaclipHandle {
   std::vector<uint16_t*> w_adapter;  // [W,W] each
   std::vector<uint16_t*> w_seg;      // [E,W] each
   uint16_t* w_det;                   // [E,W]
+  std::vector<uint16_t*> w_query;    // [query_dim,W] each (IQM query_adapters; optional)
+  std::vector<bool> have_query;
   std::vector<std::string> missing;
   int last_launches = 0;
   unsigned long long* sat_counter = nullptr;   // device counter of aaclip_saturation_check (cudaMalloc'ed at create)
@@ -701,6 +703,7 @@ int aaclip_create(const AaclipCfg* cfg, AaclipHandle** out) {
       return fail(AACLIP_EINVAL, "levels must be ascending in 1..layers");
   }
   if (c.max_batch <= 0) return fail(AACLIP_EINVAL, "max_batch must be > 0");
+  if (c.query_dim < 0 || c.query_dim % 256 != 0) return fail(AACLIP_EINVAL, "query_dim must be 0 or a multiple of 256 (got %d)", c.query_dim);
   if (c.operand_dtype != AACLIP_DT_F16 && c.operand_dtype != AACLIP_DT_BF16 && c.operand_dtype != AACLIP_DT_F32)
     return fail(AACLIP_EINVAL, "operand_dtype must be AACLIP_DT_F16, AACLIP_DT_BF16 or AACLIP_DT_F32");
 
@@ -726,6 +729,8 @@ int aaclip_create(const AaclipCfg* cfg, AaclipHandle** out) {
   for (int i = 0; i < c.adapt_until; ++i) o_ad[i] = plan.take<uint8_t>(W * W * wb);
   for (int l = 0; l < c.n_levels; ++l) o_seg[l] = plan.take<uint8_t>(E * W * wb);
   const size_t o_det = plan.take<uint8_t>(E * W * wb);
+  std::vector<size_t> o_qry(c.query_dim > 0 ? c.n_levels : 0);
+  for (size_t l = 0; l < o_qry.size(); ++l) o_qry[l] = plan.take<uint8_t>((size_t)c.query_dim * W * wb);
   const size_t o_sat = plan.take<unsigned long long>(1);
 
   h->arena_bytes = plan.off;
@@ -750,6 +755,8 @@ int aaclip_create(const AaclipCfg* cfg, AaclipHandle** out) {
   for (int i = 0; i < c.adapt_until; ++i) h->w_adapter.push_back((uint16_t*)(a + o_ad[i]));
   for (int l = 0; l < c.n_levels; ++l) h->w_seg.push_back((uint16_t*)(a + o_seg[l]));
   h->w_det = (uint16_t*)(a + o_det);
+  for (size_t l = 0; l < o_qry.size(); ++l) h->w_query.push_back((uint16_t*)(a + o_qry[l]));
+  h->have_query.assign(o_qry.size(), false);
   h->sat_counter = (unsigned long long*)(a + o_sat);      // zeroed with the arena
 
   // the set of tensors that must arrive through aaclip_set_weight before forward may run
@@ -825,6 +832,14 @@ int aaclip_set_weight(AaclipHandle* h, const char* name, const float* data, cons
     return pack(h->w_seg[idx], E, W, W, "seg." + std::to_string(idx));
   }
   if (k == "image_adapter.det_proj.fc.weight" || k == "image_adapter.det_proj.fc.0.weight") return pack(h->w_det, E, W, W, "det");
+  if (sscanf(k.c_str(), "query_adapters.%d.fc.%95s", &idx, tail) == 2) {
+    if (c.query_dim <= 0) return fail(AACLIP_EINVAL, "%s: the handle was created with query_dim = 0", name);
+    if (idx < 0 || idx >= c.n_levels) return fail(AACLIP_EINVAL, "%s: query_adapters index out of range", name);
+    if (strcmp(tail, "weight") != 0 && strcmp(tail, "0.weight") != 0) return fail(AACLIP_EINVAL, "%s: unknown tensor", name);
+    if (int rc = pack(h->w_query[idx], c.query_dim, W, W, "")) return rc;
+    h->have_query[idx] = true;
+    return AACLIP_OK;
+  }
   return fail(AACLIP_EINVAL, "%s: unknown tensor name", name);
 }
 
@@ -852,7 +867,7 @@ static WsPlan plan_ws(const AaclipHandle* h, int B) {
 // aaclip_forward in fp32-accuracy mode: same data layout and launch order as the tensor-core path, un-folded
 // LayerNorms, SIMT fp32 GEMMs / attention, fp32 patch operand. Verification mode (BASELINE config 4).
 static int forward_f32(AaclipHandle* h, const float* images, int B, uint8_t* wsb, const WsPlan& ws, float* const* seg_out,
-                       float* det_out, float* const* tokens_out, float* cls_out, cudaStream_t st) {
+                       float* det_out, float* const* tokens_out, float* cls_out, float* const* query_out, cudaStream_t st) {
   const AaclipCfg& c = h->cfg;
   const int W = c.width, F = c.mlp_dim, E = c.embed_dim, N = h->N, P = h->P;
   const int M = B * N, MP = B * P;
@@ -897,6 +912,10 @@ static int forward_f32(AaclipHandle* h, const float* images, int B, uint8_t* wsb
       const int proj_epi = c.proj_relu ? EPI_LEAKY_F32 : EPI_F32;
       { GemmEpi e; e.out_f32 = seg_out[level_idx]; e.ldo = E;
         if ((rc = run.gemm(proj_epi, tok_out, h->w_seg[level_idx], MP, E, W, e))) return rc; }
+      if (query_out != nullptr && query_out[level_idx] != nullptr) {
+        GemmEpi e; e.out_f32 = query_out[level_idx]; e.ldo = c.query_dim;
+        if ((rc = run.gemm(proj_epi, tok_out, h->w_query[level_idx], MP, c.query_dim, W, e))) return rc;
+      }
       if ((rc = l2norm(seg_out[level_idx], MP))) return rc;
       if (level_idx == c.n_levels - 1) {
         { GemmEpi e; e.out_f32 = detbuf; e.ldo = E;
@@ -927,7 +946,8 @@ size_t aaclip_workspace_bytes(AaclipHandle* h, int32_t B) {
 }
 
 int aaclip_forward(AaclipHandle* h, const float* images, int32_t B, void* workspace, size_t workspace_bytes,
-                   float* const* seg_out, float* det_out, float* const* tokens_out, float* cls_out, void* stream) {
+                   float* const* seg_out, float* det_out, float* const* tokens_out, float* cls_out,
+                   float* const* query_out, void* stream) {
   if (!h || !images || !workspace || !seg_out || !det_out) return fail(AACLIP_EINVAL, "aaclip_forward: null argument");
   if (B <= 0 || B > h->cfg.max_batch) return fail(AACLIP_EINVAL, "aaclip_forward: batch %d outside 1..%d", B, h->cfg.max_batch);
   if (!h->missing.empty())
@@ -937,13 +957,20 @@ int aaclip_forward(AaclipHandle* h, const float* images, int32_t B, void* worksp
   if (reinterpret_cast<uintptr_t>(workspace) & 255) return fail(AACLIP_EINVAL, "aaclip_forward: workspace must be 256-byte aligned");
   for (int l = 0; l < h->cfg.n_levels; ++l)
     if (!seg_out[l]) return fail(AACLIP_EINVAL, "aaclip_forward: seg_out[%d] is null", l);
+  if (query_out != nullptr) {
+    for (int l = 0; l < h->cfg.n_levels; ++l) {
+      if (query_out[l] == nullptr) continue;
+      if (h->cfg.query_dim <= 0) return fail(AACLIP_EINVAL, "aaclip_forward: query_out given but the handle has query_dim = 0");
+      if (!h->have_query[l]) return fail(AACLIP_ESTATE, "aaclip_forward: query_out[%d] requested but query_adapters.%d was never set", l, l);
+    }
+  }
 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const AaclipCfg& c = h->cfg;
   const int W = c.width, F = c.mlp_dim, E = c.embed_dim, N = h->N, P = h->P;
   const int M = B * N, MP = B * P;
   int rc;
-  if (h->f32) return forward_f32(h, images, B, static_cast<uint8_t*>(workspace), ws, seg_out, det_out, tokens_out, cls_out, st);
+  if (h->f32) return forward_f32(h, images, B, static_cast<uint8_t*>(workspace), ws, seg_out, det_out, tokens_out, cls_out, query_out, st);
   // LayerNorm folding is load-time work (kernels + a synchronisation + cudaFree of the staging copies): callers that
   // want a capture-safe, non-blocking first forward call aaclip_finalize_weights() after the last aaclip_set_weight();
   // otherwise it happens here, once.
@@ -1024,6 +1051,11 @@ int aaclip_forward(AaclipHandle* h, const float* images, int32_t B, void* worksp
       const int proj_epi = c.proj_relu ? EPI_LEAKY_F32 : EPI_F32;
       { GemmEpi e; e.out_f32 = seg_out[level_idx]; e.ldo = E;
         if ((rc = run.gemm(proj_epi, tok, h->w_seg[level_idx], MP, E, W, e))) return rc; }
+      if (query_out != nullptr && query_out[level_idx] != nullptr) {
+        // IQM branch: query_adapters[l] (model/adapter.py:202-205) on the same 16-bit ln_post tokens, same epilogue
+        GemmEpi e; e.out_f32 = query_out[level_idx]; e.ldo = c.query_dim;
+        if ((rc = run.gemm(proj_epi, tok, h->w_query[level_idx], MP, c.query_dim, W, e))) return rc;
+      }
       if ((rc = l2norm(seg_out[level_idx], MP))) return rc;
       if (level_idx == c.n_levels - 1) {
         { GemmEpi e; e.out_f32 = detbuf; e.ldo = E;

@@ -187,7 +187,7 @@ def score_maps(seg: Sequence[torch.Tensor], text: torch.Tensor, img_size: int, t
 # ---------------------------------------------------------------------------------------- the tower
 DEFAULT_CFG = dict(img_size=518, patch=14, width=1024, heads=16, layers=24, mlp_dim=4096, embed_dim=768,
                    adapt_until=6, levels=(6, 12, 18, 24), act=_lib.ACT_GELU_ERF, proj_relu=0, adapt_weight=0.1,
-                   max_batch=64, operand_dtype=_lib.DT_F16)
+                   max_batch=64, operand_dtype=_lib.DT_F16, query_dim=0)
 
 
 class AaclipEngine:
@@ -202,7 +202,7 @@ class AaclipEngine:
         self.cfg = full
         c = _lib.AaclipCfg()
         for k in ("img_size", "patch", "width", "heads", "layers", "mlp_dim", "embed_dim", "adapt_until", "act",
-                  "proj_relu", "max_batch", "operand_dtype"):
+                  "proj_relu", "max_batch", "operand_dtype", "query_dim"):
             setattr(c, k, int(full[k]))
         c.adapt_weight = float(full["adapt_weight"])
         levels = list(full["levels"])
@@ -242,8 +242,11 @@ class AaclipEngine:
             # memory to anything that runs before that copy. No per-tensor synchronisation (there are ~400 tensors).
 
     def load_state_dict(self, sd: Dict[str, torch.Tensor], prefixes=("image_encoder.", "image_adapter.")):
-        """Feed every tensor of an AdaptedCLIP state_dict whose key starts with one of `prefixes`."""
+        """Feed every tensor of an AdaptedCLIP state_dict whose key starts with one of `prefixes` (plus the IQM
+        branch's ``query_adapters.*`` when the engine was created with query_dim > 0)."""
         n = 0
+        if self.cfg["query_dim"] > 0:
+            prefixes = tuple(prefixes) + ("query_adapters.",)
         for k, v in sd.items():
             if k.startswith(prefixes) and not k.endswith("proj") and ".attn_pool" not in k:
                 self.set_weight(k, v)
@@ -275,8 +278,10 @@ class AaclipEngine:
         return self._lib.aaclip_workspace_bytes(self._h, B)
 
     # -- forward
-    def forward(self, images: torch.Tensor, want_tokens: bool = False, want_cls: bool = False):
-        """images [B,3,S,S] fp32 on the engine's device -> (seg list of [B,P,E], det [B,E], tokens|None, cls|None)."""
+    def forward(self, images: torch.Tensor, want_tokens: bool = False, want_cls: bool = False,
+                want_query: bool = False):
+        """images [B,3,S,S] fp32 on the engine's device -> (seg list of [B,P,E], det [B,E], tokens|None, cls|None), and
+        with want_query a fifth element: the IQM query-adapter projections, a list of [B,P,query_dim] fp32."""
         _need_cuda(images)
         images = images.contiguous().float()
         B = images.shape[0]
@@ -294,10 +299,15 @@ class AaclipEngine:
             if want_tokens else None
         cls = torch.empty((B, W), dtype=torch.float32, device=dev) if want_cls else None
         tok_arr = _ptr_array(tokens) if tokens is not None else None
+        query = [torch.empty((B, self.P, self.cfg["query_dim"]), dtype=torch.float32, device=dev)
+                 for _ in range(self.n_levels)] if want_query else None
+        qry_arr = _ptr_array(query) if query is not None else None
         with torch.cuda.device(dev):
             _lib.check(
                 self._lib.aaclip_forward(self._h, _ptr(images), B, _ptr(self._ws), self._ws.numel(), _ptr_array(seg),
-                                         _ptr(det), tok_arr, _ptr(cls), _stream()), "aaclip_forward")
+                                         _ptr(det), tok_arr, _ptr(cls), qry_arr, _stream()), "aaclip_forward")
+        if want_query:
+            return seg, det, tokens, cls, query
         return seg, det, tokens, cls
 
     # -- per-kernel-class device timing (bench.py roofline)

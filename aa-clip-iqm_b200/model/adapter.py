@@ -29,7 +29,7 @@ from .. import _lib
 from .. import engine as _engine
 from . import torch_path as _tp
 from .adapter_modules import SimpleAdapter, SimpleProj
-from .iqm import IQM, IQMConfig
+from .iqm import IQM, FactoredMemory, IQMConfig
 
 
 class AdaptedCLIP(nn.Module):
@@ -72,6 +72,7 @@ class AdaptedCLIP(nn.Module):
         self.text_weight = nn.Parameter(torch.tensor(0.4))      # normalised pair and never uses it (adapter.py:236-244)
         self.iqm_dropout = nn.Dropout(0.1)
         self.iqm_layer_norm = nn.LayerNorm(iqm_hidden_size)
+        self.iqm_factored = True              # cross-attention over the visual memory in factored form (model/iqm.py)
         for mod in (self.image_adapter, self.text_adapter, self.iqm, self.class_query_mlp, self.query_adapters):
             for p in mod.parameters():                                # model/adapter.py:107-123
                 if p.dim() > 1:
@@ -100,11 +101,13 @@ class AdaptedCLIP(nn.Module):
         return tuple((t.data_ptr(), t._version) for _, t in pairs)
 
     def _visual_pairs(self):
-        owner = (id(self.image_encoder), id(self.image_adapter))
+        owner = (id(self.image_encoder), id(self.image_adapter), id(self.query_adapters))
         if self._vis_list is None or self._vis_list[0] != owner:
             sd = {"image_encoder." + k: v for k, v in _tp.named(self.image_encoder).items()
                   if k != "proj" and "attn_pool" not in k}
             sd.update({"image_adapter." + k: v for k, v in _tp.named(self.image_adapter).items()})
+            if self._engine_query_dim():
+                sd.update({"query_adapters." + k: v for k, v in _tp.named(self.query_adapters).items()})
             self._vis_list = (owner, list(sd.items()))
         return self._vis_list[1]
 
@@ -116,6 +119,11 @@ class AdaptedCLIP(nn.Module):
             sd.update({"text_adapter." + k: v for k, v in _tp.named(self.text_adapter).items()})
             self._txt_list = (owner, list(sd.items()))
         return self._txt_list[1]
+
+    def _engine_query_dim(self) -> int:
+        """Width of the query adapters when the engine can run them (a multiple of 256: 512 and 768 both are), else 0
+        (then the IQM branch projects the exported fp32 tokens on the host)."""
+        return self.iqm_hidden_size if self.iqm_hidden_size % 256 == 0 else 0
 
     def refresh_engines(self):
         """Forget the packed copies (call after replacing a sub-module object; in-place updates -- load_state_dict,
@@ -140,7 +148,7 @@ class AdaptedCLIP(nn.Module):
                 adapt_until=self.image_adapt_until, levels=tuple(self.levels),
                 act=_lib.ACT_QUICK_GELU if getattr(self.clipmodel, "quick_gelu", False) else _lib.ACT_GELU_ERF,
                 proj_relu=int(self.relu), adapt_weight=self.i_w, max_batch=self._max_batch,
-                operand_dtype=self._operand_dtype)
+                operand_dtype=self._operand_dtype, query_dim=self._engine_query_dim())
             self._vis.load_state_dict(sd)
             if self._vis.missing:
                 raise RuntimeError(f"{self._vis.missing} visual-path tensors missing from the wrapped CLIP model")
@@ -170,18 +178,24 @@ class AdaptedCLIP(nn.Module):
 
     # ------------------------------------------------------------------------------------------ the two routes
     def _tower_engine(self, x: torch.Tensor, want_iqm: bool):
+        """-> (seg, det, tokens | None, cls | None, query_tokens | None). With the IQM branch wanted, the engine also
+        runs the four query-adapter GEMMs and the fp32 tokens are not exported at all."""
         self._need_cuda()
         eng = self._visual_engine()
-        chunks = [eng.forward(x[i:i + self._max_batch], want_tokens=want_iqm, want_cls=want_iqm)
+        on_device = want_iqm and self._engine_query_dim() > 0
+        chunks = [eng.forward(x[i:i + self._max_batch], want_tokens=want_iqm and not on_device, want_cls=want_iqm,
+                              want_query=True) if on_device else
+                  eng.forward(x[i:i + self._max_batch], want_tokens=want_iqm, want_cls=want_iqm) + (None,)
                   for i in range(0, x.shape[0], self._max_batch)]      # larger batches run in max_batch chunks
         if len(chunks) == 1:
             return chunks[0]
         L = len(self.levels)
         seg = [torch.cat([c[0][l] for c in chunks]) for l in range(L)]
         det = torch.cat([c[1] for c in chunks])
-        tokens = [torch.cat([c[2][l] for c in chunks]) for l in range(L)] if want_iqm else None
+        tokens = [torch.cat([c[2][l] for c in chunks]) for l in range(L)] if chunks[0][2] is not None else None
         cls = torch.cat([c[3] for c in chunks]) if want_iqm else None
-        return seg, det, tokens, cls
+        query = [torch.cat([c[4][l] for c in chunks]) for l in range(L)] if on_device else None
+        return seg, det, tokens, cls, query
 
     def _tower_autograd(self, x: torch.Tensor):
         P = _tp.named(self.image_encoder)
@@ -189,19 +203,29 @@ class AdaptedCLIP(nn.Module):
                                        bool(getattr(self.clipmodel, "quick_gelu", False)))
         seg = [F.normalize(self.image_adapter["seg_proj"][i](t), dim=-1) for i, t in enumerate(tokens)]
         det = F.normalize(self.image_adapter["det_proj"](tokens[-1]), dim=-1).mean(1)
-        return seg, det, tokens, cls
+        return seg, det, tokens, cls, None
 
     # ------------------------------------------------------------------------------------------ IQM branch
-    def _iqm_branch(self, tokens: List[torch.Tensor], cls_feature: torch.Tensor, text_embeddings: torch.Tensor):
+    def _iqm_branch(self, tokens: Optional[List[torch.Tensor]], cls_feature: torch.Tensor, text_embeddings: torch.Tensor,
+                    query_tokens: Optional[List[torch.Tensor]] = None):
         """model/adapter.py:186-269 on the tower's exports. tokens: ln_post'ed [B,P,W] per level; cls_feature: the
-        final block's CLS row [B,W] (no ln_post)."""
+        final block's CLS row [B,W] (no ln_post); query_tokens: ``query_adapters[l](tokens[l])`` [B,P,hidden] when the
+        engine has already computed them (then `tokens` is not needed).
+
+        ``self.iqm_factored`` (default True): the projected visual memory proj(cat(levels)) [B, 4P, hidden] is never
+        materialised and never pushed through the IQM's key / value projections -- the cross-attention runs in its
+        factored form (model/iqm.py: FactoredMemory); False reproduces the reference's operation order literally."""
         B = cls_feature.shape[0]
         class_query = self.class_query_mlp(cls_feature).unsqueeze(1).repeat(1, 2, 1)      # normal / abnormal query
         query_embeds = class_query + self.pos_embedding[:, :2, :].repeat(B, 1, 1)
-        visual = torch.cat([self.query_adapters[i](t) for i, t in enumerate(tokens)], dim=1)   # [B, L*P, hidden]
-        if self.visual_feature_proj is None or self.visual_feature_proj.in_features != visual.shape[-1]:
-            self.visual_feature_proj = nn.Linear(int(visual.shape[-1]), self.iqm_hidden_size).to(visual.device)
-        visual = self.visual_feature_proj(visual)
+        if query_tokens is None:
+            query_tokens = [self.query_adapters[i](t) for i, t in enumerate(tokens)]       # 4 x [B, P, hidden]
+        width = int(query_tokens[0].shape[-1])
+        if self.visual_feature_proj is None or self.visual_feature_proj.in_features != width:
+            self.visual_feature_proj = nn.Linear(width, self.iqm_hidden_size).to(query_tokens[0].device)
+        visual = FactoredMemory(query_tokens, self.visual_feature_proj)
+        if not self.iqm_factored:
+            visual = visual.materialise()
         te = text_embeddings
         if te.dim() == 2:                                   # [E,2] -> [B,2,E]
             te = te.transpose(0, 1).unsqueeze(0).repeat(B, 1, 1)
@@ -221,10 +245,10 @@ class AdaptedCLIP(nn.Module):
         iqm_outputs | None). model/adapter.py:137-271. ``iqm_outputs.last_hidden_state`` is [B,2,iqm_hidden_size]."""
         want_iqm = text_embeddings is not None
         if self._training_route():
-            seg, det, tokens, cls = self._tower_autograd(x)
+            seg, det, tokens, cls, query = self._tower_autograd(x)
         else:
-            seg, det, tokens, cls = self._tower_engine(x, want_iqm)
-        iqm_outputs = self._iqm_branch(tokens, cls, text_embeddings) if want_iqm else None
+            seg, det, tokens, cls, query = self._tower_engine(x, want_iqm)
+        iqm_outputs = self._iqm_branch(tokens, cls, text_embeddings, query_tokens=query) if want_iqm else None
         return seg, det, iqm_outputs
 
     def encode_text(self, text, adapt_text=True):

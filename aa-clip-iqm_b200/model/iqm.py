@@ -67,13 +67,58 @@ class _Heads(nn.Module):
         B, n, _ = t.shape
         return t.view(B, n, self.heads, self.head_dim).transpose(1, 2)
 
-    def forward(self, x: torch.Tensor, memory: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, memory=None) -> torch.Tensor:
+        if isinstance(memory, FactoredMemory):
+            return self.forward_factored(x, memory)
         src = x if memory is None else memory
         q, k, v = self._split(self.query(x)), self._split(self.key(src)), self._split(self.value(src))
         p = torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(self.head_dim), dim=-1)
         ctx = self.dropout(p) @ v
         B, _, n, _ = ctx.shape
         return ctx.transpose(1, 2).reshape(B, n, self.heads * self.head_dim)
+
+    def forward_factored(self, x: torch.Tensor, mem: FactoredMemory) -> torch.Tensor:
+        """Cross-attention of a FEW queries over a LONG memory u_i = Wp a_i + bp without projecting the memory.
+
+        The reference computes k_i = Wk u_i + bk and v_i = Wv u_i + bv for all 5 476 memory rows of every image
+        (3 x 5476 x H x H MACs per layer) to serve 2 queries. Per head h, with q the projected query:
+            q . k_i   = (Wp^T Wk_h^T q) . a_i + (Wk_h^T q) . bp + q . bk_h        -> project the QUERY back instead
+            sum_i p_i v_i = Wv_h (Wp (sum_i p_i a_i) + bp) + bv_h                  (sum_i p_i = 1)
+        so the memory is touched by two skinny products per layer ([n_q * heads, Ha] x [Ha, P] and its transpose
+        partner) and the concatenation over levels is a concatenation of the small score rows. Same result as
+        `forward` up to fp32 re-association (tests: <= 1e-5 on the reference fixture)."""
+        B, n, _ = x.shape
+        h, d = self.heads, self.head_dim
+        Wp, bp = mem.proj.weight, mem.proj.bias                     # [H, Ha], [H]
+        q = self._split(self.query(x))                              # [B, h, n, d]
+        Wk = self.key.weight.view(h, d, -1)                         # [h, d, H]
+        g = torch.einsum("bhnd,hdk->bhnk", q, Wk)                   # Wk_h^T q          [B, h, n, H]
+        const = g @ bp + torch.einsum("bhnd,hd->bhn", q, self.key.bias.view(h, d))
+        gp = (g @ Wp).reshape(B, h * n, -1)                         # Wp^T Wk_h^T q     [B, h*n, Ha]
+        scores = torch.cat([gp @ a.transpose(1, 2) for a in mem.levels], dim=-1)           # [B, h*n, sum P_l]
+        scores = (scores + const.reshape(B, h * n, 1)) / math.sqrt(d)
+        p = self.dropout(torch.softmax(scores, dim=-1))
+        s, o = None, 0
+        for a in mem.levels:                                        # sum_i p_i a_i     [B, h*n, Ha]
+            part = p[:, :, o:o + a.shape[1]] @ a
+            s = part if s is None else s + part
+            o += a.shape[1]
+        t = (s @ Wp.t() + bp).view(B, h, n, -1)                     # Wp s + bp         [B, h, n, H]
+        ctx = torch.einsum("bhnk,hdk->bhnd", t, self.value.weight.view(h, d, -1)) + self.value.bias.view(1, h, 1, d)
+        return ctx.transpose(1, 2).reshape(B, n, h * d)
+
+
+class FactoredMemory:
+    """The visual memory of the cross-attention in factored form: ``levels`` = the query-adapter outputs a_l
+    [B, P_l, Ha] (one tensor per tapped level, NOT concatenated) and ``proj`` = the Linear(Ha, H) the reference applies
+    to their concatenation (AdaptedCLIP.visual_feature_proj). The memory the reference materialises is
+    u = proj(cat(levels, dim=1)) [B, sum P_l, H]; `_Heads.forward_factored` attends over it without building it."""
+
+    def __init__(self, levels, proj: nn.Linear):
+        self.levels, self.proj = list(levels), proj
+
+    def materialise(self) -> torch.Tensor:
+        return self.proj(torch.cat(self.levels, dim=1))
 
 
 class _ResidualNorm(nn.Module):
@@ -95,7 +140,7 @@ class _AttentionBlock(nn.Module):
         self.attention = _Heads(cfg, kv_width)
         self.output = _ResidualNorm(cfg, cfg.hidden_size)
 
-    def forward(self, x: torch.Tensor, memory: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, memory=None) -> torch.Tensor:
         return self.output(self.attention(x, memory), x)
 
 

@@ -335,7 +335,7 @@ def run_ours(args):
                 "traffic": gemm_traffic(S, B, args.dtype),
                 "peak_source": f"{pk['source']} (sustained cuBLAS bf16; burst {pk['bf16_tflops']})",
                 "avg_launch_ms": g["ms"] / max(1, g["launches"]), "launches_per_step": g["launches"] // n_prof,
-                "share_of_step": (g["ms"] / n_prof) / (ms_total / K)}
+                "share_of_step": (g["ms"] / n_prof) * MB / (ms_total / K)}     # a step is MB micro-batches
 
     # ---- device pre-processing: decoded 1024x1024 RGB uint8 -> [B,3,S,S] fp32, HBM-bound byte work
     prep = None

@@ -79,6 +79,8 @@ typedef struct AaclipCfg {
   float adapt_weight;    /* i_w = 0.1 */
   int32_t max_batch;     /* largest B accepted by aaclip_forward */
   int32_t operand_dtype; /* AACLIP_DT_F16 (default), AACLIP_DT_BF16, or AACLIP_DT_F32 (fp32-accuracy mode) */
+  int32_t query_dim;     /* IQM branch: width of query_adapters (model/adapter.py:75-78: iqm_hidden_size, a multiple
+                          * of 256); 0 = the tower carries no query adapters */
 } AaclipCfg;
 
 typedef struct AaclipHandle AaclipHandle;
@@ -102,6 +104,8 @@ void aaclip_destroy(AaclipHandle* h);
  *   "image_encoder.transformer.resblocks.<i>.mlp.{c_fc,c_proj}.{weight,bias}"
  *   "image_adapter.layer_adapters.<i>.fc.0.weight", "image_adapter.seg_proj.<l>.fc.weight" (or ".fc.0.weight"),
  *   "image_adapter.det_proj.fc.weight" (or ".fc.0.weight")
+ *   "query_adapters.<l>.fc.weight" (or ".fc.0.weight") [query_dim, W] -- OPTIONAL (never counted as missing): the
+ *   IQM branch's per-level SimpleProj (model/adapter.py:75-78), needed only when aaclip_forward is asked for query_out
  * Replaces: load_state_dict (model/clip.py:132) / checkpoint loading (test_last.py:231-247). */
 int aaclip_set_weight(AaclipHandle* h, const char* name, const float* data, const int64_t* shape, int32_t ndim,
                       void* stream);
@@ -120,9 +124,14 @@ size_t aaclip_workspace_bytes(AaclipHandle* h, int32_t B);
  *   det_out     [B,E]   fp32
  *   tokens_out  optional (NULL or array of n_levels pointers, each NULL or [B,P,W] fp32): ln_post(tokens[l]),
  *               the input of the reference's IQM branch (model/adapter.py:202-205)
- *   cls_out     optional [B,W] fp32: x[:,0,:] after the last block, no ln_post (model/adapter.py:190) */
+ *   cls_out     optional [B,W] fp32: x[:,0,:] after the last block, no ln_post (model/adapter.py:190)
+ *   query_out   optional (NULL or array of n_levels pointers, each NULL or [B,P,query_dim] fp32):
+ *               query_adapters[l](ln_post(tokens[l])) -- model/adapter.py:202-205, the 4 x (P x W x query_dim) GEMMs of
+ *               the IQM branch run on the tensor cores from the 16-bit ln_post tokens the tower already holds
+ *               (SURVEY.md section 8f rank 2); the host side then never needs tokens_out */
 int aaclip_forward(AaclipHandle* h, const float* images, int32_t B, void* workspace, size_t workspace_bytes,
-                   float* const* seg_out, float* det_out, float* const* tokens_out, float* cls_out, void* stream);
+                   float* const* seg_out, float* det_out, float* const* tokens_out, float* cls_out,
+                   float* const* query_out, void* stream);
 
 /* Bytes of scratch aaclip_score_maps needs. */
 size_t aaclip_score_workspace_bytes(int32_t B, int32_t n_levels, int32_t P);

@@ -31,8 +31,12 @@ def test_library_exports_every_declared_symbol(built_lib):
 
 def test_cfg_struct_layout_matches_header():
     from aaclip_b200 import _lib
-    # 9 int32 + 4 levels + act + proj_relu + float + max_batch + operand_dtype = 18 4-byte fields
-    assert ctypes.sizeof(_lib.AaclipCfg) == 18 * 4
+    # 9 int32 + 4 levels + act + proj_relu + float + max_batch + operand_dtype + query_dim = 19 4-byte fields
+    assert ctypes.sizeof(_lib.AaclipCfg) == 19 * 4
+    hdr = open(os.path.join(REPO, "include", "aaclip.h")).read()
+    body = hdr[hdr.index("typedef struct AaclipCfg {"):hdr.index("} AaclipCfg;")]
+    fields = re.findall(r"^\s*(?:int32_t|float)\s+(\w+)", re.sub(r"/\*.*?\*/", "", body, flags=re.S), flags=re.M)
+    assert fields == [n for n, _ in _lib.AaclipCfg._fields_]      # same names, same order as the ctypes mirror
 
 
 def test_argument_errors_are_reported_without_a_gpu(built_lib):

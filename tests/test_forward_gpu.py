@@ -161,6 +161,42 @@ def test_saturation_counter_reports_clipped_stores():
     assert counts["fp16"] >= 257 and counts["bf16"] == 0     # at least one x16 element per token row of one block
 
 
+@pytest.mark.parametrize("relu,qdim", [(False, 768), (True, 512)])
+def test_query_adapter_outputs_match_host_projection(relu, qdim):
+    """the IQM branch's query_adapters (model/adapter.py:202-205) run inside aaclip_forward from
+    the 16-bit ln_post tokens. Checked against fp32 PyTorch on the fp32 tokens the same forward exports."""
+    import aaclip_b200  # noqa: F401
+    from aaclip_b200 import engine, weights
+    S, B, seed = 224, 2, 27
+    sd = weights.make_visual_state_dict(seed=seed, img_size=S, relu=relu)
+    g = torch.Generator().manual_seed(seed)
+    fc = "fc.0.weight" if relu else "fc.weight"
+    wq = [torch.randn(qdim, 1024, generator=g) * 0.03 for _ in range(4)]
+    for l in range(4):
+        sd[f"query_adapters.{l}.{fc}"] = wq[l]
+    eng = engine.AaclipEngine("cuda", img_size=S, max_batch=B, proj_relu=int(relu), query_dim=qdim)
+    eng.load_state_dict(sd)
+    assert eng.missing == 0
+    images = weights.make_images(seed, B, S).cuda()
+    seg, det, tokens, cls, query = eng.forward(images, want_tokens=True, want_cls=True, want_query=True)
+    seg2, det2, _, _ = eng.forward(images)                         # the extra GEMMs must not disturb anything else
+    torch.cuda.synchronize()
+    assert torch.equal(det, det2) and all(torch.equal(a, b) for a, b in zip(seg, seg2))
+    for l in range(4):
+        ref = tokens[l] @ wq[l].cuda().t()
+        if relu:
+            ref = torch.nn.functional.leaky_relu(ref, 0.01)
+        assert tuple(query[l].shape) == (B, (S // 14) ** 2, qdim)
+        err = (query[l] - ref).abs().max().item()
+        assert err < 5e-3 * max(1.0, ref.abs().max().item()), (l, err)
+    # asking for query_out on an engine without query adapters is an argument error, not a crash
+    plain = engine.AaclipEngine("cuda", img_size=S, max_batch=B)
+    plain.load_state_dict(weights.make_visual_state_dict(seed=seed, img_size=S))
+    plain.cfg["query_dim"] = 768
+    with pytest.raises(RuntimeError, match="query_dim"):
+        plain.forward(images, want_query=True)
+
+
 def test_auroc_and_ap_agree_with_the_fp32_oracle_to_three_decimals():
     """north_star: "AUROC ... identical to 3 decimals". Eight seeded images through the sm_100a path (fp16 operands) and
     through the fp32 oracle, scored against the same synthetic ground truth (a noisy threshold of the oracle's own maps,

@@ -24,10 +24,17 @@ def test_iqm_branch_matches_reference(name):
     tok = [torch.randn(B, P, 1024, generator=g) for _ in range(4)]
     cls = torch.randn(B, 1024, generator=g)
     text = torch.from_numpy(fx["text"])
+    assert model.iqm_factored
     with torch.no_grad():
-        out = model._iqm_branch(tok, cls, text.unsqueeze(0).repeat(B, 1, 1))
+        out = model._iqm_branch(tok, cls, text.unsqueeze(0).repeat(B, 1, 1))        # factored cross-attention
+        model.iqm_factored = False
+        lit = model._iqm_branch(tok, cls, text.unsqueeze(0).repeat(B, 1, 1))        # the reference's literal order
+        model.iqm_factored = True
     assert tuple(out.last_hidden_state.shape) == (B, 2, hidden)
-    assert np.abs(out.last_hidden_state.numpy() - fx["branch_alone"]).max() < 1e-5
+    err_f = np.abs(out.last_hidden_state.numpy() - fx["branch_alone"]).max()
+    err_l = np.abs(lit.last_hidden_state.numpy() - fx["branch_alone"]).max()
+    print(f"{name}: IQM branch vs reference: factored {err_f:.2e}, literal {err_l:.2e}")
+    assert err_l < 1e-5 and err_f < 1e-5
     # a [768,2] anchor (no batch axis) takes the reference's transpose route: 2 text tokens of width 768 -> new lazy layer
     with torch.no_grad():
         out2 = model._iqm_branch(tok, cls, text)
