@@ -34,6 +34,29 @@ def _ptr_array(tensors: Sequence[Optional[torch.Tensor]]):
     return arr
 
 
+class StreamGuard:
+    """Orders uses of a buffer that one object shares between calls (an engine's workspace, a predictor's staging
+    input): a use on a different CUDA stream than the previous one first waits for the event recorded after that use.
+    Same-stream use costs one event record. It makes interleaved calls from several streams SAFE (serialised on the
+    buffer); it does not make a handle thread-safe."""
+
+    def __init__(self):
+        self._event = None
+        self._stream = None
+
+    def enter(self):
+        cur = torch.cuda.current_stream()
+        if self._event is not None and self._stream != cur:
+            cur.wait_event(self._event)
+
+    def leave(self):
+        cur = torch.cuda.current_stream()
+        if self._event is None:
+            self._event = torch.cuda.Event()
+        self._event.record(cur)
+        self._stream = cur
+
+
 # ---------------------------------------------------------------------------------------- building blocks
 _TORCH_DT = {torch.float16: _lib.DT_F16, torch.bfloat16: _lib.DT_BF16}
 
@@ -218,6 +241,7 @@ class AaclipEngine:
         self.N = self.P + 1
         self.n_levels = len(levels)
         self._ws: Optional[torch.Tensor] = None
+        self._ws_guard = StreamGuard()
 
     def close(self):
         if getattr(self, "_h", None):
@@ -290,6 +314,7 @@ class AaclipEngine:
             raise ValueError(f"expected images [B,3,{S},{S}], got {tuple(images.shape)}")
         E, W = self.cfg["embed_dim"], self.cfg["width"]
         need = self.workspace_bytes(B)
+        self._ws_guard.enter()        # the workspace is shared by every call: order uses from different streams
         if self._ws is None or self._ws.numel() < need:
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
         dev = self.device
@@ -306,6 +331,7 @@ class AaclipEngine:
             _lib.check(
                 self._lib.aaclip_forward(self._h, _ptr(images), B, _ptr(self._ws), self._ws.numel(), _ptr_array(seg),
                                          _ptr(det), tok_arr, _ptr(cls), qry_arr, _stream()), "aaclip_forward")
+        self._ws_guard.leave()
         if want_query:
             return seg, det, tokens, cls, query
         return seg, det, tokens, cls
@@ -354,6 +380,7 @@ class AaclipTextEngine:
         with torch.cuda.device(self.device):
             _lib.check(self._lib.aaclip_text_create(ctypes.byref(c), ctypes.byref(self._h)), "aaclip_text_create")
         self._ws: Optional[torch.Tensor] = None
+        self._ws_guard = StreamGuard()
 
     def close(self):
         if getattr(self, "_h", None):
@@ -418,12 +445,14 @@ class AaclipTextEngine:
             tk = tokens[i:i + step].to(self.device, torch.int32).contiguous()
             m = tk.shape[0]
             need = self._lib.aaclip_text_workspace_bytes(self._h, m)
+            self._ws_guard.enter()
             if self._ws is None or self._ws.numel() < need:
                 self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
             out = torch.empty((m, self.cfg["embed_dim"]), dtype=torch.float32, device=self.device)
             with torch.cuda.device(self.device):
                 _lib.check(self._lib.aaclip_encode_text(self._h, _ptr(tk), m, _ptr(self._ws), self._ws.numel(), _ptr(out),
                                                         _stream()), "aaclip_encode_text")
+            self._ws_guard.leave()
             outs.append(out)
         return outs[0] if len(outs) == 1 else torch.cat(outs)
 

@@ -35,6 +35,7 @@ class AnomalyPredictor:
             raise RuntimeError(f"{self.engine.missing} weight tensors of the visual path are missing from the state dict")
         self.text = text.to(self.device, torch.float32).contiguous()
         self._stage_in: Optional[torch.Tensor] = None
+        self._stage_guard = _engine.StreamGuard()       # _stage_in is shared by predict_u8 / predict_host calls
         self._pre = None
 
     # -- device-resident entry point (what bench.py's `value` times)
@@ -57,7 +58,10 @@ class AnomalyPredictor:
         if self._stage_in is None or self._stage_in.shape[0] < B:
             self._stage_in = torch.empty((max(B, self.max_batch), 3, self.img_size, self.img_size), dtype=torch.float32,
                                          device=self.device)
-        return self.predict_device(self._pre(x, out=self._stage_in[:B]))
+        self._stage_guard.enter()
+        out = self.predict_device(self._pre(x, out=self._stage_in[:B]))
+        self._stage_guard.leave()
+        return out
 
     @property
     def launches_per_batch(self) -> int:
@@ -74,8 +78,10 @@ class AnomalyPredictor:
             self._stage_in = torch.empty((max(B, self.max_batch), 3, self.img_size, self.img_size), dtype=torch.float32,
                                          device=self.device)
         dev_in = self._stage_in[:B]
+        self._stage_guard.enter()
         dev_in.copy_(images_pinned, non_blocking=True)
         maps, scores = self.predict_device(dev_in)
+        self._stage_guard.leave()
         maps_out_pinned.copy_(maps, non_blocking=True)
         scores_out_pinned.copy_(scores, non_blocking=True)
 
@@ -126,6 +132,8 @@ class HostStream:
             self.d2h.wait_event(computed)
             maps_out_pinned.copy_(maps, non_blocking=True)
             scores_out_pinned.copy_(scores, non_blocking=True)
+            maps.record_stream(self.d2h)         # allocated on the compute stream, read here
+            scores.record_stream(self.d2h)
             self.out_done[slot].record(self.d2h)
         return self.out_done[slot]
 

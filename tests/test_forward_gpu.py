@@ -325,3 +325,45 @@ def test_argument_errors():
         eng.set_weight("image_encoder.class_embedding", torch.zeros(4))
     with pytest.raises(RuntimeError, match="no CPU path"):
         eng.forward(torch.zeros(1, 3, 224, 224))
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_two_devices_in_one_process():
+    """Function attributes (the > 48 KiB shared-memory opt-in) and the SM count are per device: a second engine on
+    cuda:1 of the same process must work and agree bit for bit with the one on cuda:0."""
+    import aaclip_b200  # noqa: F401
+    from aaclip_b200 import engine, weights
+    S, B, seed = 224, 2, 29
+    sd = weights.make_visual_state_dict(seed=seed, img_size=S)
+    images, text = weights.make_images(seed, B, S), weights.make_text_anchor(seed)
+    outs = []
+    for dev in ("cuda:0", "cuda:1"):
+        eng = engine.AaclipEngine(dev, img_size=S, max_batch=B)
+        eng.load_state_dict(sd)
+        with torch.cuda.device(dev):
+            seg, det, _, _ = eng.forward(images.to(dev))
+            maps, score = engine.score_maps(seg, text.to(dev), S, test=True, ksize=7, sigma=1.0, det=det)
+            torch.cuda.synchronize()
+        outs.append((maps.cpu(), score.cpu()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
+def test_workspace_is_safe_across_streams():
+    """One engine driven from two CUDA streams back to back (no explicit synchronisation by the caller): the shared
+    workspace is ordered by the engine (StreamGuard), results equal the single-stream ones."""
+    import aaclip_b200  # noqa: F401
+    from aaclip_b200 import engine, weights
+    S, B, seed = 224, 2, 30
+    eng = engine.AaclipEngine("cuda", img_size=S, max_batch=B)
+    eng.load_state_dict(weights.make_visual_state_dict(seed=seed, img_size=S))
+    xa, xb = weights.make_images(seed, B, S).cuda(), weights.make_images(seed + 1, B, S).cuda()
+    ref_a, ref_b = eng.forward(xa)[1].clone(), eng.forward(xb)[1].clone()
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    for _ in range(3):
+        with torch.cuda.stream(s1):
+            da = eng.forward(xa)[1]
+        with torch.cuda.stream(s2):
+            db = eng.forward(xb)[1]
+    torch.cuda.synchronize()
+    assert torch.equal(da, ref_a) and torch.equal(db, ref_b)

@@ -36,6 +36,8 @@ def launches():
     lines = [l for l in open(path) if not l.startswith("==")]
     agg, tot = collections.OrderedDict(), 0.0
     for row in csv.DictReader(lines):
+        if row.get("Metric Name", "gpu__time_duration.sum") != "gpu__time_duration.sum":
+            continue                      # the round-2 capture carries DRAM byte counters in the same CSV
         name = row["Kernel Name"]
         v = float(row["Metric Value"].replace(",", ""))
         v *= {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(row["Metric Unit"], 1.0)
