@@ -13,6 +13,8 @@ pytestmark = pytest.mark.gpu
 MAP_TOL = 1e-2     # north_star: anomaly maps within 1e-2 abs in bf16 mode
 SCORE_TOL = 1e-3   # north_star: image scores within 1e-3
 FEAT_TOL = 2e-3    # unit-norm patch features (cosine-level error, not in north_star; keeps the maps honest)
+TOKEN_TOL = 1e-2   # ln_post tokens / final CLS row exported for the IQM branch: O(1)..O(5) values after 24 blocks of
+                   # fp16-operand GEMMs (measured 2-3e-3, printed by the test)
 
 
 def _engine_outputs(name, domain="Industrial", operand_dtype=0):
@@ -96,8 +98,12 @@ def test_forward_matches_cpu_oracle_on_the_box_and_exports_iqm_inputs():
     for l in range(4):
         assert (seg[l].cpu() - o["seg"][l]).abs().max().item() < FEAT_TOL
         # ln_post(tokens): the IQM branch's input (model/adapter.py:202-205); values are O(1)
-        assert (tokens[l].cpu() - o["tokens"][l]).abs().max().item() < 5e-2
-    assert (cls.cpu() - o["cls"]).abs().max().item() < 5e-2
+        terr = (tokens[l].cpu() - o["tokens"][l]).abs().max().item()
+        print(f"level {l}: ln_post tokens max abs err {terr:.3e} (|max| {o['tokens'][l].abs().max().item():.2f})")
+        assert terr < TOKEN_TOL
+    cerr = (cls.cpu() - o["cls"]).abs().max().item()
+    print(f"final CLS row max abs err {cerr:.3e} (|max| {o['cls'].abs().max().item():.2f})")
+    assert cerr < TOKEN_TOL
 
 
 def test_massive_activation_channels_stay_within_tolerance():
