@@ -45,11 +45,15 @@ class StreamGuard:
         self._stream = None
 
     def enter(self):
+        if torch.cuda.is_current_stream_capturing():
+            return                      # inside a CUDA-graph capture the graph's own edges order the uses
         cur = torch.cuda.current_stream()
         if self._event is not None and self._stream != cur:
             cur.wait_event(self._event)
 
     def leave(self):
+        if torch.cuda.is_current_stream_capturing():
+            return
         cur = torch.cuda.current_stream()
         if self._event is None:
             self._event = torch.cuda.Event()

@@ -45,6 +45,14 @@ class AnomalyPredictor:
         k, s = DOMAIN_BLUR[self.domain]
         return _engine.score_maps(seg, self.text, self.img_size, test=True, ksize=k, sigma=s, det=det)
 
+    # -- the same step as a CUDA graph (one launch per batch instead of 157)
+    def capture(self, batch: int) -> "CapturedStep":
+        """Captures predict_device for `batch` images into a CUDA graph with static input / output buffers. The C ABI
+        allocates nothing and never synchronises after aaclip_finalize_weights, so the whole step -- tensor-map
+        encoding happens on the host at capture time -- replays from one cudaGraphLaunch. Worth it when the HOST is the
+        bottleneck (small batches, small images); at B = 32 @518 the GPU is never waiting for launches (bench.py --graph)."""
+        return CapturedStep(self, batch)
+
     # -- decoded images in (SURVEY 8f rank 3): the dataset transform runs on the device too
     def predict_u8(self, images_u8) -> Tuple[torch.Tensor, torch.Tensor]:
         """images [B,H,W,3] uint8 (decoded RGB, one size) -> (maps [B,S,S], scores [B]) on the GPU. The reference's
@@ -84,6 +92,32 @@ class AnomalyPredictor:
         self._stage_guard.leave()
         maps_out_pinned.copy_(maps, non_blocking=True)
         scores_out_pinned.copy_(scores, non_blocking=True)
+
+
+class CapturedStep:
+    """predict_device as a replayable CUDA graph: ``step = predictor.capture(B); maps, scores = step(images)``.
+    `images` are copied into the graph's static input; the returned tensors are the graph's static outputs (valid until
+    the next call)."""
+
+    def __init__(self, predictor: AnomalyPredictor, batch: int):
+        p = predictor
+        self.static_in = torch.zeros((batch, 3, p.img_size, p.img_size), dtype=torch.float32, device=p.device)
+        side = torch.cuda.Stream(device=p.device)
+        side.wait_stream(torch.cuda.current_stream(p.device))
+        with torch.cuda.stream(side):             # warm-up outside the capture: function attributes, workspaces
+            for _ in range(2):
+                p.predict_device(self.static_in)
+        torch.cuda.current_stream(p.device).wait_stream(side)
+        torch.cuda.synchronize(p.device)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.maps, self.scores = p.predict_device(self.static_in)
+
+    def __call__(self, images: torch.Tensor):
+        if images.data_ptr() != self.static_in.data_ptr():
+            self.static_in.copy_(images, non_blocking=True)
+        self.graph.replay()
+        return self.maps, self.scores
 
 
 class HostStream:

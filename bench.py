@@ -215,9 +215,14 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    captured = pred.capture(B) if args.graph else None
+
     def step_device(i):
         for m in range(MB):
-            maps, scores = pred.predict_device(dev_imgs[(i * MB + m) % n_in])
+            if captured is not None:
+                maps, scores = captured(dev_imgs[(i * MB + m) % n_in])      # device-to-device input copy + one graph launch
+            else:
+                maps, scores = pred.predict_device(dev_imgs[(i * MB + m) % n_in])
             if gather is not None:
                 gather.submit(m, maps, scores)          # overlaps the next micro-batch's kernels
         if gather is not None:
@@ -411,7 +416,7 @@ def run_ours(args):
                                     f"ViT-L-14-336 @{S} global batch {world * per_rank} data-parallel over {world} GPUs, {per_rank} images "
                                     f"per GPU in micro-batches of {B}, NCCL gather of maps + scores overlapped with compute"),
                        "img_size": S, "batch_per_gpu": per_rank, "micro_batch": B, "micro_batches_per_step": MB,
-                       "global_batch": world * per_rank, "parallelism": f"dp{world}",
+                       "global_batch": world * per_rank, "parallelism": f"dp{world}", "cuda_graph": bool(args.graph),
                        "weights": "random-init (seeded), reference architecture",
                        "operands": {"fp16": "fp16 tensor-core operands, fp32 accumulate/residual/LN/softmax",
                                     "bf16": "bf16 tensor-core operands, fp32 accumulate",
@@ -454,6 +459,8 @@ def main():
                     help="tensor-core operand type; fp32 = the fp32-accuracy verification mode (BASELINE config 4)")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", action="store_true",
+                    help="run the device-resident step as one captured CUDA graph per batch (pipeline.CapturedStep)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -39,7 +39,7 @@ def _engine_outputs(name, domain="Industrial", operand_dtype=0):
     return fx, eng, sd, images, text, seg, det, tokens, cls, maps, score
 
 
-@pytest.mark.parametrize("name", ["vitl_224_b2", "vitl_224_b1_relu", "vitl_518_b1", "vitl_518_b2"])
+@pytest.mark.parametrize("name", ["vitl_224_b2", "vitl_224_b1_relu", "vitl_336_b2", "vitl_518_b1", "vitl_518_b2"])
 def test_forward_matches_reference_golden(name):
     fx, eng, sd, images, text, seg, det, tokens, cls, maps, score = _engine_outputs(name)
     rows = torch.as_tensor(fx["rows"]).cuda()
@@ -373,3 +373,22 @@ def test_workspace_is_safe_across_streams():
             db = eng.forward(xb)[1]
     torch.cuda.synchronize()
     assert torch.equal(da, ref_a) and torch.equal(db, ref_b)
+
+
+def test_step_is_cuda_graph_capturable():
+    """The C-ABI contract (include/aaclip.h): after aaclip_finalize_weights a forward + scoring step allocates nothing
+    and never synchronises, so it can be stream-captured -- programmatic-dependent-launch attributes included -- and
+    replayed with new inputs; the replay must equal the direct call bit for bit."""
+    import aaclip_b200  # noqa: F401
+    from aaclip_b200 import pipeline, weights
+    S, B, seed = 224, 2, 33
+    pred = pipeline.AnomalyPredictor(weights.make_visual_state_dict(seed=seed, img_size=S), weights.make_text_anchor(seed),
+                                     img_size=S, max_batch=B)
+    xa, xb = weights.make_images(seed, B, S).cuda(), weights.make_images(seed + 1, B, S).cuda()
+    ref_a = [t.clone() for t in pred.predict_device(xa)]
+    ref_b = [t.clone() for t in pred.predict_device(xb)]
+    step = pred.capture(B)
+    for x, ref in ((xa, ref_a), (xb, ref_b), (xa, ref_a)):
+        maps, scores = step(x)
+        torch.cuda.synchronize()
+        assert torch.equal(maps, ref[0]) and torch.equal(scores, ref[1])
