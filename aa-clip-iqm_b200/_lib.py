@@ -98,6 +98,8 @@ def _sources():
 def needs_build() -> bool:
     if not LIB_PATH.exists():
         return True
+    if os.environ.get("AACLIP_NO_REBUILD"):   # pre-built kernel variants (tools/build_variants.sh) are used as they are
+        return False
     t = LIB_PATH.stat().st_mtime
     return any(p.stat().st_mtime > t for p in _sources())
 

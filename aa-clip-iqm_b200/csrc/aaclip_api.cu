@@ -216,10 +216,18 @@ template <bool BF16>
 int launch_attention_t(const CUtensorMap& tq, void* out, int B, int N, int D, int causal, cudaStream_t st) {
   static PerDeviceOnce once;
   if (int rc = opt_in_smem(once, attention_tcgen05_kernel<BF16>, attn_cfg::SMEM_BYTES)) return rc;
-  dim3 grid((N + attn_cfg::BQ * attn_cfg::QT - 1) / (attn_cfg::BQ * attn_cfg::QT), D / 64, B);
+  int sms = 0;
+  if (int rc = ensure_device(&sms)) return rc;
+  // persistent: one CTA per SM draws (image, head, 256 query rows) items from a counter slot (attention_tcgen05.cuh);
+  // slots are handed out round-robin, so launches in flight on different streams never share one
+  static std::atomic<unsigned> next_slot{0};
+  AttnSched* sched = nullptr;
+  CUDA_TRY(cudaGetSymbolAddress(reinterpret_cast<void**>(&sched), g_attn_sched));
+  sched += next_slot.fetch_add(1, std::memory_order_relaxed) % attn_cfg::SCHED_SLOTS;
+  const int items = B * (D / attn_cfg::HD) * ((N + attn_cfg::BQ * attn_cfg::QT - 1) / (attn_cfg::BQ * attn_cfg::QT));
   const float scale_log2 = 0.125f * 1.4426950408889634f;  // head_dim^-0.5 * log2(e)
-  CUDA_TRY(launch_pdl(attention_tcgen05_kernel<BF16>, grid, dim3(attn_cfg::THREADS), attn_cfg::SMEM_BYTES, st, tq,
-                      reinterpret_cast<uint16_t*>(out), N, D, causal, scale_log2));
+  CUDA_TRY(launch_pdl(attention_tcgen05_kernel<BF16>, dim3(items < sms ? items : sms), dim3(attn_cfg::THREADS),
+                      attn_cfg::SMEM_BYTES, st, tq, reinterpret_cast<uint16_t*>(out), N, D, causal, scale_log2, B, sched));
   return AACLIP_OK;
 }
 
@@ -678,6 +686,9 @@ struct BlockRunF32 {
 #ifdef AACLIP_ATTN_DBG_TIMELINE
 extern "C" int aaclip_debug_attn_timeline(long long* dst) {
   return cudaMemcpyFromSymbol(dst, aaclip::g_attn_timeline, sizeof(long long) * 2 * 16 * 8) == cudaSuccess ? 0 : -1;
+}
+extern "C" int aaclip_debug_attn_timeline_mma(long long* dst) {
+  return cudaMemcpyFromSymbol(dst, aaclip::g_attn_timeline_mma, sizeof(long long) * 2 * 16 * 8) == cudaSuccess ? 0 : -1;
 }
 #endif
 
