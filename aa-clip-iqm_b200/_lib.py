@@ -152,6 +152,12 @@ def _declare(lib):
     lib.aaclip_score_maps.restype = i32
     lib.aaclip_score_maps.argtypes = [_c_void_pp, i32, vp, i32, i32, i32, i32, i32, i32, i32, f32, vp, sz, vp, vp,
                                       vp, vp]
+    lib.aaclip_score_maps_raw.restype = i32
+    lib.aaclip_score_maps_raw.argtypes = lib.aaclip_score_maps.argtypes
+    lib.aaclip_seg_normalize.restype = i32
+    lib.aaclip_seg_normalize.argtypes = [vp, i32]
+    lib.aaclip_adapter.restype = i32
+    lib.aaclip_adapter.argtypes = [i32, vp, vp, vp, i32, i32, f32, vp, sz, vp, vp]
     lib.aaclip_last_launch_count.restype = i32
     lib.aaclip_last_launch_count.argtypes = [vp]
     lib.aaclip_stat_columns.restype = i32
@@ -229,6 +235,7 @@ EXPORTED_SYMBOLS = [
     "aaclip_resample_ksize", "aaclip_resample_coeffs_host", "aaclip_preprocess_workspace_bytes", "aaclip_preprocess_u8",
     "aaclip_finalize_weights", "aaclip_saturation_check", "aaclip_saturation_count",
     "aaclip_text_finalize_weights", "aaclip_text_saturation_check", "aaclip_text_saturation_count",
+    "aaclip_score_maps_raw", "aaclip_seg_normalize", "aaclip_adapter",
 ]
 
 

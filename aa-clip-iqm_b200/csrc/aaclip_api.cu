@@ -207,6 +207,7 @@ int launch_gemm(int epi_mode, bool bf16, const void* A, const void* W, int M, in
     AACLIP_GEMM_CASE(EPI_LN_BIAS_BF16)
     AACLIP_GEMM_CASE(EPI_LN_BIAS_GELU_BF16)
     AACLIP_GEMM_CASE(EPI_LN_BIAS_QGELU_BF16)
+    AACLIP_GEMM_CASE(EPI_LEAKY_16_SQ)
 #undef AACLIP_GEMM_CASE
     default: return fail(AACLIP_EINVAL, "gemm: unknown epilogue %d", epi_mode);
   }
@@ -216,18 +217,10 @@ template <bool BF16>
 int launch_attention_t(const CUtensorMap& tq, void* out, int B, int N, int D, int causal, cudaStream_t st) {
   static PerDeviceOnce once;
   if (int rc = opt_in_smem(once, attention_tcgen05_kernel<BF16>, attn_cfg::SMEM_BYTES)) return rc;
-  int sms = 0;
-  if (int rc = ensure_device(&sms)) return rc;
-  // persistent: one CTA per SM draws (image, head, 256 query rows) items from a counter slot (attention_tcgen05.cuh);
-  // slots are handed out round-robin, so launches in flight on different streams never share one
-  static std::atomic<unsigned> next_slot{0};
-  AttnSched* sched = nullptr;
-  CUDA_TRY(cudaGetSymbolAddress(reinterpret_cast<void**>(&sched), g_attn_sched));
-  sched += next_slot.fetch_add(1, std::memory_order_relaxed) % attn_cfg::SCHED_SLOTS;
-  const int items = B * (D / attn_cfg::HD) * ((N + attn_cfg::BQ * attn_cfg::QT - 1) / (attn_cfg::BQ * attn_cfg::QT));
+  dim3 grid((N + attn_cfg::BQ * attn_cfg::QT - 1) / (attn_cfg::BQ * attn_cfg::QT), D / 64, B);
   const float scale_log2 = 0.125f * 1.4426950408889634f;  // head_dim^-0.5 * log2(e)
-  CUDA_TRY(launch_pdl(attention_tcgen05_kernel<BF16>, dim3(items < sms ? items : sms), dim3(attn_cfg::THREADS),
-                      attn_cfg::SMEM_BYTES, st, tq, reinterpret_cast<uint16_t*>(out), N, D, causal, scale_log2, B, sched));
+  CUDA_TRY(launch_pdl(attention_tcgen05_kernel<BF16>, grid, dim3(attn_cfg::THREADS), attn_cfg::SMEM_BYTES, st, tq,
+                      reinterpret_cast<uint16_t*>(out), N, D, causal, scale_log2));
   return AACLIP_OK;
 }
 
@@ -519,6 +512,7 @@ struct AaclipHandle {
   std::vector<bool> have_query;
   std::vector<std::string> missing;
   int last_launches = 0;
+  bool seg_normalize = true;   // aaclip_seg_normalize: false = seg_out stays un-normalised (the scoring call normalises)
   unsigned long long* sat_counter = nullptr;   // device counter of aaclip_saturation_check (cudaMalloc'ed at create)
   bool sat_on = false;
   // optional per-kernel-class device timing (aaclip_profile_*)
@@ -608,23 +602,34 @@ struct BlockRun {
     { GemmEpi e; e.bias = b.b_proj; e.out_f32 = x; e.out_16 = x16; e.stats_out = stats; e.ldo = W;
       if ((rc = gemm(EPI_BIAS_RESID_F32, hid, b.w_proj, M, W, F, e, AACLIP_PROF_GEMM_PROJ))) return rc; }
     sat.scan(x16, static_cast<size_t>(M) * W, st);
-    if (w_adapter != nullptr) {
-      { GemmEpi e; e.out_f32 = abuf; e.ldo = W;
-        if ((rc = gemm(EPI_LEAKY_F32, x16, w_adapter, M, W, W, e))) return rc; }
-      ProfScope ps(prof, AACLIP_PROF_OTHER, 0.0, st);
-      const int grid = (M + 7) / 8;
-      const float w = adapt_weight, w1 = 1.0f - adapt_weight;
-      if (W == 1024) {
-        if (bf16) launch_pdl(adapter_blend_kernel<1024, true>, dim3(grid), dim3(256), 0, st, x, static_cast<const float*>(abuf), M, w, w1, x16, stats, np);
-        else launch_pdl(adapter_blend_kernel<1024, false>, dim3(grid), dim3(256), 0, st, x, static_cast<const float*>(abuf), M, w, w1, x16, stats, np);
-      } else {
-        if (bf16) launch_pdl(adapter_blend_kernel<768, true>, dim3(grid), dim3(256), 0, st, x, static_cast<const float*>(abuf), M, w, w1, x16, stats, np);
-        else launch_pdl(adapter_blend_kernel<768, false>, dim3(grid), dim3(256), 0, st, x, static_cast<const float*>(abuf), M, w, w1, x16, stats, np);
-      }
-      LAUNCH_CHECK("adapter_blend_kernel");
-      ++launches;
-      sat.scan(x16, static_cast<size_t>(M) * W, st);
+    if (w_adapter != nullptr) return adapter(w_adapter, M, adapt_weight);
+    return AACLIP_OK;
+  }
+
+  // residual adapter + blend, model/adapter.py:163-170: a = LeakyReLU(x W^T); a <- a |x| / |a|; x <- w a + (1-w) x.
+  // a leaves the GEMM in the 16-bit operand dtype together with the per-row partials of sum a^2 (EPI_LEAKY_16_SQ); both
+  // live in the fp32-sized `abuf` slot of the workspace.
+  int adapter(const uint16_t* w_adapter, int M, float adapt_weight) {
+    const int np = kStatPartials(W);
+    int rc;
+    uint16_t* a16 = reinterpret_cast<uint16_t*>(abuf);
+    float* a_stats = reinterpret_cast<float*>(a16 + static_cast<size_t>(M) * W);
+    { GemmEpi e; e.out_16 = a16; e.stats_out = a_stats; e.ldo = W;
+      if ((rc = gemm(EPI_LEAKY_16_SQ, x16, w_adapter, M, W, W, e))) return rc; }
+    sat.scan(a16, static_cast<size_t>(M) * W, st);
+    ProfScope ps(prof, AACLIP_PROF_OTHER, 0.0, st);
+    const int grid = (M + 7) / 8;
+    const float w = adapt_weight, w1 = 1.0f - adapt_weight;
+    if (W == 1024) {
+      if (bf16) launch_pdl(adapter_blend16_kernel<1024, true>, dim3(grid), dim3(256), 0, st, x, static_cast<const uint16_t*>(a16), static_cast<const float*>(a_stats), M, w, w1, x16, stats, np);
+      else launch_pdl(adapter_blend16_kernel<1024, false>, dim3(grid), dim3(256), 0, st, x, static_cast<const uint16_t*>(a16), static_cast<const float*>(a_stats), M, w, w1, x16, stats, np);
+    } else {
+      if (bf16) launch_pdl(adapter_blend16_kernel<768, true>, dim3(grid), dim3(256), 0, st, x, static_cast<const uint16_t*>(a16), static_cast<const float*>(a_stats), M, w, w1, x16, stats, np);
+      else launch_pdl(adapter_blend16_kernel<768, false>, dim3(grid), dim3(256), 0, st, x, static_cast<const uint16_t*>(a16), static_cast<const float*>(a_stats), M, w, w1, x16, stats, np);
     }
+    LAUNCH_CHECK("adapter_blend16_kernel");
+    ++launches;
+    sat.scan(x16, static_cast<size_t>(M) * W, st);
     return AACLIP_OK;
   }
 };
@@ -686,9 +691,6 @@ struct BlockRunF32 {
 #ifdef AACLIP_ATTN_DBG_TIMELINE
 extern "C" int aaclip_debug_attn_timeline(long long* dst) {
   return cudaMemcpyFromSymbol(dst, aaclip::g_attn_timeline, sizeof(long long) * 2 * 16 * 8) == cudaSuccess ? 0 : -1;
-}
-extern "C" int aaclip_debug_attn_timeline_mma(long long* dst) {
-  return cudaMemcpyFromSymbol(dst, aaclip::g_attn_timeline_mma, sizeof(long long) * 2 * 16 * 8) == cudaSuccess ? 0 : -1;
 }
 #endif
 
@@ -1067,7 +1069,7 @@ int aaclip_forward(AaclipHandle* h, const float* images, int32_t B, void* worksp
         GemmEpi e; e.out_f32 = query_out[level_idx]; e.ldo = c.query_dim;
         if ((rc = run.gemm(proj_epi, tok, h->w_query[level_idx], MP, c.query_dim, W, e))) return rc;
       }
-      if ((rc = l2norm(seg_out[level_idx], MP))) return rc;
+      if (h->seg_normalize && (rc = l2norm(seg_out[level_idx], MP))) return rc;
       if (level_idx == c.n_levels - 1) {
         { GemmEpi e; e.out_f32 = detbuf; e.ldo = E;
           if ((rc = run.gemm(proj_epi, tok, h->w_det, MP, E, W, e))) return rc; }
@@ -1151,10 +1153,10 @@ size_t aaclip_score_workspace_bytes(int32_t B, int32_t n_levels, int32_t P) {
   return align_up((size_t)B * n_levels * 2 * P * sizeof(float), 256);
 }
 
-int aaclip_score_maps(const float* const* seg, int32_t n_levels, const float* text, int32_t text_per_image,
-                      int32_t B, int32_t G, int32_t E, int32_t S, int32_t test_mode, int32_t ksize, float sigma,
-                      void* workspace, size_t workspace_bytes, float* maps_out, const float* det, float* score_out,
-                      void* stream) {
+static int score_maps_impl(bool seg_raw, const float* const* seg, int32_t n_levels, const float* text,
+                           int32_t text_per_image, int32_t B, int32_t G, int32_t E, int32_t S, int32_t test_mode,
+                           int32_t ksize, float sigma, void* workspace, size_t workspace_bytes, float* maps_out,
+                           const float* det, float* score_out, void* stream) {
   if (!seg || !text || !workspace || !maps_out) return fail(AACLIP_EINVAL, "aaclip_score_maps: null argument");
   if (n_levels <= 0 || n_levels > AACLIP_MAX_LEVELS) return fail(AACLIP_EINVAL, "aaclip_score_maps: n_levels must be 1..4");
   if (B <= 0 || G <= 0 || E <= 0 || S <= 0) return fail(AACLIP_EINVAL, "aaclip_score_maps: bad shape");
@@ -1173,7 +1175,8 @@ int aaclip_score_maps(const float* const* seg, int32_t n_levels, const float* te
   {
     const long long rows = (long long)B * n_levels * P;
     const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
-    launch_pdl(similarity_kernel, dim3(grid), dim3(256), 0, st, sp, text, tstride, s, B, n_levels, P, E);
+    if (seg_raw) launch_pdl(similarity_kernel<true>, dim3(grid), dim3(256), 0, st, sp, text, tstride, s, B, n_levels, P, E);
+    else launch_pdl(similarity_kernel<false>, dim3(grid), dim3(256), 0, st, sp, text, tstride, s, B, n_levels, P, E);
     LAUNCH_CHECK("similarity_kernel");
   }
   MapTaps taps;
@@ -1202,6 +1205,42 @@ int aaclip_score_maps(const float* const* seg, int32_t n_levels, const float* te
     LAUNCH_CHECK("image_score_kernel");
   }
   return AACLIP_OK;
+}
+
+int aaclip_score_maps(const float* const* seg, int32_t n_levels, const float* text, int32_t text_per_image,
+                      int32_t B, int32_t G, int32_t E, int32_t S, int32_t test_mode, int32_t ksize, float sigma,
+                      void* workspace, size_t workspace_bytes, float* maps_out, const float* det, float* score_out,
+                      void* stream) {
+  return score_maps_impl(false, seg, n_levels, text, text_per_image, B, G, E, S, test_mode, ksize, sigma, workspace,
+                         workspace_bytes, maps_out, det, score_out, stream);
+}
+
+int aaclip_score_maps_raw(const float* const* seg, int32_t n_levels, const float* text, int32_t text_per_image,
+                          int32_t B, int32_t G, int32_t E, int32_t S, int32_t test_mode, int32_t ksize, float sigma,
+                          void* workspace, size_t workspace_bytes, float* maps_out, const float* det, float* score_out,
+                          void* stream) {
+  return score_maps_impl(true, seg, n_levels, text, text_per_image, B, G, E, S, test_mode, ksize, sigma, workspace,
+                         workspace_bytes, maps_out, det, score_out, stream);
+}
+
+int aaclip_seg_normalize(AaclipHandle* h, int32_t enable) {
+  if (!h) return fail(AACLIP_EINVAL, "aaclip_seg_normalize: null handle");
+  h->seg_normalize = enable != 0;
+  return AACLIP_OK;
+}
+
+int aaclip_adapter(int32_t dtype, float* x, void* x16, const void* W16, int32_t M, int32_t D, float weight,
+                   void* workspace, size_t workspace_bytes, float* stats_out, void* stream) {
+  if (!x || !x16 || !W16 || !workspace || !stats_out) return fail(AACLIP_EINVAL, "aaclip_adapter: null argument");
+  if (dtype != AACLIP_DT_F16 && dtype != AACLIP_DT_BF16) return fail(AACLIP_EINVAL, "aaclip_adapter: bad dtype %d", dtype);
+  if (M <= 0 || (D != 768 && D != 1024)) return fail(AACLIP_EINVAL, "aaclip_adapter: D=%d unsupported (768 or 1024)", D);
+  const int np = kStatPartials(D);
+  const size_t need = static_cast<size_t>(M) * D * 2 + static_cast<size_t>(M) * np * 2 * sizeof(float);
+  if (workspace_bytes < need) return fail(AACLIP_EINVAL, "aaclip_adapter: workspace too small (%zu < %zu)", workspace_bytes, need);
+  BlockRun run;
+  run.prof = nullptr; run.bf16 = dtype == AACLIP_DT_BF16; run.W = D; run.st = static_cast<cudaStream_t>(stream);
+  run.x = x; run.x16 = static_cast<uint16_t*>(x16); run.abuf = static_cast<float*>(workspace); run.stats = stats_out;
+  return run.adapter(static_cast<const uint16_t*>(W16), M, weight);
 }
 
 }  // extern "C"

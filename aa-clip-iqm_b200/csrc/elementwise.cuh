@@ -245,6 +245,58 @@ __global__ void adapter_blend_kernel(float* __restrict__ x, const float* __restr
   }
 }
 
+// The same blend fed by the adapter GEMM's EPI_LEAKY_16_SQ epilogue: a arrives in the 16-bit operand dtype and its
+// squared norm as `np` per-row partials (sum, sumsq) of the unrounded values (fixed order: batch-invariant).
+template <int D, bool BF16>
+__global__ void adapter_blend16_kernel(float* __restrict__ x, const uint16_t* __restrict__ a16,
+                                       const float* __restrict__ a_stats, int rows, float w, float one_minus_w,
+                                       uint16_t* __restrict__ x16, float* __restrict__ stats_out, int np) {
+  ptx::pdl_trigger();
+  ptx::pdl_wait();
+  constexpr int V = D / 128;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  float4* xr = reinterpret_cast<float4*>(x + static_cast<size_t>(warp) * D);
+  const uint2* ar = reinterpret_cast<const uint2*>(a16 + static_cast<size_t>(warp) * D);
+  float4 xv[V];
+  uint2 aw[V];
+  float sx = 0.f;
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    xv[j] = xr[lane + 32 * j];
+    aw[j] = ar[lane + 32 * j];
+    sx += (xv[j].x * xv[j].x + xv[j].y * xv[j].y) + (xv[j].z * xv[j].z + xv[j].w * xv[j].w);
+  }
+  float sa = 0.f;
+  {
+    const float2* ap = reinterpret_cast<const float2*>(a_stats) + static_cast<size_t>(warp) * np;
+    for (int i = 0; i < np; ++i) sa += __ldg(ap + i).y;   // every lane: same order, same value
+  }
+  const float nx = sqrtf(warp_sum(sx)), na = sqrtf(sa);
+  float s = 0.f, q = 0.f;
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    float a0, a1, a2, a3;
+    ptx::unpack16<BF16>(aw[j].x, a0, a1);
+    ptx::unpack16<BF16>(aw[j].y, a2, a3);
+    float4 o;
+    o.x = w * (a0 * nx / na) + one_minus_w * xv[j].x;
+    o.y = w * (a1 * nx / na) + one_minus_w * xv[j].y;
+    o.z = w * (a2 * nx / na) + one_minus_w * xv[j].z;
+    o.w = w * (a3 * nx / na) + one_minus_w * xv[j].w;
+    xr[lane + 32 * j] = o;
+    reinterpret_cast<uint2*>(x16 + static_cast<size_t>(warp) * D)[lane + 32 * j] =
+        make_uint2(ptx::pack16<BF16>(o.x, o.y), ptx::pack16<BF16>(o.z, o.w));
+    s += (o.x + o.y) + (o.z + o.w);
+    q += (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w);
+  }
+  s = warp_sum(s);
+  q = warp_sum(q);
+  float2* o = reinterpret_cast<float2*>(stats_out) + static_cast<size_t>(warp) * np;
+  if (lane < np) o[lane] = (lane == 0) ? make_float2(s, q) : make_float2(0.f, 0.f);
+}
+
 // Validation pass for the 16-bit operand mode (aaclip_saturation_check): counts the elements of a 16-bit activation
 // buffer that hit the format's ceiling -- fp16: +-65504 (what cvt.rn.satfinite stores for anything larger) or a
 // non-finite pattern; bf16: inf / nan (bf16 has fp32's range, so only non-finite inputs get there). n is a multiple of 8
@@ -374,8 +426,10 @@ struct SegPtrs { const float* p[4]; };
 
 // NCH 16-byte feature loads per lane (issued before the first FMA) against the anchor pair [E,2], read as two float4
 // per feature float4 (6 KB, L1-resident)
+// (q accumulates the squared norm of the row for the RAW form of the kernel; dead code otherwise)
 template <int NCH>
-__device__ __forceinline__ void similarity_row(const float* f, const float* t, int lane, int i0, float& s0, float& s1) {
+__device__ __forceinline__ void similarity_row(const float* f, const float* t, int lane, int i0, float& s0, float& s1,
+                                               float& q) {
   const float4* f4 = reinterpret_cast<const float4*>(f);
   const float4* t4 = reinterpret_cast<const float4*>(t);
   float4 fv[NCH];
@@ -390,11 +444,16 @@ __device__ __forceinline__ void similarity_row(const float* f, const float* t, i
     u0 = fmaf(fv[j].y, ta.z, u0); u1 = fmaf(fv[j].y, ta.w, u1);
     s0 = fmaf(fv[j].z, tb.x, s0); s1 = fmaf(fv[j].z, tb.y, s1);
     u0 = fmaf(fv[j].w, tb.z, u0); u1 = fmaf(fv[j].w, tb.w, u1);
+    q += (fv[j].x * fv[j].x + fv[j].y * fv[j].y) + (fv[j].z * fv[j].z + fv[j].w * fv[j].w);
   }
   s0 += u0;
   s1 += u1;
 }
 
+// RAW = true: the feature rows are the un-normalised projections (aaclip_seg_normalize(h, 0)); the kernel applies
+// F.normalize(dim=-1, eps=1e-12) (model/adapter.py:182) itself -- <f/max(|f|,eps), t> -- instead of a separate pass
+// that reads and re-writes all four feature tensors.
+template <bool RAW>
 __global__ void similarity_kernel(SegPtrs seg, const float* __restrict__ text, long long text_bstride,
                                   float* __restrict__ s, int B, int L, int P, int E) {
   ptx::pdl_trigger();
@@ -408,25 +467,28 @@ __global__ void similarity_kernel(SegPtrs seg, const float* __restrict__ text, l
   const int b = static_cast<int>(warp / (static_cast<long long>(P) * L));
   const float* f = seg.p[l] + (static_cast<size_t>(b) * P + p) * E;
   const float* t = text + static_cast<size_t>(b) * text_bstride;
-  float s0 = 0.f, s1 = 0.f;
+  float s0 = 0.f, s1 = 0.f, q = 0.f;
   if (E == 768) {
-    similarity_row<6>(f, t, lane, 0, s0, s1);      // all six 16-byte loads of the lane in flight at once
+    similarity_row<6>(f, t, lane, 0, s0, s1, q);   // all six 16-byte loads of the lane in flight at once
   } else if ((E & 127) == 0) {
-    for (int i0 = 0; i0 < E / 4; i0 += 32) similarity_row<1>(f, t, lane, i0, s0, s1);
+    for (int i0 = 0; i0 < E / 4; i0 += 32) similarity_row<1>(f, t, lane, i0, s0, s1, q);
   } else {
     for (int i = lane; i < E; i += 32) {
       const float fv = f[i];
       const float2 tv = __ldg(reinterpret_cast<const float2*>(t) + i);
       s0 = fmaf(fv, tv.x, s0);
       s1 = fmaf(fv, tv.y, s1);
+      q = fmaf(fv, fv, q);
     }
   }
   s0 = warp_sum(s0);
   s1 = warp_sum(s1);
+  float scale = 100.0f;
+  if constexpr (RAW) scale = 100.0f / fmaxf(sqrtf(warp_sum(q)), 1e-12f);
   if (lane == 0) {
     float* o = s + ((static_cast<size_t>(b) * L + l) * 2) * P + p;
-    o[0] = 100.0f * s0;
-    o[P] = 100.0f * s1;
+    o[0] = scale * s0;
+    o[P] = scale * s1;
   }
 }
 

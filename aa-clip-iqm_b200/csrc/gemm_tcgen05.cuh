@@ -35,6 +35,10 @@ enum EpiMode : int {
   EPI_LN_BIAS_BF16 = 8,       // out_16 = rstd*(acc - mean*colsum) + bias'
   EPI_LN_BIAS_GELU_BF16 = 9,  // out_16 = gelu_erf(...)
   EPI_LN_BIAS_QGELU_BF16 = 10,
+  // residual adapter (model/adapter_modules.py:6-13): out_16 = LeakyReLU(acc) in the operand dtype, plus per-row partial
+  // (sum, sum of squares) of the UNROUNDED values over each 128-column slice (stats_out) -- the blend kernel needs
+  // ||a||_2 of the whole row and then reads a as 2 bytes per element instead of 4
+  EPI_LEAKY_16_SQ = 11,
 };
 
 struct GemmEpi {
@@ -107,6 +111,11 @@ __host__ __device__ constexpr bool epi_has_bias() {
 }
 
 template <int EPI>
+__host__ __device__ constexpr bool epi_has_stats() {   // emits per-row (sum, sumsq) partials of what it wrote
+  return EPI == EPI_BIAS_RESID_F32 || EPI == EPI_LEAKY_16_SQ;
+}
+
+template <int EPI>
 __host__ __device__ constexpr bool epi_is_ln() {
   return EPI == EPI_LN_BIAS_BF16 || EPI == EPI_LN_BIAS_GELU_BF16 || EPI == EPI_LN_BIAS_QGELU_BF16;
 }
@@ -133,11 +142,12 @@ __device__ __forceinline__ float4 epilogue_apply(bool ok, float4 v, int row, int
   if constexpr (EPI == EPI_BIAS_QGELU_BF16 || EPI == EPI_LN_BIAS_QGELU_BF16) {
     v.x = quick_gelu(v.x); v.y = quick_gelu(v.y); v.z = quick_gelu(v.z); v.w = quick_gelu(v.w);
   }
-  if constexpr (EPI == EPI_LEAKY_F32) {
+  if constexpr (EPI == EPI_LEAKY_F32 || EPI == EPI_LEAKY_16_SQ) {
     v.x = v.x > 0.f ? v.x : 0.01f * v.x; v.y = v.y > 0.f ? v.y : 0.01f * v.y;
     v.z = v.z > 0.f ? v.z : 0.01f * v.z; v.w = v.w > 0.f ? v.w : 0.01f * v.w;
   }
-  if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_QGELU_BF16 || epi_is_ln<EPI>()) {
+  if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_QGELU_BF16 || epi_is_ln<EPI>() ||
+                EPI == EPI_LEAKY_16_SQ) {
     const uint2 w = make_uint2(ptx::pack16<BF16>(v.x, v.y), ptx::pack16<BF16>(v.z, v.w));
     if (ok) *reinterpret_cast<uint2*>(e.out_16 + static_cast<size_t>(row) * e.ldo + n) = w;
   } else if constexpr (EPI == EPI_BIAS_RESID_F32) {
@@ -197,31 +207,6 @@ struct GemmPairCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 512 + EPI_WARPS * EPI_STAGE_BYTES + 1024;
 };
 
-// Tail split. The persistent schedule walks the output tiles in waves of `num_pairs`; the last, partial wave leaves
-// most CTA pairs idle (N = 1024: 688 tiles on 74 pairs = 9.3 waves, 52 of 74 pairs idle for a whole tile time). When the
-// tiles of that last wave are at most half as many as the pairs, each of them is processed as two independent
-// half-width units (256 x BN/2: N = BN/2 MMAs, the epilogue warps of column group 0 handle the 128 columns), so the
-// tail costs half a tile time instead of one. Results are bit-identical: every output element is still one
-// accumulator over the same K order.
-#ifndef AACLIP_GEMM_TAIL_SPLIT
-#define AACLIP_GEMM_TAIL_SPLIT 1
-#endif
-struct GemmUnit {
-  int m_pair, n_col, cols;   // output rows 256*m_pair.., columns [n_col, n_col + cols)
-};
-template <int BN>
-__device__ __forceinline__ GemmUnit gemm_unit(int u, int full_tiles, int n_tiles) {
-  int tile = u, half = 0, cols = BN;
-  if (u >= full_tiles) {
-    const int r = u - full_tiles;
-    tile = full_tiles + (r >> 1);
-    half = r & 1;
-    cols = BN / 2;
-  }
-  const int m_pair = tile / n_tiles, n_blk = tile - m_pair * n_tiles;
-  return GemmUnit{m_pair, n_blk * BN + half * (BN / 2), cols};
-}
-
 template <int EPI, bool BF16, int BN>
 // (18 warps are allocated like 20: 96 registers per thread at most -- __maxnreg__(112) is refused at launch)
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GemmPairCfg<BN>::THREADS, 1)
@@ -246,11 +231,6 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const int n_tiles = N / BN;
   const int num_tiles = m_pairs * n_tiles;
   const int num_kb = K / BK;
-  // work units: whole tiles, then (tail split) the tiles of the last partial wave as two half-width units each
-  const int tail_tiles = num_tiles % num_pairs;
-  const bool split_tail = AACLIP_GEMM_TAIL_SPLIT && tail_tiles > 0 && 2 * tail_tiles <= num_pairs && num_tiles > num_pairs;
-  const int full_tiles = split_tail ? num_tiles - tail_tiles : num_tiles;
-  const int num_units = full_tiles + 2 * (num_tiles - full_tiles);
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_a);
@@ -287,12 +267,10 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     int stage = 0;
     uint32_t phase = 0;
     const uint32_t full0_leader = ptx::mapa_u32(ptx::smem_u32(&full_bar[0]), 0);
-    for (int u = pair; u < num_units; u += num_pairs) {
-      const GemmUnit un = gemm_unit<BN>(u, full_tiles, n_tiles);
-      const int m_row = (2 * un.m_pair + static_cast<int>(rank)) * BM;
-      // this CTA's half of the unit's W rows. (A half-width unit still moves the full BN/2-row box: only its first
-      // BN/4 rows are read by the MMAs; rows past N are zero-filled by TMA.)
-      const int n_row = un.n_col + static_cast<int>(rank) * (un.cols / 2);
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      const int m_pair = tile / n_tiles, n_blk = tile - m_pair * n_tiles;
+      const int m_row = (2 * m_pair + static_cast<int>(rank)) * BM;
+      const int n_row = n_blk * BN + static_cast<int>(rank) * (BN / 2);
       for (int kb = 0; kb < num_kb; ++kb) {
         ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
         if (ptx::elect_one()) {
@@ -308,15 +286,13 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA; warp-uniform loop, one elected lane issues) =====================
     if (rank == 0) {
-      constexpr uint32_t idesc_full = ptx::make_idesc_16(2 * BM, BN, 0, BF16);
-      constexpr uint32_t idesc_half = ptx::make_idesc_16(2 * BM, BN / 2, 0, BF16);
+      constexpr uint32_t idesc = ptx::make_idesc_16(2 * BM, BN, 0, BF16);
       const uint32_t smem_base = ptx::smem_u32(smem);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int u = pair; u < num_units; u += num_pairs) {
-        const uint32_t idesc = u >= full_tiles ? idesc_half : idesc_full;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
         ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -349,18 +325,9 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const uint32_t stage_u32 = ptx::smem_u32(smem + STAGES * STAGE_BYTES + 512 + e * C::EPI_STAGE_BYTES);
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int u = pair; u < num_units; u += num_pairs) {
-      const GemmUnit un = gemm_unit<BN>(u, full_tiles, n_tiles);
-      const int row0 = (2 * un.m_pair + static_cast<int>(rank)) * BM + q * 32;
-      const int n_base = un.n_col + cg * COLS_PER_WARP;      // first column of this warp's slice
-      if (cg * COLS_PER_WARP >= un.cols) {
-        // half-width unit: this warp's column group does not exist. Keep the accumulator hand-shake in step.
-        ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa_u32(ptx::smem_u32(&tmem_empty_bar[acc]), 0));
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-        continue;
-      }
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      const int m_pair = tile / n_tiles, n_blk = tile - m_pair * n_tiles;
+      const int row0 = (2 * m_pair + static_cast<int>(rank)) * BM + q * 32;
       if constexpr (EPI == EPI_BIAS_RESID_F32 && AACLIP_GEMM_RESID_PREFETCH)
         // The residual rows this warp will add come from HBM (the stream is 180 MB, far beyond L2): pull them into L2
         // now, while the MMAs of this tile are still running, so that the loads in the chunk loop below are L2 hits
@@ -370,7 +337,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         // registers, both measured slower -- tools/experiments/README.md. ncu: the out-projection moves 4.5 TB/s of
         // DRAM traffic in isolation, 70 % of the measured copy bandwidth; it is bandwidth-, not latency-bound.)
         if (num_kb <= AACLIP_GEMM_RESID_PREFETCH_MAXKB && row0 + lane < M) {
-          const float* rp = epi.out_f32 + static_cast<size_t>(row0 + lane) * epi.ldo + n_base;
+          const float* rp = epi.out_f32 + static_cast<size_t>(row0 + lane) * epi.ldo + n_blk * BN + cg * COLS_PER_WARP;
 #pragma unroll
           for (int i = 0; i < COLS_PER_WARP / 32; ++i) ptx::prefetch_l2(rp + i * 32);
         }
@@ -401,7 +368,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const int sub = lane >> 3, unit = lane & 7;
       // coalesced domain: this thread handles rows row0 + j*4 + sub (j < 8) in every 32-column chunk
       float mean_j[8], rstd_j[8];   // EPI_LN_*: LayerNorm statistics of its 8 rows
-      float st_s[8], st_q[8];       // EPI_BIAS_RESID_F32 + stats_out: running sum / sum of squares of the new rows
+      float st_s[8], st_q[8];       // epi_has_stats + stats_out: running sum / sum of squares of the rows written
       if constexpr (epi_is_ln<EPI>()) {
         // the coalesced-domain owners of a row pick its statistics up with one shuffle each
 #pragma unroll
@@ -410,13 +377,13 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           rstd_j[j] = __shfl_sync(0xffffffffu, rstd, j * 4 + sub);
         }
       }
-      if constexpr (EPI == EPI_BIAS_RESID_F32) {
+      if constexpr (epi_has_stats<EPI>()) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) st_s[j] = st_q[j] = 0.f;
       }
 #pragma unroll 1
       for (int c = 0; c < CHUNKS; ++c) {
-        const int n = n_base + c * 32 + unit * 4;
+        const int n = n_blk * BN + cg * COLS_PER_WARP + c * 32 + unit * 4;
         float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), cs4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if constexpr (epi_has_bias<EPI>()) bias4 = __ldg(reinterpret_cast<const float4*>(epi.bias + n));
         if constexpr (epi_is_ln<EPI>()) cs4 = __ldg(reinterpret_cast<const float4*>(epi.colsum + n));
@@ -455,6 +422,10 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const float4 x = epilogue_apply<EPI, BF16>(ok, v, row0 + rr, n, epi, bias4, j < 4 ? resid_a[j & 3] : resid_b[j & 3]);
             st_s[j] += (x.x + x.y) + (x.z + x.w);      // rows >= M accumulate garbage that is never stored
             st_q[j] += (x.x * x.x + x.y * x.y) + (x.z * x.z + x.w * x.w);
+          } else if constexpr (EPI == EPI_LEAKY_16_SQ) {
+            const float4 x = epilogue_apply<EPI, BF16>(ok, v, row0 + rr, n, epi, bias4);
+            st_s[j] += (x.x + x.y) + (x.z + x.w);
+            st_q[j] += (x.x * x.x + x.y * x.y) + (x.z * x.z + x.w * x.w);
           } else if constexpr (epi_is_ln<EPI>()) {
             epilogue_apply<EPI, BF16>(ok, v, row0 + rr, n, epi, bias4, make_float4(0.f, 0.f, 0.f, 0.f), cs4, mean_j[j],
                                       rstd_j[j]);
@@ -464,13 +435,13 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
         __syncwarp();
       }
-      if constexpr (EPI == EPI_BIAS_RESID_F32) {
+      if constexpr (epi_has_stats<EPI>()) {
         if (epi.stats_out != nullptr) {
           // partial (sum, sumsq) of this warp's COLS_PER_WARP columns for each of its 32 rows. The 8 lanes of a row
           // group (unit = 0..7) hold 8 rows x 2 values each; a halving butterfly (each xor step exchanges half of the
           // still-live values) leaves lane `unit` with the complete sums of row j = unit: 14 shuffles instead of 48,
           // every lane stores one row. Fixed order: bit-reproducible and batch-invariant.
-          const int np = N / COLS_PER_WARP, pi = n_base / COLS_PER_WARP;
+          const int np = N / COLS_PER_WARP, pi = n_blk * C::COL_GROUPS + cg;
           float v[16];
 #pragma unroll
           for (int j = 0; j < 8; ++j) { v[j] = st_s[j]; v[8 + j] = st_q[j]; }

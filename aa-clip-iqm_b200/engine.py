@@ -177,11 +177,13 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, skip_cls
 
 
 def score_maps(seg: Sequence[torch.Tensor], text: torch.Tensor, img_size: int, test: bool = True, ksize: int = 7,
-               sigma: float = 1.0, det: Optional[torch.Tensor] = None
+               sigma: float = 1.0, det: Optional[torch.Tensor] = None, raw: bool = False
                ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     """Similarity -> (blur) -> bilinear upsample (-> level sum | softmax) and optional image score (aaclip_score_maps).
 
     seg: list of [B,P,E] fp32 unit-norm patch features; text: [E,2] or [B,E,2].
+    raw=True: seg holds the un-normalised projections of a tower with ``seg_normalize(False)``; the similarity kernel
+    applies F.normalize itself (aaclip_score_maps_raw).
     test=True  -> maps [B,S,S], summed over the given levels; test=False -> one level, maps [B,2,S,S].
     """
     _need_cuda(text, *seg)
@@ -204,11 +206,28 @@ def score_maps(seg: Sequence[torch.Tensor], text: torch.Tensor, img_size: int, t
     if det is not None:
         det = det.contiguous().float()
         score = torch.empty((B,), dtype=torch.float32, device=text.device)
+    fn = lib.aaclip_score_maps_raw if raw else lib.aaclip_score_maps
     _lib.check(
-        lib.aaclip_score_maps(_ptr_array(seg), L, _ptr(text), per_image, B, G, E, img_size, int(test), ksize,
-                              float(sigma), _ptr(ws), ws_bytes, _ptr(maps), _ptr(det), _ptr(score), _stream()),
+        fn(_ptr_array(seg), L, _ptr(text), per_image, B, G, E, img_size, int(test), ksize,
+           float(sigma), _ptr(ws), ws_bytes, _ptr(maps), _ptr(det), _ptr(score), _stream()),
         "aaclip_score_maps")
     return maps, score
+
+
+def adapter(x: torch.Tensor, x16: torch.Tensor, w16: torch.Tensor, weight: float) -> torch.Tensor:
+    """Residual adapter + blend of one block in place (aaclip_adapter): x [M,D] fp32, x16 its raw 16-bit copy (updated),
+    w16 [D,D] packed fc.0.weight. Returns the LayerNorm partials [M, D/stat_columns, 2] of the new x."""
+    _need_cuda(x, x16, w16)
+    assert x.dtype == torch.float32 and x16.dtype == w16.dtype and x.is_contiguous() and x16.is_contiguous()
+    M, D = x.shape
+    lib = _lib.load()
+    np_ = D // lib.aaclip_stat_columns()
+    stats = torch.empty((M, np_, 2), dtype=torch.float32, device=x.device)
+    ws_bytes = M * D * 2 + M * np_ * 8
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+    _lib.check(lib.aaclip_adapter(_dt(x16), _ptr(x), _ptr(x16), _ptr(w16.contiguous()), M, D, float(weight), _ptr(ws),
+                                  ws_bytes, _ptr(stats), _stream()), "aaclip_adapter")
+    return stats
 
 
 # ---------------------------------------------------------------------------------------- the tower
@@ -339,6 +358,12 @@ class AaclipEngine:
         if want_query:
             return seg, det, tokens, cls, query
         return seg, det, tokens, cls
+
+    def seg_normalize(self, on: bool = True):
+        """on=False: forward() returns the raw seg projections (no F.normalize pass); hand them to
+        ``score_maps(..., raw=True)``, whose similarity kernel normalises in the one pass it makes anyway."""
+        _lib.check(self._lib.aaclip_seg_normalize(self._h, int(on)), "aaclip_seg_normalize")
+        self.seg_is_raw = not on
 
     # -- per-kernel-class device timing (bench.py roofline)
     def profile_enable(self, on: bool = True):

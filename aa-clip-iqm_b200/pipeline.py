@@ -33,6 +33,9 @@ class AnomalyPredictor:
         self.engine.load_state_dict(state_dict)
         if self.engine.missing:
             raise RuntimeError(f"{self.engine.missing} weight tensors of the visual path are missing from the state dict")
+        # the patch features go straight into the scoring call: skip the stand-alone F.normalize passes over them
+        # (model/adapter.py:182) and let the similarity kernel normalise in the pass it makes anyway
+        self.engine.seg_normalize(False)
         self.text = text.to(self.device, torch.float32).contiguous()
         self._stage_in: Optional[torch.Tensor] = None
         self._stage_guard = _engine.StreamGuard()       # _stage_in is shared by predict_u8 / predict_host calls
@@ -43,7 +46,7 @@ class AnomalyPredictor:
         """images [B,3,S,S] fp32 already on the GPU -> (maps [B,S,S], scores [B]) on the GPU."""
         seg, det, _, _ = self.engine.forward(images)
         k, s = DOMAIN_BLUR[self.domain]
-        return _engine.score_maps(seg, self.text, self.img_size, test=True, ksize=k, sigma=s, det=det)
+        return _engine.score_maps(seg, self.text, self.img_size, test=True, ksize=k, sigma=s, det=det, raw=True)
 
     # -- the same step as a CUDA graph (one launch per batch instead of 157)
     def capture(self, batch: int) -> "CapturedStep":

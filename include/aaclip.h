@@ -150,6 +150,18 @@ int aaclip_score_maps(const float* const* seg, int32_t n_levels, const float* te
                       void* stream);
 
 /* Columns covered by one LayerNorm partial written by aaclip_gemm16_resid (= accumulator columns per epilogue warp). */
+/* The same call for seg tensors that are NOT unit-norm (a tower with aaclip_seg_normalize(h, 0)): the similarity
+ * kernel applies F.normalize(dim=-1, eps=1e-12) (model/adapter.py:182) itself, in the one pass it makes over the
+ * features, instead of a separate normalisation pass that reads and re-writes all of them. */
+int aaclip_score_maps_raw(const float* const* seg, int32_t n_levels, const float* text, int32_t text_per_image,
+                          int32_t B, int32_t G, int32_t E, int32_t S, int32_t test_mode, int32_t ksize, float sigma,
+                          void* workspace, size_t workspace_bytes, float* maps_out, const float* det, float* score_out,
+                          void* stream);
+
+/* enable = 0: aaclip_forward leaves seg_out as the raw projections tokens W^T (no F.normalize); det_out is unchanged.
+ * For callers that hand seg_out straight to aaclip_score_maps_raw. Default 1 = the reference's return values. */
+int aaclip_seg_normalize(AaclipHandle* h, int32_t enable);
+
 int aaclip_stat_columns(void);
 
 /* Kernel launches enqueued by the last aaclip_forward on this handle (for bench.py's gpu_launches). */
@@ -304,6 +316,14 @@ int aaclip_gemm16_ln(int32_t dtype, const void* A, const void* W16, int32_t M, i
  * LayerNorm partials stats_out [M][N/aaclip_stat_columns()][2] (the inputs of the next folded-LN GEMM). */
 int aaclip_gemm16_resid(int32_t dtype, const void* A, const void* W, int32_t M, int32_t N, int32_t K,
                         const float* bias, float* x, void* x16_out, float* stats_out, int32_t ldo, void* stream);
+
+/* Residual adapter + blend of one block (model/adapter.py:163-170, model/adapter_modules.py:6-13), exactly the two
+ * launches aaclip_forward issues:  a = LeakyReLU_0.01(x W^T);  a <- a |x|_2 / |a|_2 per row;  x <- weight a + (1-weight) x.
+ *   x [M,D] fp32 in place;  x16 [M,D] `dtype`: in = the raw 16-bit copy of x (the GEMM operand), out = copy of the new x;
+ *   W16 [D,D] `dtype` (aaclip_pack16 of fc.0.weight);  stats_out [M][D/aaclip_stat_columns()][2] LayerNorm partials of
+ *   the new x;  workspace >= M*D*2 + M*(D/aaclip_stat_columns())*8 bytes.  D in {768, 1024}. */
+int aaclip_adapter(int32_t dtype, float* x, void* x16, const void* W16, int32_t M, int32_t D, float weight,
+                   void* workspace, size_t workspace_bytes, float* stats_out, void* stream);
 
 /* Fused multi-head attention: qkv `dtype` [B,N,3*D] -> out `dtype` [B,N,D]; head dim 64; softmax scale 1/8. */
 int aaclip_attention(int32_t dtype, const void* qkv, void* out, int32_t B, int32_t N, int32_t D, int32_t causal,

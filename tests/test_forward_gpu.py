@@ -308,13 +308,20 @@ def test_full_size_batch_properties():
     halves = [pred.predict_device(images[k:k + 16]) for k in (0, 16)]
     halves = [(m.clone(), s.clone()) for m, s in halves]
     assert torch.equal(torch.cat([h[0] for h in halves]), m_a) and torch.equal(torch.cat([h[1] for h in halves]), s_a)
+    assert pred.launches_per_batch == 150      # 147 tower launches + similarity, anomaly-map and image-score kernels
+    # the predictor runs the tower with raw seg projections (the similarity kernel normalises); with the reference's
+    # return values switched back on, the features are unit-norm and the maps agree with the fused route
+    pred.engine.seg_normalize(True)
     seg, det, _, _ = pred.engine.forward(images)
     for f in seg:
         n = f.norm(dim=-1)
         assert torch.allclose(n, torch.ones_like(n), atol=1e-5)
+    from aaclip_b200 import engine as _engine
+    m_n, s_n = _engine.score_maps(seg, pred.text, S, test=True, ksize=7, sigma=1.0, det=det)
+    assert (m_n - m_a).abs().max().item() < 1e-4 and torch.equal(s_n, s_a)
+    pred.engine.seg_normalize(False)
     assert torch.isfinite(m_a).all() and m_a.abs().max().item() <= 4 * 100.5
     assert ((s_a >= 0) & (s_a <= 1)).all()
-    assert pred.launches_per_batch == 154      # 151 tower launches + similarity, anomaly-map and image-score kernels
 
 
 def test_argument_errors():

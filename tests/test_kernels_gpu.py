@@ -167,6 +167,53 @@ def test_score_maps_against_oracle(eng):
     assert (m.cpu() - ref).abs().max().item() < 1e-4
 
 
+def test_score_maps_raw_normalises_in_the_similarity_pass(eng):
+    """aaclip_score_maps_raw on un-normalised projections == aaclip_score_maps on F.normalize of them (the oracle's
+    order of operations, model/adapter.py:182 then forward_utils.py:199), including an all-zero row (eps 1e-12)."""
+    _lib, engine = eng
+    B, G, E, S = 2, 24, 768, 336
+    raw = [torch.randn(B, G * G, E, device="cuda") * (0.3 + l) for l in range(4)]
+    raw[1][0, 5] = 0.0
+    text = F.normalize(torch.randn(B, E, 2, device="cuda"), dim=1)
+    det = F.normalize(torch.randn(B, G * G, E, device="cuda"), dim=-1).mean(1)
+    from oracle import aaclip_oracle as orc
+    a, sa = engine.score_maps(raw, text, S, test=True, ksize=7, sigma=1.0, det=det, raw=True)
+    ref = orc.anomaly_maps([F.normalize(r, dim=-1).cpu() for r in raw], text.cpu(), S, "Industrial")
+    assert torch.isfinite(a).all()
+    assert (a.cpu() - ref).abs().max().item() < 1e-4
+    b, sb = engine.score_maps([F.normalize(r, dim=-1) for r in raw], text, S, test=True, ksize=7, sigma=1.0, det=det)
+    assert (a - b).abs().max().item() < 5e-5 and torch.equal(sa, sb)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("M,D", [(300, 1024), (2740, 1024), (77 * 3, 768)])
+def test_adapter_gemm_and_blend(eng, M, D, dtype):
+    """aaclip_adapter (GEMM with the LeakyReLU + 16-bit store + sum-of-squares epilogue, then the blend kernel) against
+    model/adapter.py:163-170 in fp32 on the same 16-bit operands; also the outputs the next block consumes: the raw
+    16-bit copy of the new x and its LayerNorm partials."""
+    _lib, engine = eng
+    g = torch.Generator(device="cuda").manual_seed(M + D)
+    x = torch.randn(M, D, device="cuda", generator=g) * 1.3 + 0.2
+    w = (torch.randn(D, D, device="cuda", generator=g) * D ** -0.5).to(dtype)
+    x16 = x.to(dtype)
+    a = F.leaky_relu(x16.float() @ w.float().t(), 0.01)
+    a = a * x.norm(dim=-1, keepdim=True) / a.norm(dim=-1, keepdim=True)
+    ref = 0.1 * a + 0.9 * x
+    xo, x16o = x.clone(), x16.clone()
+    stats = engine.adapter(xo, x16o, w, 0.1)
+    tol = 4 * EPS[dtype] * 0.1 * a.abs().max().item() + 1e-5      # a is rounded once to 16 bits, then weighted by 0.1
+    assert (xo - ref).abs().max().item() < tol
+    assert torch.equal(x16o, xo.to(dtype))
+    cols = _lib.load().aaclip_stat_columns()
+    assert stats.shape == (M, D // cols, 2)
+    assert torch.allclose(stats[..., 0].sum(1), xo.sum(1), atol=2e-3, rtol=1e-5)
+    assert torch.allclose(stats[..., 1].sum(1), (xo * xo).sum(1), atol=2e-3, rtol=1e-5)
+    # row-local: a row alone gives the same bits as the row inside the batch
+    x1, x161 = x[7:8].clone(), x16[7:8].clone()
+    engine.adapter(x1, x161, w, 0.1)
+    assert torch.equal(x1[0], xo[7])
+
+
 # ---------------------------------------------------------------------------------------------------------
 # LayerNorm folded into the GEMMs that produce / consume the residual stream (model/transformer.py:245-254)
 @pytest.mark.parametrize("dtype", DTYPES)

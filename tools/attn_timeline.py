@@ -18,29 +18,14 @@ for _ in range(3):
 torch.cuda.synchronize()
 buf = (ctypes.c_longlong * (2 * 16 * 8))()
 assert lib.aaclip_debug_attn_timeline(buf) == 0
-names = ["loop", "s_full", "ld+free", "max", "exp0", "o_full(+write-back)", "exp1", "arrive"]
-NT = 16   # the first 16 tiles CTA 5 processes (11 tiles per item @1370 tokens: one item boundary is inside)
+names = ["loop", "s_full", "ld+free", "max", "exp0", "o_full", "exp1", "arrive"]
 t0 = min(buf[(t * 16 + 0) * 8 + 0] for t in range(2))
 for t in range(2):
     print(f"Q tile {t}: (cycles since the first stamp; then deltas between consecutive stamps)")
     prev = None
-    for j in range(NT):
+    for j in range(11):
         row = [buf[(t * 16 + j) * 8 + k] for k in range(8)]
         d = [row[0] - (prev if prev is not None else row[0])] + [row[k] - row[k - 1] for k in range(1, 8)]
         prev = row[7]
-        print(f"  g={j:2d} start {row[0] - t0:7d}  " + "  ".join(f"{n} {x:5d}" for n, x in zip(names, d)) +
+        print(f"  j={j:2d} start {row[0] - t0:7d}  " + "  ".join(f"{n} {x:5d}" for n, x in zip(names, d)) +
               f"   total {row[7] - row[0]:5d}")
-
-# the MMA issuer warps of the same CTA: absolute times (same clock), so that the hand-overs can be followed:
-# softmax "arrive" (p_full) -> issuer "p_full seen" -> "PV issued"
-mb = (ctypes.c_longlong * (2 * 16 * 8))()
-if hasattr(lib, "aaclip_debug_attn_timeline_mma") and lib.aaclip_debug_attn_timeline_mma(mb) == 0:
-    for t in range(2):
-        print(f"MMA issuer of Q tile {t}: S(g): k_full wait, s_free wait, issue;  PV(g): v_full+p_full wait, issue; "
-              f"[softmax p_full arrive -> issuer saw it -> PV issued]")
-        for j in range(NT):
-            row = [mb[(t * 16 + j) * 8 + k] for k in range(7)]
-            arrive = buf[(t * 16 + j) * 8 + 7]
-            print(f"  g={j:2d} S start {row[0] - t0:7d}  k_full {row[1] - row[0]:5d}  s_free {row[2] - row[1]:5d}  issue {row[3] - row[2]:5d}"
-                  f"   PV start {row[4] - t0:7d}  wait {row[5] - row[4]:5d}  issue {row[6] - row[5]:5d}"
-                  f"   [arrive@{arrive - t0:7d}  seen +{row[5] - arrive:5d}  issued +{row[6] - arrive:5d}]")
