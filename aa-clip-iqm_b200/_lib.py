@@ -213,6 +213,8 @@ def _declare(lib):
     lib.aaclip_ln_fold.argtypes = [i32, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp]
     lib.aaclip_gemm16_ln.restype = i32
     lib.aaclip_gemm16_ln.argtypes = [i32, vp, vp, i32, i32, i32, i32, vp, vp, vp, i32, i32, vp, i32, vp]
+    lib.aaclip_gemm16_ln_tok.restype = i32
+    lib.aaclip_gemm16_ln_tok.argtypes = [i32, vp, vp, i32, i32, i32, i32, vp, vp, vp, i32, i32, i32, vp, i32, vp]
     lib.aaclip_gemm16_resid.restype = i32
     lib.aaclip_gemm16_resid.argtypes = [i32, vp, vp, i32, i32, i32, vp, vp, vp, vp, i32, vp]
     lib.aaclip_attention.restype = i32
@@ -235,7 +237,7 @@ EXPORTED_SYMBOLS = [
     "aaclip_resample_ksize", "aaclip_resample_coeffs_host", "aaclip_preprocess_workspace_bytes", "aaclip_preprocess_u8",
     "aaclip_finalize_weights", "aaclip_saturation_check", "aaclip_saturation_count",
     "aaclip_text_finalize_weights", "aaclip_text_saturation_check", "aaclip_text_saturation_count",
-    "aaclip_score_maps_raw", "aaclip_seg_normalize", "aaclip_adapter",
+    "aaclip_score_maps_raw", "aaclip_seg_normalize", "aaclip_adapter", "aaclip_gemm16_ln_tok",
 ]
 
 

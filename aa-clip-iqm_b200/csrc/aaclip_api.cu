@@ -208,6 +208,8 @@ int launch_gemm(int epi_mode, bool bf16, const void* A, const void* W, int M, in
     AACLIP_GEMM_CASE(EPI_LN_BIAS_GELU_BF16)
     AACLIP_GEMM_CASE(EPI_LN_BIAS_QGELU_BF16)
     AACLIP_GEMM_CASE(EPI_LEAKY_16_SQ)
+    AACLIP_GEMM_CASE(EPI_LN_F32_TOK)
+    AACLIP_GEMM_CASE(EPI_LN_LEAKY_F32_TOK)
 #undef AACLIP_GEMM_CASE
     default: return fail(AACLIP_EINVAL, "gemm: unknown epilogue %d", epi_mode);
   }
@@ -510,6 +512,11 @@ struct AaclipHandle {
   uint16_t* w_det;                   // [E,W]
   std::vector<uint16_t*> w_query;    // [query_dim,W] each (IQM query_adapters; optional)
   std::vector<bool> have_query;
+  // ln_post folded into the token-tap projections (16-bit modes): W' = W diag(gamma_post) in w_seg / w_det / w_query,
+  // plus colsum(W') and bias' = W beta_post per projection. Index: 0..n_levels-1 seg, n_levels det, then query.
+  struct ProjFold { float* stage = nullptr; uint16_t* w16 = nullptr; float* colsum = nullptr; float* bias_f = nullptr; int rows = 0; };
+  std::vector<ProjFold> proj;
+  float* zero_bias = nullptr;        // max(E, query_dim) zeros: the projections have no bias of their own
   std::vector<std::string> missing;
   int last_launches = 0;
   bool seg_normalize = true;   // aaclip_seg_normalize: false = seg_out stays un-normalised (the scoring call normalises)
@@ -745,6 +752,11 @@ int aaclip_create(const AaclipCfg* cfg, AaclipHandle** out) {
   std::vector<size_t> o_qry(c.query_dim > 0 ? c.n_levels : 0);
   for (size_t l = 0; l < o_qry.size(); ++l) o_qry[l] = plan.take<uint8_t>((size_t)c.query_dim * W * wb);
   const size_t o_sat = plan.take<unsigned long long>(1);
+  const size_t n_proj = (size_t)c.n_levels + 1 + o_qry.size();
+  const size_t proj_rows_max = E > (size_t)c.query_dim ? E : (size_t)c.query_dim;
+  std::vector<size_t> o_pcs(n_proj), o_pbf(n_proj);
+  for (size_t i = 0; i < n_proj; ++i) { o_pcs[i] = plan.take<float>(proj_rows_max); o_pbf[i] = plan.take<float>(proj_rows_max); }
+  const size_t o_zero = plan.take<float>(proj_rows_max);
 
   h->arena_bytes = plan.off;
   cudaError_t e = cudaMalloc(&h->arena, h->arena_bytes);
@@ -771,6 +783,15 @@ int aaclip_create(const AaclipCfg* cfg, AaclipHandle** out) {
   for (size_t l = 0; l < o_qry.size(); ++l) h->w_query.push_back((uint16_t*)(a + o_qry[l]));
   h->have_query.assign(o_qry.size(), false);
   h->sat_counter = (unsigned long long*)(a + o_sat);      // zeroed with the arena
+  h->proj.resize(n_proj);
+  for (size_t i = 0; i < n_proj; ++i) {
+    AaclipHandle::ProjFold& pf = h->proj[i];
+    pf.colsum = (float*)(a + o_pcs[i]); pf.bias_f = (float*)(a + o_pbf[i]);
+    if (i < (size_t)c.n_levels) { pf.w16 = h->w_seg[i]; pf.rows = (int)E; }
+    else if (i == (size_t)c.n_levels) { pf.w16 = h->w_det; pf.rows = (int)E; }
+    else { pf.w16 = h->w_query[i - c.n_levels - 1]; pf.rows = c.query_dim; }
+  }
+  h->zero_bias = (float*)(a + o_zero);
 
   // the set of tensors that must arrive through aaclip_set_weight before forward may run
   auto need = [&](const std::string& k) { h->missing.push_back(k); };
@@ -788,6 +809,7 @@ int aaclip_create(const AaclipCfg* cfg, AaclipHandle** out) {
 void aaclip_destroy(AaclipHandle* h) {
   if (h == nullptr) return;
   free_block_staging(h->blk);
+  for (auto& pf : h->proj) if (pf.stage) cudaFree(pf.stage);
   if (h->arena) cudaFree(h->arena);
   for (auto& r : h->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   delete h;
@@ -824,8 +846,28 @@ int aaclip_set_weight(AaclipHandle* h, const char* name, const float* data, cons
   if (k == "positional_embedding") return copy_f32(h->pos, (int64_t)h->N * W, k);
   if (k == "ln_pre.weight") return copy_f32(h->lnpre_g, W, k);
   if (k == "ln_pre.bias") return copy_f32(h->lnpre_b, W, k);
+  if ((k == "ln_post.weight" || k == "ln_post.bias") && h->folded)
+    return fail(AACLIP_ESTATE, "%s: ln_post has already been folded into the token-tap projections (first forward ran); "
+                               "create a new handle to load different backbone weights", name);
   if (k == "ln_post.weight") return copy_f32(h->lnpost_g, W, k);
   if (k == "ln_post.bias") return copy_f32(h->lnpost_b, W, k);
+  // seg / det / query projections: ln_post is folded into them (16-bit modes). Before the fold the fp32 weight is
+  // staged; a projection that arrives after it (trained heads re-fed, late query adapters) is folded on the spot.
+  auto proj = [&](size_t pi, uint16_t* dst, int64_t R, const std::string& key) -> int {
+    if (h->f32) return pack(dst, R, W, W, key);
+    if (n != R * W) return fail(AACLIP_EINVAL, "%s: expected %lld x %lld elements, got %lld", name, (long long)R, (long long)W, (long long)n);
+    AaclipHandle::ProjFold& pf = h->proj[pi];
+    if (h->folded) {
+      if (h->bf16) ln_fold_kernel<true><<<(R + 7) / 8, 256, 0, st>>>(data, h->zero_bias, h->lnpost_g, h->lnpost_b, pf.w16, pf.colsum, pf.bias_f, (int)R, (int)W);
+      else ln_fold_kernel<false><<<(R + 7) / 8, 256, 0, st>>>(data, h->zero_bias, h->lnpost_g, h->lnpost_b, pf.w16, pf.colsum, pf.bias_f, (int)R, (int)W);
+      LAUNCH_CHECK("ln_fold_kernel");
+    } else {
+      if (pf.stage == nullptr) CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&pf.stage), R * W * sizeof(float)));
+      CUDA_TRY(cudaMemcpyAsync(pf.stage, data, R * W * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
+    if (!key.empty()) erase_key(h->missing, key);
+    return AACLIP_OK;
+  };
 
   int idx = -1;
   char tail[96];
@@ -842,14 +884,14 @@ int aaclip_set_weight(AaclipHandle* h, const char* name, const float* data, cons
   if (sscanf(k.c_str(), "image_adapter.seg_proj.%d.fc.%95s", &idx, tail) == 2) {
     if (idx < 0 || idx >= c.n_levels) return fail(AACLIP_EINVAL, "%s: seg_proj index out of range", name);
     if (strcmp(tail, "weight") != 0 && strcmp(tail, "0.weight") != 0) return fail(AACLIP_EINVAL, "%s: unknown tensor", name);
-    return pack(h->w_seg[idx], E, W, W, "seg." + std::to_string(idx));
+    return proj((size_t)idx, h->w_seg[idx], E, "seg." + std::to_string(idx));
   }
-  if (k == "image_adapter.det_proj.fc.weight" || k == "image_adapter.det_proj.fc.0.weight") return pack(h->w_det, E, W, W, "det");
+  if (k == "image_adapter.det_proj.fc.weight" || k == "image_adapter.det_proj.fc.0.weight") return proj((size_t)c.n_levels, h->w_det, E, "det");
   if (sscanf(k.c_str(), "query_adapters.%d.fc.%95s", &idx, tail) == 2) {
     if (c.query_dim <= 0) return fail(AACLIP_EINVAL, "%s: the handle was created with query_dim = 0", name);
     if (idx < 0 || idx >= c.n_levels) return fail(AACLIP_EINVAL, "%s: query_adapters index out of range", name);
     if (strcmp(tail, "weight") != 0 && strcmp(tail, "0.weight") != 0) return fail(AACLIP_EINVAL, "%s: unknown tensor", name);
-    if (int rc = pack(h->w_query[idx], c.query_dim, W, W, "")) return rc;
+    if (int rc = proj((size_t)c.n_levels + 1 + idx, h->w_query[idx], c.query_dim, "")) return rc;
     h->have_query[idx] = true;
     return AACLIP_OK;
   }
@@ -990,7 +1032,6 @@ int aaclip_forward(AaclipHandle* h, const float* images, int32_t B, void* worksp
   if ((rc = aaclip_finalize_weights(h, stream))) return rc;
   uint8_t* wsb = static_cast<uint8_t*>(workspace);
   uint16_t* patchA = (uint16_t*)(wsb + ws.patchA);
-  uint16_t* tok = (uint16_t*)(wsb + ws.tok);
   float* detbuf = (float*)(wsb + ws.det);
   const bool bf = h->bf16;
   BlockRun run;
@@ -1058,21 +1099,26 @@ int aaclip_forward(AaclipHandle* h, const float* images, int32_t B, void* worksp
   for (int i = 0; i < c.layers; ++i) {
     if ((rc = run.run(h->blk[i], i < c.adapt_until ? h->w_adapter[i] : nullptr, c.adapt_weight))) return rc;
     if (level_idx < c.n_levels && c.levels[level_idx] == i + 1) {
+      // token tap: x[1:] of every image -> ln_post -> projections (model/adapter.py:171-184). ln_post is folded into
+      // the projections: they read the raw 16-bit residual stream (all N rows per image) and the epilogue drops the CLS
+      // rows; the fp32 ln_post tokens are only materialised when the caller asks for them (host IQM branch).
       float* tok_f32 = (tokens_out != nullptr) ? tokens_out[level_idx] : nullptr;
-      if ((rc = lnorm(x, h->lnpost_g, h->lnpost_b, tok, tok_f32, MP, P, nullptr))) return rc;
-      run.sat.scan(tok, static_cast<size_t>(MP) * W, st);
-      const int proj_epi = c.proj_relu ? EPI_LEAKY_F32 : EPI_F32;
-      { GemmEpi e; e.out_f32 = seg_out[level_idx]; e.ldo = E;
-        if ((rc = run.gemm(proj_epi, tok, h->w_seg[level_idx], MP, E, W, e))) return rc; }
+      if (tok_f32 != nullptr && (rc = lnorm(x, h->lnpost_g, h->lnpost_b, nullptr, tok_f32, MP, P, nullptr))) return rc;
+      const int proj_epi = c.proj_relu ? EPI_LN_LEAKY_F32_TOK : EPI_LN_F32_TOK;
+      auto tap = [&](size_t pi, float* out, int cols) -> int {
+        const AaclipHandle::ProjFold& pf = h->proj[pi];
+        GemmEpi e; e.out_f32 = out; e.ldo = cols; e.patches = P;
+        e.bias = pf.bias_f; e.colsum = pf.colsum; e.stats = run.stats; e.n_partials = kStatPartials(W); e.inv_width = 1.0f / W;
+        return run.gemm(proj_epi, run.x16, pf.w16, M, cols, W, e);
+      };
+      if ((rc = tap((size_t)level_idx, seg_out[level_idx], E))) return rc;
       if (query_out != nullptr && query_out[level_idx] != nullptr) {
-        // IQM branch: query_adapters[l] (model/adapter.py:202-205) on the same 16-bit ln_post tokens, same epilogue
-        GemmEpi e; e.out_f32 = query_out[level_idx]; e.ldo = c.query_dim;
-        if ((rc = run.gemm(proj_epi, tok, h->w_query[level_idx], MP, c.query_dim, W, e))) return rc;
+        // IQM branch: query_adapters[l] (model/adapter.py:202-205) on the same tokens, same epilogue
+        if ((rc = tap((size_t)c.n_levels + 1 + level_idx, query_out[level_idx], c.query_dim))) return rc;
       }
       if (h->seg_normalize && (rc = l2norm(seg_out[level_idx], MP))) return rc;
       if (level_idx == c.n_levels - 1) {
-        { GemmEpi e; e.out_f32 = detbuf; e.ldo = E;
-          if ((rc = run.gemm(proj_epi, tok, h->w_det, MP, E, W, e))) return rc; }
+        if ((rc = tap((size_t)c.n_levels, detbuf, E))) return rc;
         if ((rc = l2norm(detbuf, MP))) return rc;
         ProfScope ps(h, AACLIP_PROF_OTHER, 0.0, st);
         launch_pdl(mean_over_patches_kernel, dim3((E + MEAN_COLS - 1) / MEAN_COLS, B), dim3(MEAN_COLS, MEAN_SEGS), 0, st, static_cast<const float*>(detbuf), det_out, P, E);
@@ -1098,7 +1144,19 @@ int aaclip_finalize_weights(AaclipHandle* h, void* stream) {
   if (h->f32 || h->folded) return AACLIP_OK;
   if (!h->missing.empty())
     return fail(AACLIP_ESTATE, "aaclip_finalize_weights: %zu weight tensors not set (first: %s)", h->missing.size(), h->missing[0].c_str());
-  if (int rc = fold_blocks(h->blk, h->bf16, h->cfg.width, h->cfg.mlp_dim, static_cast<cudaStream_t>(stream))) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int W = h->cfg.width;
+  for (AaclipHandle::ProjFold& pf : h->proj) {
+    if (pf.stage == nullptr) continue;      // an optional query adapter that was never set
+    if (h->bf16) ln_fold_kernel<true><<<(pf.rows + 7) / 8, 256, 0, st>>>(pf.stage, h->zero_bias, h->lnpost_g, h->lnpost_b, pf.w16, pf.colsum, pf.bias_f, pf.rows, W);
+    else ln_fold_kernel<false><<<(pf.rows + 7) / 8, 256, 0, st>>>(pf.stage, h->zero_bias, h->lnpost_g, h->lnpost_b, pf.w16, pf.colsum, pf.bias_f, pf.rows, W);
+    LAUNCH_CHECK("ln_fold_kernel");
+  }
+  if (int rc = fold_blocks(h->blk, h->bf16, W, h->cfg.mlp_dim, st)) return rc;   // synchronises the stream
+  for (AaclipHandle::ProjFold& pf : h->proj) {
+    if (pf.stage) cudaFree(pf.stage);
+    pf.stage = nullptr;
+  }
   h->folded = true;
   return AACLIP_OK;
 }
@@ -1659,6 +1717,21 @@ int aaclip_gemm16_ln(int32_t dtype, const void* A, const void* W16, int32_t M, i
   e.bias = bias_f; e.colsum = colsum; e.stats = stats; e.n_partials = n_partials; e.inv_width = 1.0f / ln_width;
   e.out_16 = reinterpret_cast<uint16_t*>(out_16); e.ldo = ldo;
   return launch_gemm(epi, dtype == AACLIP_DT_BF16, A, W16, M, N, K, e, static_cast<cudaStream_t>(stream));
+}
+
+int aaclip_gemm16_ln_tok(int32_t dtype, const void* A, const void* W16, int32_t M, int32_t N, int32_t K, int32_t leaky,
+                         const float* bias_f, const float* colsum, const float* stats, int32_t n_partials,
+                         int32_t ln_width, int32_t patches, float* out_f32, int32_t ldo, void* stream) {
+  if (!A || !W16 || !bias_f || !colsum || !stats || !out_f32) return fail(AACLIP_EINVAL, "aaclip_gemm16_ln_tok: null argument");
+  if (dtype != AACLIP_DT_F16 && dtype != AACLIP_DT_BF16) return fail(AACLIP_EINVAL, "aaclip_gemm16_ln_tok: bad dtype %d", dtype);
+  if (n_partials < 1 || n_partials > 16 || ln_width <= 0) return fail(AACLIP_EINVAL, "aaclip_gemm16_ln_tok: n_partials must be 1..16");
+  if (patches <= 0 || M % (patches + 1) != 0) return fail(AACLIP_EINVAL, "aaclip_gemm16_ln_tok: M must be a multiple of patches + 1");
+  if (ldo < N || ldo % 4 != 0) return fail(AACLIP_EINVAL, "aaclip_gemm16_ln_tok: ldo must be >= N and a multiple of 4");
+  GemmEpi e;
+  e.bias = bias_f; e.colsum = colsum; e.stats = stats; e.n_partials = n_partials; e.inv_width = 1.0f / ln_width;
+  e.out_f32 = out_f32; e.ldo = ldo; e.patches = patches;
+  return launch_gemm(leaky ? EPI_LN_LEAKY_F32_TOK : EPI_LN_F32_TOK, dtype == AACLIP_DT_BF16, A, W16, M, N, K, e,
+                     static_cast<cudaStream_t>(stream));
 }
 
 int aaclip_gemm16_resid(int32_t dtype, const void* A, const void* W, int32_t M, int32_t N, int32_t K,

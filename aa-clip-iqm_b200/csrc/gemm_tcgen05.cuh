@@ -39,6 +39,11 @@ enum EpiMode : int {
   // (sum, sum of squares) of the UNROUNDED values over each 128-column slice (stats_out) -- the blend kernel needs
   // ||a||_2 of the whole row and then reads a as 2 bytes per element instead of 4
   EPI_LEAKY_16_SQ = 11,
+  // token taps (model/adapter.py:171-184): ln_post folded into the seg / det / query projections. A = the raw 16-bit
+  // residual stream INCLUDING the CLS rows (row m = b*(P+1) + t); rows with t = 0 are dropped and row m lands at
+  // out_f32[b*P + t - 1] -- x[1:] of every image, without a LayerNorm pass or a token copy
+  EPI_LN_F32_TOK = 12,        // out_f32 = rstd*(acc - mean*colsum) + bias'
+  EPI_LN_LEAKY_F32_TOK = 13,  // ... followed by LeakyReLU(0.01) (--relu)
 };
 
 struct GemmEpi {
@@ -107,7 +112,13 @@ template <int EPI>
 __host__ __device__ constexpr bool epi_has_bias() {
   return EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_QGELU_BF16 ||
          EPI == EPI_BIAS_RESID_F32 || EPI == EPI_BIAS_F32 || EPI == EPI_LN_BIAS_BF16 ||
-         EPI == EPI_LN_BIAS_GELU_BF16 || EPI == EPI_LN_BIAS_QGELU_BF16;
+         EPI == EPI_LN_BIAS_GELU_BF16 || EPI == EPI_LN_BIAS_QGELU_BF16 || EPI == EPI_LN_F32_TOK ||
+         EPI == EPI_LN_LEAKY_F32_TOK;
+}
+
+template <int EPI>
+__host__ __device__ constexpr bool epi_is_tok() {      // token-tap projections: CLS rows dropped, output rows re-based
+  return EPI == EPI_LN_F32_TOK || EPI == EPI_LN_LEAKY_F32_TOK;
 }
 
 template <int EPI>
@@ -117,7 +128,8 @@ __host__ __device__ constexpr bool epi_has_stats() {   // emits per-row (sum, su
 
 template <int EPI>
 __host__ __device__ constexpr bool epi_is_ln() {
-  return EPI == EPI_LN_BIAS_BF16 || EPI == EPI_LN_BIAS_GELU_BF16 || EPI == EPI_LN_BIAS_QGELU_BF16;
+  return EPI == EPI_LN_BIAS_BF16 || EPI == EPI_LN_BIAS_GELU_BF16 || EPI == EPI_LN_BIAS_QGELU_BF16 ||
+         EPI == EPI_LN_F32_TOK || EPI == EPI_LN_LEAKY_F32_TOK;
 }
 
 // `b` = bias[n..n+3] (and `cs` = colsum[n..n+3]) are loaded once per 32-column chunk by the caller; `mean` / `rstd`
@@ -142,12 +154,12 @@ __device__ __forceinline__ float4 epilogue_apply(bool ok, float4 v, int row, int
   if constexpr (EPI == EPI_BIAS_QGELU_BF16 || EPI == EPI_LN_BIAS_QGELU_BF16) {
     v.x = quick_gelu(v.x); v.y = quick_gelu(v.y); v.z = quick_gelu(v.z); v.w = quick_gelu(v.w);
   }
-  if constexpr (EPI == EPI_LEAKY_F32 || EPI == EPI_LEAKY_16_SQ) {
+  if constexpr (EPI == EPI_LEAKY_F32 || EPI == EPI_LEAKY_16_SQ || EPI == EPI_LN_LEAKY_F32_TOK) {
     v.x = v.x > 0.f ? v.x : 0.01f * v.x; v.y = v.y > 0.f ? v.y : 0.01f * v.y;
     v.z = v.z > 0.f ? v.z : 0.01f * v.z; v.w = v.w > 0.f ? v.w : 0.01f * v.w;
   }
-  if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_QGELU_BF16 || epi_is_ln<EPI>() ||
-                EPI == EPI_LEAKY_16_SQ) {
+  if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_QGELU_BF16 ||
+                (epi_is_ln<EPI>() && !epi_is_tok<EPI>()) || EPI == EPI_LEAKY_16_SQ) {
     const uint2 w = make_uint2(ptx::pack16<BF16>(v.x, v.y), ptx::pack16<BF16>(v.z, v.w));
     if (ok) *reinterpret_cast<uint2*>(e.out_16 + static_cast<size_t>(row) * e.ldo + n) = w;
   } else if constexpr (EPI == EPI_BIAS_RESID_F32) {
@@ -381,6 +393,15 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
         for (int j = 0; j < 8; ++j) st_s[j] = st_q[j] = 0.f;
       }
+      int tok_row[8];               // epi_is_tok: output row of each of the 8 rows, -1 = dropped (CLS row or beyond M)
+      if constexpr (epi_is_tok<EPI>()) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int rr = row0 + j * 4 + sub;
+          const int bi = rr / (epi.patches + 1), t = rr - bi * (epi.patches + 1);
+          tok_row[j] = (rr < M && t != 0) ? bi * epi.patches + t - 1 : -1;
+        }
+      }
 #pragma unroll 1
       for (int c = 0; c < CHUNKS; ++c) {
         const int n = n_blk * BN + cg * COLS_PER_WARP + c * 32 + unit * 4;
@@ -426,6 +447,9 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const float4 x = epilogue_apply<EPI, BF16>(ok, v, row0 + rr, n, epi, bias4);
             st_s[j] += (x.x + x.y) + (x.z + x.w);
             st_q[j] += (x.x * x.x + x.y * x.y) + (x.z * x.z + x.w * x.w);
+          } else if constexpr (epi_is_tok<EPI>()) {
+            epilogue_apply<EPI, BF16>(tok_row[j] >= 0, v, tok_row[j], n, epi, bias4, make_float4(0.f, 0.f, 0.f, 0.f), cs4,
+                                      mean_j[j], rstd_j[j]);
           } else if constexpr (epi_is_ln<EPI>()) {
             epilogue_apply<EPI, BF16>(ok, v, row0 + rr, n, epi, bias4, make_float4(0.f, 0.f, 0.f, 0.f), cs4, mean_j[j],
                                       rstd_j[j]);

@@ -134,6 +134,22 @@ def gemm16_ln(a: torch.Tensor, w16: torch.Tensor, epi: int, bias_f: torch.Tensor
     return out
 
 
+
+def gemm16_ln_tok(a: torch.Tensor, w16: torch.Tensor, bias_f: torch.Tensor, colsum: torch.Tensor, stats: torch.Tensor,
+                  ln_width: int, patches: int, leaky: bool = False) -> torch.Tensor:
+    """Token-tap projection with ln_post folded in (aaclip_gemm16_ln_tok): `a` holds all patches+1 raw 16-bit rows of
+    every image; returns [B*patches, N] fp32 = act(LayerNorm(x)[1:] @ W^T) per image (CLS rows dropped)."""
+    _need_cuda(a, w16, bias_f, colsum, stats)
+    assert a.dtype == w16.dtype and a.is_contiguous() and w16.is_contiguous() and stats.is_contiguous()
+    M, K = a.shape
+    N = w16.shape[0]
+    out = torch.empty((M // (patches + 1) * patches, N), dtype=torch.float32, device=a.device)
+    _lib.check(_lib.load().aaclip_gemm16_ln_tok(_dt(a), _ptr(a), _ptr(w16), M, N, K, int(leaky), _ptr(bias_f), _ptr(colsum),
+                                                _ptr(stats), stats.shape[1], ln_width, patches, _ptr(out), N, _stream()),
+               "aaclip_gemm16_ln_tok")
+    return out
+
+
 def gemm16_resid(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, x: torch.Tensor, want_x16: bool = True,
                  want_stats: bool = True):
     """x += a @ w^T + bias in place (fp32); returns (x16 | None, stats [M, N/stat_columns, 2] | None)

@@ -312,6 +312,14 @@ int aaclip_gemm16_ln(int32_t dtype, const void* A, const void* W16, int32_t M, i
                      const float* bias_f, const float* colsum, const float* stats, int32_t n_partials,
                      int32_t ln_width, void* out_16, int32_t ldo, void* stream);
 
+/* Token-tap projection with ln_post folded in (model/adapter.py:171-184), as aaclip_forward launches it for seg_proj /
+ * det_proj / query_adapters: A = the raw 16-bit residual stream with ALL patches+1 rows of every image (M = B*(patches+1));
+ * the rows of the CLS tokens are dropped and row b*(patches+1)+t lands at out_f32[b*patches + t - 1]:
+ *   out_f32 = act(rstd_m * (A W16^T - mean_m * colsum) + bias_f),  act = LeakyReLU(0.01) if `leaky` else identity. */
+int aaclip_gemm16_ln_tok(int32_t dtype, const void* A, const void* W16, int32_t M, int32_t N, int32_t K, int32_t leaky,
+                         const float* bias_f, const float* colsum, const float* stats, int32_t n_partials,
+                         int32_t ln_width, int32_t patches, float* out_f32, int32_t ldo, void* stream);
+
 /* Residual GEMM: x[M,N] (fp32, in place) += A W^T + bias; optionally also the raw 16-bit copy of the new x and its
  * LayerNorm partials stats_out [M][N/aaclip_stat_columns()][2] (the inputs of the next folded-LN GEMM). */
 int aaclip_gemm16_resid(int32_t dtype, const void* A, const void* W, int32_t M, int32_t N, int32_t K,

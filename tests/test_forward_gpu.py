@@ -308,7 +308,7 @@ def test_full_size_batch_properties():
     halves = [pred.predict_device(images[k:k + 16]) for k in (0, 16)]
     halves = [(m.clone(), s.clone()) for m, s in halves]
     assert torch.equal(torch.cat([h[0] for h in halves]), m_a) and torch.equal(torch.cat([h[1] for h in halves]), s_a)
-    assert pred.launches_per_batch == 150      # 147 tower launches + similarity, anomaly-map and image-score kernels
+    assert pred.launches_per_batch == 146      # 143 tower launches + similarity, anomaly-map and image-score kernels
     # the predictor runs the tower with raw seg projections (the similarity kernel normalises); with the reference's
     # return values switched back on, the features are unit-norm and the maps agree with the fused route
     pred.engine.seg_normalize(True)

@@ -252,6 +252,34 @@ def test_folded_layernorm_gemm_chain(eng, M, W, N, dtype):
     assert (yq.float() - y_ref * torch.sigmoid(1.702 * y_ref)).abs().max().item() < tol
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("B,P,W,N,leaky", [(2, 256, 1024, 768, False), (3, 576, 1024, 768, True), (1, 1369, 1024, 512, False)])
+def test_token_tap_projection_with_folded_ln_post(eng, B, P, W, N, leaky, dtype):
+    """aaclip_gemm16_ln_tok against model/adapter.py:171-184 in fp32: x[1:] of every image -> ln_post -> SimpleProj
+    (optionally LeakyReLU). The GEMM reads all P+1 rows per image from the raw 16-bit stream; the CLS rows must not
+    appear in the output and every patch row must land at b*P + t - 1."""
+    _lib, engine = eng
+    g = torch.Generator(device="cuda").manual_seed(B * 31 + P)
+    M = B * (P + 1)
+    x = torch.randn(M, W, device="cuda", generator=g) * 2.0 + 0.3
+    x[::7, 5] += 40.0                                          # an outlier channel on some rows
+    gamma = 1.0 + 0.1 * torch.randn(W, device="cuda", generator=g)
+    beta = 0.1 * torch.randn(W, device="cuda", generator=g)
+    w = torch.randn(N, W, device="cuda", generator=g) * W ** -0.5
+    cols = _lib.load().aaclip_stat_columns()
+    stats = torch.stack([x.view(M, W // cols, cols).sum(-1), (x * x).view(M, W // cols, cols).sum(-1)], -1).contiguous()
+    w16, cs, bf = engine.ln_fold(w, torch.zeros(N, device="cuda"), gamma, beta, dtype)
+    out = engine.gemm16_ln_tok(x.to(dtype), w16, bf, cs, stats, W, P, leaky=leaky)
+    ref = F.layer_norm(x, (W,), gamma, beta, 1e-5).view(B, P + 1, W)[:, 1:].reshape(B * P, W) @ w.t()
+    if leaky:
+        ref = F.leaky_relu(ref, 0.01)
+    assert out.shape == (B * P, N)
+    # operand rounding: x and W' are rounded once to 16 bits, K = 1024 products of O(1) x O(W^-0.5) terms
+    tol = {torch.float16: 2e-2, torch.bfloat16: 1.5e-1}[dtype]
+    assert (out - ref).abs().max().item() < tol
+    assert ((out - ref).abs().mean() / ref.abs().mean()).item() < 8 * EPS[dtype]
+
+
 def test_folded_layernorm_is_row_local(eng):
     """Batch invariance: a row's folded-LN output must not depend on which other rows are in the launch."""
     _lib, engine = eng
