@@ -273,7 +273,9 @@ __global__ void adapter_blend16_kernel(float* __restrict__ x, const uint16_t* __
     const float2* ap = reinterpret_cast<const float2*>(a_stats) + static_cast<size_t>(warp) * np;
     for (int i = 0; i < np; ++i) sa += __ldg(ap + i).y;   // every lane: same order, same value
   }
-  const float nx = sqrtf(warp_sum(sx)), na = sqrtf(sa);
+  // (one scale per row: a is already rounded to 16 bits here, so the reference's per-element order a*|x|/|a| buys
+  // nothing; the fp32-accuracy mode keeps it)
+  const float r = w * (sqrtf(warp_sum(sx)) / sqrtf(sa));
   float s = 0.f, q = 0.f;
 #pragma unroll
   for (int j = 0; j < V; ++j) {
@@ -281,10 +283,10 @@ __global__ void adapter_blend16_kernel(float* __restrict__ x, const uint16_t* __
     ptx::unpack16<BF16>(aw[j].x, a0, a1);
     ptx::unpack16<BF16>(aw[j].y, a2, a3);
     float4 o;
-    o.x = w * (a0 * nx / na) + one_minus_w * xv[j].x;
-    o.y = w * (a1 * nx / na) + one_minus_w * xv[j].y;
-    o.z = w * (a2 * nx / na) + one_minus_w * xv[j].z;
-    o.w = w * (a3 * nx / na) + one_minus_w * xv[j].w;
+    o.x = fmaf(r, a0, one_minus_w * xv[j].x);
+    o.y = fmaf(r, a1, one_minus_w * xv[j].y);
+    o.z = fmaf(r, a2, one_minus_w * xv[j].z);
+    o.w = fmaf(r, a3, one_minus_w * xv[j].w);
     xr[lane + 32 * j] = o;
     reinterpret_cast<uint2*>(x16 + static_cast<size_t>(warp) * D)[lane + 32 * j] =
         make_uint2(ptx::pack16<BF16>(o.x, o.y), ptx::pack16<BF16>(o.z, o.w));

@@ -166,8 +166,12 @@ __device__ __forceinline__ float4 epilogue_apply(bool ok, float4 v, int row, int
     v.x += resid.x; v.y += resid.y; v.z += resid.z; v.w += resid.w;   // residual loaded by the caller
     const uint2 w = make_uint2(ptx::pack16<BF16>(v.x, v.y), ptx::pack16<BF16>(v.z, v.w));
     if (ok) {
+#ifndef AACLIP_GEMM_DBG_NOXSTORE  // what-if (timing only, wrong results): no fp32 residual write
       *reinterpret_cast<float4*>(e.out_f32 + static_cast<size_t>(row) * e.ldo + n) = v;
+#endif
+#ifndef AACLIP_GEMM_DBG_NOX16     // what-if (timing only, wrong results): no 16-bit copy
       if (e.out_16 != nullptr) *reinterpret_cast<uint2*>(e.out_16 + static_cast<size_t>(row) * e.ldo + n) = w;
+#endif
     }
   } else {
     size_t orow = static_cast<size_t>(row);
@@ -415,8 +419,12 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int rr = row0 + (j0 + j) * 4 + sub;
+#ifdef AACLIP_GEMM_DBG_NORESID   // what-if (timing only, wrong results): no residual read
+            dst[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+#else
             dst[j] = (rr < M) ? *reinterpret_cast<const float4*>(epi.out_f32 + static_cast<size_t>(rr) * epi.ldo + n)
                               : make_float4(0.f, 0.f, 0.f, 0.f);
+#endif
           }
         };
         if constexpr (EPI == EPI_BIAS_RESID_F32) load_resid(resid_a, 0);
