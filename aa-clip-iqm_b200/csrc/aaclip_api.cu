@@ -219,10 +219,27 @@ template <bool BF16>
 int launch_attention_t(const CUtensorMap& tq, void* out, int B, int N, int D, int causal, cudaStream_t st) {
   static PerDeviceOnce once;
   if (int rc = opt_in_smem(once, attention_tcgen05_kernel<BF16>, attn_cfg::SMEM_BYTES)) return rc;
-  dim3 grid((N + attn_cfg::BQ * attn_cfg::QT - 1) / (attn_cfg::BQ * attn_cfg::QT), D / 64, B);
+  int sms = 0;
+  if (int rc = ensure_device(&sms)) return rc;
+  // persistent CTAs draw (image, head, 256 query rows) items from a counter slot that the kernel leaves zeroed; slots
+  // are handed out round-robin, so launches in flight on different streams (or captured in different graphs) do not
+  // share one unless more than SCHED_SLOTS of them are pending at once
+  static std::atomic<unsigned> next_slot{0};
+  AttnSched* sched = nullptr;
+  CUDA_TRY(cudaGetSymbolAddress(reinterpret_cast<void**>(&sched), g_attn_sched));
+  sched += next_slot.fetch_add(1, std::memory_order_relaxed) % attn_cfg::SCHED_SLOTS;
+  const int items = B * (D / attn_cfg::HD) * ((N + attn_cfg::BQ * attn_cfg::QT - 1) / (attn_cfg::BQ * attn_cfg::QT));
+  // the output as a 3-D tensor [B][N][D] for the bulk stores: one 32-row x 64-column box per softmax warp and item
+  CUtensorMap to;
+  {
+    const uint64_t dims[3] = {(uint64_t)D, (uint64_t)N, (uint64_t)B};
+    const uint64_t str[2] = {(uint64_t)D * 2, (uint64_t)N * D * 2};
+    const uint32_t box[3] = {attn_cfg::HD, 32, 1};
+    if (int rc = make_tmap_16(&to, out, 3, dims, str, box, BF16)) return rc;
+  }
   const float scale_log2 = 0.125f * 1.4426950408889634f;  // head_dim^-0.5 * log2(e)
-  CUDA_TRY(launch_pdl(attention_tcgen05_kernel<BF16>, grid, dim3(attn_cfg::THREADS), attn_cfg::SMEM_BYTES, st, tq,
-                      reinterpret_cast<uint16_t*>(out), N, D, causal, scale_log2));
+  CUDA_TRY(launch_pdl(attention_tcgen05_kernel<BF16>, dim3(items < sms ? items : sms), dim3(attn_cfg::THREADS),
+                      attn_cfg::SMEM_BYTES, st, tq, to, N, D, causal, scale_log2, B, sched));
   return AACLIP_OK;
 }
 
@@ -696,8 +713,9 @@ struct BlockRunF32 {
 }  // namespace
 
 #ifdef AACLIP_ATTN_DBG_TIMELINE
-extern "C" int aaclip_debug_attn_timeline(long long* dst) {
-  return cudaMemcpyFromSymbol(dst, aaclip::g_attn_timeline, sizeof(long long) * 2 * 16 * 8) == cudaSuccess ? 0 : -1;
+extern "C" int aaclip_debug_attn_timeline(long long* dst, long long* dst_mma) {
+  if (cudaMemcpyFromSymbol(dst, aaclip::g_attn_timeline, sizeof(long long) * 2 * 16 * 8) != cudaSuccess) return -1;
+  return cudaMemcpyFromSymbol(dst_mma, aaclip::g_attn_timeline_mma, sizeof(long long) * 2 * 16 * 8) == cudaSuccess ? 0 : -1;
 }
 #endif
 

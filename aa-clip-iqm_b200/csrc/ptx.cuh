@@ -112,6 +112,24 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* tmap, ui
       : "memory");
 }
 
+// shared -> global bulk tensor store (elements outside the tensor are clipped). Completion is tracked per THREAD in bulk
+// async-groups: commit, then wait_group_read before the shared-memory source is overwritten.
+__device__ __forceinline__ void tma_store_3d(const void* tmap, const void* smem_src, int32_t c0, int32_t c1, int32_t c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(tmap)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_group_read0() {
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_group0() {
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 // ------------------------------------------------------------------ tcgen05 / TMEM
 template <uint32_t kCols>
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result) {

@@ -113,8 +113,8 @@ def test_attention_extreme_logits(eng):
 
 @pytest.mark.parametrize("dtype", DTYPES)
 def test_attention_growing_logits_redo_path(eng, dtype):
-    """Every K/V tile's scores exceed the previous tile's by far more than the lazy-maximum pass tolerates: each tile
-    after the first overflows its row-sum check and is redone on the exact-max path (attention_tcgen05.cuh LAZYMAX)."""
+    """Every K/V tile's scores exceed the previous tile's by far more than the lazy rescale threshold (2^8): the running
+    maximum moves, and O in TMEM and the row sum are rescaled, on every tile (attention_tcgen05.cuh)."""
     _lib, engine = eng
     g = torch.Generator(device="cuda").manual_seed(11)
     N = 1370
@@ -126,6 +126,38 @@ def test_attention_growing_logits_redo_path(eng, dtype):
     out = engine.attention(qkv).float()
     assert torch.isfinite(out).all()
     assert (out - _attn_ref(qkv, False)).abs().max().item() < (3e-2 if dtype == torch.bfloat16 else 1e-2)
+
+
+def test_attention_persistent_schedule(eng):
+    """The kernel is persistent: CTAs draw (image, head, query block) items from a counter slot that every launch must
+    leave zeroed. (1) more items than SMs and fewer items than SMs give the same rows; (2) launches in flight on two
+    streams at once use different slots; (3) more launches than there are slots (256) wrap around cleanly."""
+    _lib, engine = eng
+    g = torch.Generator(device="cuda").manual_seed(5)
+    big = (torch.randn(12, 700, 3 * 1024, device="cuda", generator=g) * 1.5).half()       # 12*16*3 = 576 items
+    ref = engine.attention(big).clone()
+    for i in (0, 7, 11):                                                                     # 48 items: fewer than SMs
+        assert torch.equal(engine.attention(big[i:i + 1])[0], ref[i])
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    other = (torch.randn(12, 700, 3 * 1024, device="cuda", generator=g) * 1.5).half()
+    ref_other = engine.attention(other).clone()
+    torch.cuda.synchronize()
+    outs = []
+    for _ in range(4):
+        with torch.cuda.stream(s1):
+            a = engine.attention(big)
+        with torch.cuda.stream(s2):
+            b = engine.attention(other)
+        outs.append((a, b))
+    torch.cuda.synchronize()
+    for a, b in outs:
+        assert torch.equal(a, ref) and torch.equal(b, ref_other)
+    small = (torch.randn(1, 130, 3 * 64, device="cuda", generator=g)).half()
+    first = engine.attention(small).clone()
+    for _ in range(600):
+        out = engine.attention(small)
+    assert torch.equal(out, first)
+    assert torch.equal(engine.attention(big), ref)
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
