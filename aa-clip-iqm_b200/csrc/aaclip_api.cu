@@ -216,7 +216,8 @@ int launch_gemm(int epi_mode, bool bf16, const void* A, const void* W, int M, in
 }
 
 template <bool BF16>
-int launch_attention_t(const CUtensorMap& tq, void* out, int B, int N, int D, int causal, cudaStream_t st) {
+int launch_attention_t(const CUtensorMap& tq, void* out, int B, int N, int D, int causal, cudaStream_t st,
+                       int descending) {
   static PerDeviceOnce once;
   if (int rc = opt_in_smem(once, attention_tcgen05_kernel<BF16>, attn_cfg::SMEM_BYTES)) return rc;
   int sms = 0;
@@ -239,11 +240,12 @@ int launch_attention_t(const CUtensorMap& tq, void* out, int B, int N, int D, in
   }
   const float scale_log2 = 0.125f * 1.4426950408889634f;  // head_dim^-0.5 * log2(e)
   CUDA_TRY(launch_pdl(attention_tcgen05_kernel<BF16>, dim3(items < sms ? items : sms), dim3(attn_cfg::THREADS),
-                      attn_cfg::SMEM_BYTES, st, tq, to, N, D, causal, scale_log2, B, sched));
+                      attn_cfg::SMEM_BYTES, st, tq, to, N, D, causal, scale_log2, B, sched, descending));
   return AACLIP_OK;
 }
 
-int launch_attention(bool bf16, const void* qkv, void* out, int B, int N, int D, int causal, cudaStream_t st) {
+int launch_attention(bool bf16, const void* qkv, void* out, int B, int N, int D, int causal, cudaStream_t st,
+                     int descending = 0) {
   if (int rc = ensure_device()) return rc;
   if (B <= 0 || N <= 0 || D <= 0 || D % 64 != 0) return fail(AACLIP_EINVAL, "attention: bad shape B=%d N=%d D=%d", B, N, D);
   CUtensorMap tq;
@@ -251,7 +253,8 @@ int launch_attention(bool bf16, const void* qkv, void* out, int B, int N, int D,
   const uint64_t str[2] = {(uint64_t)3 * D * 2, (uint64_t)N * 3 * D * 2};
   const uint32_t box[3] = {attn_cfg::HD, attn_cfg::BKV, 1};
   if (int rc = make_tmap_16(&tq, qkv, 3, dims, str, box, bf16)) return rc;
-  return bf16 ? launch_attention_t<true>(tq, out, B, N, D, causal, st) : launch_attention_t<false>(tq, out, B, N, D, causal, st);
+  return bf16 ? launch_attention_t<true>(tq, out, B, N, D, causal, st, descending)
+              : launch_attention_t<false>(tq, out, B, N, D, causal, st, descending);
 }
 
 template <int D, bool BF16>
@@ -596,11 +599,39 @@ struct BlockRun {
   float* x; uint16_t* x16; uint16_t* qkv; uint16_t* att; uint16_t* hid; float* abuf; float* stats;
   cudaStream_t st;
   int launches = 0;
+  // Serpentine row order (GemmEpi::descending): every GEMM / attention launch walks the row blocks in the direction
+  // opposite to the kernel that wrote its input, so it starts with the rows that are still in L2. `last_desc` = the
+  // direction of the last kernel that wrote an activation of the stream; element-wise kernels run ascending.
+  // AACLIP_SERPENTINE=0 in the environment keeps every launch ascending (A/B runs).
+  bool last_desc = false;
+  static bool serpentine() {
+    static const bool on = [] {
+      const char* e = getenv("AACLIP_SERPENTINE");
+      return !(e != nullptr && e[0] == '0');
+    }();
+    return on;
+  }
+  int next_dir() {
+    if (!serpentine()) return 0;
+    last_desc = !last_desc;
+    return last_desc ? 1 : 0;
+  }
 
   int gemm(int epi, const void* A, const void* Wt, int m, int n, int k, const GemmEpi& e, int cls = AACLIP_PROF_GEMM) {
     ProfScope ps(prof, cls, 2.0 * m * n * k, st);
     ++launches;
-    return launch_gemm(epi, bf16, A, Wt, m, n, k, e, st);
+    GemmEpi ed = e;
+    ed.descending = next_dir();
+    return launch_gemm(epi, bf16, A, Wt, m, n, k, ed, st);
+  }
+  // a GEMM that only READS the stream (token-tap projections): opposite to the last writer, and the next kernel still
+  // sees that writer's direction
+  int gemm_tap(int epi, const void* A, const void* Wt, int m, int n, int k, const GemmEpi& e) {
+    ProfScope ps(prof, AACLIP_PROF_GEMM, 2.0 * m * n * k, st);
+    ++launches;
+    GemmEpi ed = e;
+    ed.descending = (serpentine() && !last_desc) ? 1 : 0;
+    return launch_gemm(epi, bf16, A, Wt, m, n, k, ed, st);
   }
 
   int run(const BlockW& b, const uint16_t* w_adapter, float adapt_weight) {
@@ -613,7 +644,7 @@ struct BlockRun {
     {
       ProfScope ps(prof, AACLIP_PROF_ATTENTION, 4.0 * items * (W / 64) * (double)tokens * tokens * 64, st);
       ++launches;
-      if ((rc = launch_attention(bf16, qkv, att, items, tokens, W, causal, st))) return rc;
+      if ((rc = launch_attention(bf16, qkv, att, items, tokens, W, causal, st, next_dir()))) return rc;
     }
     sat.scan(att, static_cast<size_t>(M) * W, st);
     { GemmEpi e; e.bias = b.b_out; e.out_f32 = x; e.out_16 = x16; e.stats_out = stats; e.ldo = W;
@@ -652,6 +683,7 @@ struct BlockRun {
       else launch_pdl(adapter_blend16_kernel<768, false>, dim3(grid), dim3(256), 0, st, x, static_cast<const uint16_t*>(a16), static_cast<const float*>(a_stats), M, w, w1, x16, stats, np);
     }
     LAUNCH_CHECK("adapter_blend16_kernel");
+    last_desc = false;                     // an element-wise kernel: rows ascending
     ++launches;
     sat.scan(x16, static_cast<size_t>(M) * W, st);
     return AACLIP_OK;
@@ -1110,6 +1142,7 @@ int aaclip_forward(AaclipHandle* h, const float* images, int32_t B, void* worksp
   }
   // ln_pre in place; also emits the 16-bit copy and the LayerNorm partials block 0's folded ln_1 needs
   if ((rc = lnorm(x, h->lnpre_g, h->lnpre_b, run.x16, x, M, 0, run.stats))) return rc;
+  run.last_desc = false;                   // an element-wise kernel wrote the stream: rows ascending
   run.sat.scan(run.x16, static_cast<size_t>(M) * W, st);
 
   // ---- residual attention blocks (model/transformer.py:239-258) + adapters (model/adapter.py:161-172)
@@ -1127,7 +1160,7 @@ int aaclip_forward(AaclipHandle* h, const float* images, int32_t B, void* worksp
         const AaclipHandle::ProjFold& pf = h->proj[pi];
         GemmEpi e; e.out_f32 = out; e.ldo = cols; e.patches = P;
         e.bias = pf.bias_f; e.colsum = pf.colsum; e.stats = run.stats; e.n_partials = kStatPartials(W); e.inv_width = 1.0f / W;
-        return run.gemm(proj_epi, run.x16, pf.w16, M, cols, W, e);
+        return run.gemm_tap(proj_epi, run.x16, pf.w16, M, cols, W, e);
       };
       if ((rc = tap((size_t)level_idx, seg_out[level_idx], E))) return rc;
       if (query_out != nullptr && query_out[level_idx] != nullptr) {

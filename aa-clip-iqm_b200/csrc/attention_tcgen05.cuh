@@ -221,7 +221,7 @@ template <bool BF16>
 __global__ void __launch_bounds__(attn_cfg::THREADS, 1)
 attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_out,
                             int n_tok, int D, int causal, float scale_log2, int n_images,
-                            AttnSched* __restrict__ sched) {
+                            AttnSched* __restrict__ sched, int descending) {
   using namespace attn_cfg;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -307,7 +307,9 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __g
     for (;;) {
       const bool more = idx < shape.n_items;
       AttnItem it{0, 0, 0, 0};
-      if (more) it = shape.decode(idx);         // the only place that divides: everyone else reads the decoded item
+      // the only place that divides: everyone else reads the decoded item. descending: last image first -- the rows the
+      // QKV GEMM wrote last (when it ran ascending) are still in L2 (gemm_tcgen05.cuh: GemmEpi::descending)
+      if (more) it = shape.decode(descending ? shape.n_items - 1 - idx : idx);
       ptx::mbar_wait(&item_empty[slot], slot_ph ^ 1);
       if (lane == 0) {
         item_slot[slot] = make_int4(it.b, it.h, it.q_base, it.n_qt);

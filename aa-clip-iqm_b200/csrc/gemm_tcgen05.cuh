@@ -61,6 +61,11 @@ struct GemmEpi {
   int n_partials = 0;                 // EPI_LN_*: partials per row in `stats`
   float inv_width = 0.f;              // EPI_LN_*: 1 / (LayerNorm width)
   float eps = 1e-5f;
+  // Row-block order of the persistent schedule: 0 = ascending, 1 = descending. The activation tensors of the step
+  // (90-360 MB) are larger than the 126 MB L2, so a consumer that walks the rows in the SAME direction as its producer
+  // finds nothing of it in L2; walking them the other way round starts with the rows the producer wrote last. The
+  // launch sequence alternates (aaclip_api.cu: BlockRun); the result is bit-identical either way.
+  int descending = 0;
 };
 
 
@@ -284,7 +289,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint32_t phase = 0;
     const uint32_t full0_leader = ptx::mapa_u32(ptx::smem_u32(&full_bar[0]), 0);
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-      const int m_pair = tile / n_tiles, n_blk = tile - m_pair * n_tiles;
+      const int m_lin = tile / n_tiles, n_blk = tile - m_lin * n_tiles;
+      const int m_pair = epi.descending ? m_pairs - 1 - m_lin : m_lin;
       const int m_row = (2 * m_pair + static_cast<int>(rank)) * BM;
       const int n_row = n_blk * BN + static_cast<int>(rank) * (BN / 2);
       for (int kb = 0; kb < num_kb; ++kb) {
@@ -342,7 +348,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-      const int m_pair = tile / n_tiles, n_blk = tile - m_pair * n_tiles;
+      const int m_lin = tile / n_tiles, n_blk = tile - m_lin * n_tiles;
+      const int m_pair = epi.descending ? m_pairs - 1 - m_lin : m_lin;
       const int row0 = (2 * m_pair + static_cast<int>(rank)) * BM + q * 32;
       if constexpr (EPI == EPI_BIAS_RESID_F32 && AACLIP_GEMM_RESID_PREFETCH)
         // The residual rows this warp will add come from HBM (the stream is 180 MB, far beyond L2): pull them into L2
