@@ -64,7 +64,10 @@
 namespace aaclip {
 
 namespace attn_cfg {
-constexpr int BQ = 128, QT = 2, BKV = 128, HD = 64, KV_STAGES = 3, Q_STAGES = 2, ITEM_SLOTS = 2;
+#ifndef AACLIP_ATTN_KV_STAGES
+#define AACLIP_ATTN_KV_STAGES 3
+#endif
+constexpr int BQ = 128, QT = 2, BKV = 128, HD = 64, KV_STAGES = AACLIP_ATTN_KV_STAGES, Q_STAGES = 2, ITEM_SLOTS = 2;
 constexpr int TILE_BYTES = 128 * HD * 2;          // one Q / K / V tile: 128 rows x 128 B = 16 KiB
 constexpr int N_SOFTMAX_WARPS = 4 * QT;
 constexpr int THREADS = 32 * N_SOFTMAX_WARPS + 128;   // softmax warpgroups + {TMA, QT MMA issuers, idle}
@@ -72,7 +75,10 @@ constexpr int W_TMA = N_SOFTMAX_WARPS, W_MMA0 = N_SOFTMAX_WARPS + 1;
 // setmaxnreg only re-distributes what the CTA was launched with (THREADS x the launch register count, which ptxas
 // derives from __launch_bounds__: 384 x 168): 256 x 216 + 128 x 56 <= 64 512.
 constexpr int SOFTMAX_REGS = 216;
-constexpr int OTHER_REGS = 56;   // 256 x 216 + 128 x 56 = 62 464 <= 64 512: the issuers keep their cursors in registers
+#ifndef AACLIP_ATTN_OTHER_REGS
+#define AACLIP_ATTN_OTHER_REGS 56
+#endif
+constexpr int OTHER_REGS = AACLIP_ATTN_OTHER_REGS;   // 256 x 216 + 128 x 56 = 62 464 <= 64 512: the issuers keep their cursors in registers
 constexpr int TMEM_COLS = 256 * QT;
 constexpr int TM_S = 0, TM_O = QT * BKV, TM_P = TM_O + QT * HD;   // TMEM column map
 constexpr int OFF_Q = 0;                          // [Q_STAGES][QT] tiles
