@@ -158,6 +158,15 @@ def _declare(lib):
     lib.aaclip_seg_normalize.argtypes = [vp, i32]
     lib.aaclip_adapter.restype = i32
     lib.aaclip_adapter.argtypes = [i32, vp, vp, vp, i32, i32, f32, vp, sz, vp, vp]
+    # (guarded: tools/variants/*.so built from an older commit for an A/B run may predate these entry points;
+    # tests/test_cabi_symbols.py checks that the in-tree library exports every declared symbol)
+    if hasattr(lib, "aaclip_split_hilo"):
+        lib.aaclip_split_hilo.restype = i32
+        lib.aaclip_split_hilo.argtypes = [i32, vp, vp, vp, i64, vp]
+        lib.aaclip_join_hilo.restype = i32
+        lib.aaclip_join_hilo.argtypes = [i32, vp, vp, vp, i64, vp]
+        lib.aaclip_gemm16_resid_hl.restype = i32
+        lib.aaclip_gemm16_resid_hl.argtypes = [i32, vp, vp, i32, i32, i32, vp, vp, vp, vp, i32, vp]
     lib.aaclip_last_launch_count.restype = i32
     lib.aaclip_last_launch_count.argtypes = [vp]
     lib.aaclip_stat_columns.restype = i32
@@ -238,6 +247,7 @@ EXPORTED_SYMBOLS = [
     "aaclip_finalize_weights", "aaclip_saturation_check", "aaclip_saturation_count",
     "aaclip_text_finalize_weights", "aaclip_text_saturation_check", "aaclip_text_saturation_count",
     "aaclip_score_maps_raw", "aaclip_seg_normalize", "aaclip_adapter", "aaclip_gemm16_ln_tok",
+    "aaclip_split_hilo", "aaclip_join_hilo", "aaclip_gemm16_resid_hl",
 ]
 
 

@@ -210,6 +210,7 @@ int launch_gemm(int epi_mode, bool bf16, const void* A, const void* W, int M, in
     AACLIP_GEMM_CASE(EPI_LEAKY_16_SQ)
     AACLIP_GEMM_CASE(EPI_LN_F32_TOK)
     AACLIP_GEMM_CASE(EPI_LN_LEAKY_F32_TOK)
+    AACLIP_GEMM_CASE(EPI_BIAS_RESID_HL)
 #undef AACLIP_GEMM_CASE
     default: return fail(AACLIP_EINVAL, "gemm: unknown epilogue %d", epi_mode);
   }
@@ -259,22 +260,23 @@ int launch_attention(bool bf16, const void* qkv, void* out, int B, int N, int D,
 
 template <int D, bool BF16>
 void launch_layernorm_t(const float* x, const float* g, const float* b, void* out16, float* out_f32, int rows,
-                        int skipP, bool normalize, cudaStream_t st, float* stats_out, int np) {
+                        int skipP, bool normalize, cudaStream_t st, float* stats_out, int np, uint16_t* out_lo) {
   const int threads = 256, grid = (rows + 7) / 8;
   uint16_t* o = reinterpret_cast<uint16_t*>(out16);
-  if (normalize) launch_pdl(layernorm_kernel<D, true, BF16>, dim3(grid), dim3(threads), 0, st, x, g, b, o, out_f32, rows, skipP, 1e-5f, stats_out, np);
-  else launch_pdl(layernorm_kernel<D, false, BF16>, dim3(grid), dim3(threads), 0, st, x, g, b, o, out_f32, rows, skipP, 1e-5f, stats_out, np);
+  if (normalize) launch_pdl(layernorm_kernel<D, true, BF16>, dim3(grid), dim3(threads), 0, st, x, g, b, o, out_f32, rows, skipP, 1e-5f, stats_out, np, out_lo);
+  else launch_pdl(layernorm_kernel<D, false, BF16>, dim3(grid), dim3(threads), 0, st, x, g, b, o, out_f32, rows, skipP, 1e-5f, stats_out, np, out_lo);
 }
 
 int launch_layernorm(bool bf16, const float* x, const float* g, const float* b, void* out16, float* out_f32, int rows,
-                     int D, int skipP, bool normalize, cudaStream_t st, float* stats_out = nullptr, int np = 0) {
+                     int D, int skipP, bool normalize, cudaStream_t st, float* stats_out = nullptr, int np = 0,
+                     uint16_t* out_lo = nullptr) {
   if (rows <= 0) return AACLIP_OK;
   if (D == 1024) {
-    if (bf16) launch_layernorm_t<1024, true>(x, g, b, out16, out_f32, rows, skipP, normalize, st, stats_out, np);
-    else launch_layernorm_t<1024, false>(x, g, b, out16, out_f32, rows, skipP, normalize, st, stats_out, np);
+    if (bf16) launch_layernorm_t<1024, true>(x, g, b, out16, out_f32, rows, skipP, normalize, st, stats_out, np, out_lo);
+    else launch_layernorm_t<1024, false>(x, g, b, out16, out_f32, rows, skipP, normalize, st, stats_out, np, out_lo);
   } else if (D == 768) {
-    if (bf16) launch_layernorm_t<768, true>(x, g, b, out16, out_f32, rows, skipP, normalize, st, stats_out, np);
-    else launch_layernorm_t<768, false>(x, g, b, out16, out_f32, rows, skipP, normalize, st, stats_out, np);
+    if (bf16) launch_layernorm_t<768, true>(x, g, b, out16, out_f32, rows, skipP, normalize, st, stats_out, np, out_lo);
+    else launch_layernorm_t<768, false>(x, g, b, out16, out_f32, rows, skipP, normalize, st, stats_out, np, out_lo);
   } else {
     return fail(AACLIP_EINVAL, "layernorm: D=%d unsupported (768 or 1024)", D);
   }
@@ -296,6 +298,21 @@ __global__ void gather_cls_kernel(const float* __restrict__ x, float* __restrict
   ptx::pdl_wait();
   const int b = blockIdx.x;
   for (int i = threadIdx.x; i < D; i += blockDim.x) out[static_cast<size_t>(b) * D + i] = x[static_cast<size_t>(b) * tokens * D + i];
+}
+
+// one row per group of `tokens` rows of the (hi, lo) residual stream -> fp32 [groups, D]: row `pick[g]` of group g
+// (pick == nullptr: row 0 = the CLS token, model/adapter.py:190)
+template <bool BF16>
+__global__ void gather_row_hl_kernel(const uint16_t* __restrict__ hi, const uint16_t* __restrict__ lo,
+                                     float* __restrict__ out, int tokens, int D, const int32_t* __restrict__ pick) {
+  ptx::pdl_trigger();
+  ptx::pdl_wait();
+  const int g = blockIdx.x;
+  const size_t row = static_cast<size_t>(g) * tokens + (pick != nullptr ? pick[g] : 0);
+  const uint2* h = reinterpret_cast<const uint2*>(hi + row * D);
+  const uint2* l = reinterpret_cast<const uint2*>(lo + row * D);
+  for (int i = threadIdx.x; i < D / 4; i += blockDim.x)
+    reinterpret_cast<float4*>(out + static_cast<size_t>(g) * D)[i] = ptx::unpack_hilo4<BF16>(h[i], l[i]);
 }
 
 int launch_pack(bool bf16, const float* src, void* dst, long long R, long long C, long long Cp, cudaStream_t st) {
@@ -498,12 +515,13 @@ void free_block_staging(std::vector<BlockW>& blk) {
 constexpr int kStatCols = 256 / GemmPairCfg<256>::COL_GROUPS;
 inline int kStatPartials(size_t W) { return static_cast<int>(W) / kStatCols; }
 
-struct CoreWs { size_t x, x16, qkv, att, hid, abuf, stats, end; };
+struct CoreWs { size_t x, x16, xlo, qkv, att, hid, abuf, stats, end; };
 // ab = bytes per activation-operand element: 2, or 4 in fp32-accuracy mode (x16 then holds the fp32 LayerNorm output)
 CoreWs plan_core_ws(ArenaPlan& p, size_t M, size_t W, size_t F, size_t ab) {
   CoreWs w;
-  w.x = p.take<float>(M * W);            // residual stream, fp32
-  w.x16 = p.take<uint8_t>(M * W * ab);   // its raw 16-bit copy = A operand of QKV / c_fc / adapter GEMMs
+  w.x = p.take<float>(M * W);            // fp32 staging of the stream before ln_pre / the text embedding; fp32 mode: the stream
+  w.x16 = p.take<uint8_t>(M * W * ab);   // 16-bit modes: the hi plane of the residual stream = A operand of QKV / c_fc / adapter GEMMs
+  w.xlo = p.take<uint8_t>(M * W * 2);    // 16-bit modes: the lo plane (x = hi + lo, ptx::pack16_hilo)
   w.qkv = p.take<uint8_t>(M * 3 * W * ab);
   w.att = p.take<uint8_t>(M * W * ab);
   w.hid = p.take<uint8_t>(M * F * ab);
@@ -596,7 +614,9 @@ struct BlockRun {
   SatCheck sat;
   bool bf16;
   int items, tokens, W, F, causal, act;
-  float* x; uint16_t* x16; uint16_t* qkv; uint16_t* att; uint16_t* hid; float* abuf; float* stats;
+  // the residual stream x = x16 + xlo: two 16-bit planes (ptx::pack16_hilo); x16, the rounded value, is the A operand
+  // of the QKV / c_fc / adapter / tap GEMMs. stats: its LayerNorm partials.
+  uint16_t* x16; uint16_t* xlo; uint16_t* qkv; uint16_t* att; uint16_t* hid; float* abuf; float* stats;
   cudaStream_t st;
   int launches = 0;
   // Serpentine row order (GemmEpi::descending): every GEMM / attention launch walks the row blocks in the direction
@@ -647,15 +667,15 @@ struct BlockRun {
       if ((rc = launch_attention(bf16, qkv, att, items, tokens, W, causal, st, next_dir()))) return rc;
     }
     sat.scan(att, static_cast<size_t>(M) * W, st);
-    { GemmEpi e; e.bias = b.b_out; e.out_f32 = x; e.out_16 = x16; e.stats_out = stats; e.ldo = W;
-      if ((rc = gemm(EPI_BIAS_RESID_F32, att, b.w_out, M, W, W, e, AACLIP_PROF_GEMM_OUT))) return rc; }
+    { GemmEpi e; e.bias = b.b_out; e.out_16 = x16; e.out_lo = xlo; e.stats_out = stats; e.ldo = W;
+      if ((rc = gemm(EPI_BIAS_RESID_HL, att, b.w_out, M, W, W, e, AACLIP_PROF_GEMM_OUT))) return rc; }
     sat.scan(x16, static_cast<size_t>(M) * W, st);
     { GemmEpi e; e.bias = b.bf_fc; e.colsum = b.cs_fc; e.stats = stats; e.n_partials = np; e.inv_width = 1.0f / W;
       e.out_16 = hid; e.ldo = F;
       if ((rc = gemm(act == AACLIP_ACT_QUICK_GELU ? EPI_LN_BIAS_QGELU_BF16 : EPI_LN_BIAS_GELU_BF16, x16, b.w_fc, M, F, W, e, AACLIP_PROF_GEMM_FC))) return rc; }
     sat.scan(hid, static_cast<size_t>(M) * F, st);
-    { GemmEpi e; e.bias = b.b_proj; e.out_f32 = x; e.out_16 = x16; e.stats_out = stats; e.ldo = W;
-      if ((rc = gemm(EPI_BIAS_RESID_F32, hid, b.w_proj, M, W, F, e, AACLIP_PROF_GEMM_PROJ))) return rc; }
+    { GemmEpi e; e.bias = b.b_proj; e.out_16 = x16; e.out_lo = xlo; e.stats_out = stats; e.ldo = W;
+      if ((rc = gemm(EPI_BIAS_RESID_HL, hid, b.w_proj, M, W, F, e, AACLIP_PROF_GEMM_PROJ))) return rc; }
     sat.scan(x16, static_cast<size_t>(M) * W, st);
     if (w_adapter != nullptr) return adapter(w_adapter, M, adapt_weight);
     return AACLIP_OK;
@@ -676,13 +696,13 @@ struct BlockRun {
     const int grid = (M + 7) / 8;
     const float w = adapt_weight, w1 = 1.0f - adapt_weight;
     if (W == 1024) {
-      if (bf16) launch_pdl(adapter_blend16_kernel<1024, true>, dim3(grid), dim3(256), 0, st, x, static_cast<const uint16_t*>(a16), static_cast<const float*>(a_stats), M, w, w1, x16, stats, np);
-      else launch_pdl(adapter_blend16_kernel<1024, false>, dim3(grid), dim3(256), 0, st, x, static_cast<const uint16_t*>(a16), static_cast<const float*>(a_stats), M, w, w1, x16, stats, np);
+      if (bf16) launch_pdl(adapter_blend_hl_kernel<1024, true>, dim3(grid), dim3(256), 0, st, x16, xlo, static_cast<const uint16_t*>(a16), static_cast<const float*>(a_stats), M, w, w1, stats, np);
+      else launch_pdl(adapter_blend_hl_kernel<1024, false>, dim3(grid), dim3(256), 0, st, x16, xlo, static_cast<const uint16_t*>(a16), static_cast<const float*>(a_stats), M, w, w1, stats, np);
     } else {
-      if (bf16) launch_pdl(adapter_blend16_kernel<768, true>, dim3(grid), dim3(256), 0, st, x, static_cast<const uint16_t*>(a16), static_cast<const float*>(a_stats), M, w, w1, x16, stats, np);
-      else launch_pdl(adapter_blend16_kernel<768, false>, dim3(grid), dim3(256), 0, st, x, static_cast<const uint16_t*>(a16), static_cast<const float*>(a_stats), M, w, w1, x16, stats, np);
+      if (bf16) launch_pdl(adapter_blend_hl_kernel<768, true>, dim3(grid), dim3(256), 0, st, x16, xlo, static_cast<const uint16_t*>(a16), static_cast<const float*>(a_stats), M, w, w1, stats, np);
+      else launch_pdl(adapter_blend_hl_kernel<768, false>, dim3(grid), dim3(256), 0, st, x16, xlo, static_cast<const uint16_t*>(a16), static_cast<const float*>(a_stats), M, w, w1, stats, np);
     }
-    LAUNCH_CHECK("adapter_blend16_kernel");
+    LAUNCH_CHECK("adapter_blend_hl_kernel");
     last_desc = false;                     // an element-wise kernel: rows ascending
     ++launches;
     sat.scan(x16, static_cast<size_t>(M) * W, st);
@@ -1086,18 +1106,28 @@ int aaclip_forward(AaclipHandle* h, const float* images, int32_t B, void* worksp
   const bool bf = h->bf16;
   BlockRun run;
   run.prof = h; run.bf16 = bf; run.items = B; run.tokens = N; run.W = W; run.F = F; run.causal = 0; run.act = c.act;
-  run.x = (float*)(wsb + ws.core.x); run.x16 = (uint16_t*)(wsb + ws.core.x16); run.qkv = (uint16_t*)(wsb + ws.core.qkv);
+  run.x16 = (uint16_t*)(wsb + ws.core.x16); run.xlo = (uint16_t*)(wsb + ws.core.xlo); run.qkv = (uint16_t*)(wsb + ws.core.qkv);
   run.att = (uint16_t*)(wsb + ws.core.att); run.hid = (uint16_t*)(wsb + ws.core.hid);
   run.abuf = (float*)(wsb + ws.core.abuf); run.stats = (float*)(wsb + ws.core.stats); run.st = st;
   if (h->sat_on) { run.sat.counter = h->sat_counter; run.sat.bf16 = bf; }
-  float* x = run.x;
+  float* x = (float*)(wsb + ws.core.x);   // fp32 staging: patch embedding + CLS + positional embedding, until ln_pre
   int& launches = run.launches;
 
   auto lnorm = [&](const float* in, const float* g, const float* bta, void* o16, float* o32, int rows, int skipP,
-                   float* stats_out) -> int {
+                   float* stats_out, uint16_t* o_lo = nullptr) -> int {
     ProfScope ps(h, AACLIP_PROF_LAYERNORM, 0.0, st);
     ++launches;
-    return launch_layernorm(bf, in, g, bta, o16, o32, rows, W, skipP, true, st, stats_out, kStatPartials(W));
+    return launch_layernorm(bf, in, g, bta, o16, o32, rows, W, skipP, true, st, stats_out, kStatPartials(W), o_lo);
+  };
+  // the (hi, lo) residual stream back as fp32 rows in the staging buffer (exports only: fp32 ln_post tokens)
+  auto stream_to_f32 = [&]() -> int {
+    ProfScope ps(h, AACLIP_PROF_OTHER, 0.0, st);
+    ++launches;
+    const size_t n4 = static_cast<size_t>(M) * W / 4;
+    if (bf) launch_pdl(hilo_to_f32_kernel<true>, dim3(148 * 8), dim3(256), 0, st, static_cast<const uint16_t*>(run.x16), static_cast<const uint16_t*>(run.xlo), x, n4);
+    else launch_pdl(hilo_to_f32_kernel<false>, dim3(148 * 8), dim3(256), 0, st, static_cast<const uint16_t*>(run.x16), static_cast<const uint16_t*>(run.xlo), x, n4);
+    LAUNCH_CHECK("hilo_to_f32_kernel");
+    return AACLIP_OK;
   };
   auto l2norm = [&](float* t, int rows) -> int {
     ProfScope ps(h, AACLIP_PROF_OTHER, 0.0, st);
@@ -1140,8 +1170,8 @@ int aaclip_forward(AaclipHandle* h, const float* images, int32_t B, void* worksp
     launch_pdl(cls_row_kernel, dim3(B), dim3(256), 0, st, x, static_cast<const float*>(h->cls), static_cast<const float*>(h->pos), N, W);
     LAUNCH_CHECK("cls_row_kernel"); ++launches;
   }
-  // ln_pre in place; also emits the 16-bit copy and the LayerNorm partials block 0's folded ln_1 needs
-  if ((rc = lnorm(x, h->lnpre_g, h->lnpre_b, run.x16, x, M, 0, run.stats))) return rc;
+  // ln_pre: fp32 staging -> the residual stream in its (hi, lo) form + the LayerNorm partials block 0's folded ln_1 needs
+  if ((rc = lnorm(x, h->lnpre_g, h->lnpre_b, run.x16, nullptr, M, 0, run.stats, run.xlo))) return rc;
   run.last_desc = false;                   // an element-wise kernel wrote the stream: rows ascending
   run.sat.scan(run.x16, static_cast<size_t>(M) * W, st);
 
@@ -1154,7 +1184,10 @@ int aaclip_forward(AaclipHandle* h, const float* images, int32_t B, void* worksp
       // the projections: they read the raw 16-bit residual stream (all N rows per image) and the epilogue drops the CLS
       // rows; the fp32 ln_post tokens are only materialised when the caller asks for them (host IQM branch).
       float* tok_f32 = (tokens_out != nullptr) ? tokens_out[level_idx] : nullptr;
-      if (tok_f32 != nullptr && (rc = lnorm(x, h->lnpost_g, h->lnpost_b, nullptr, tok_f32, MP, P, nullptr))) return rc;
+      if (tok_f32 != nullptr) {
+        if ((rc = stream_to_f32())) return rc;
+        if ((rc = lnorm(x, h->lnpost_g, h->lnpost_b, nullptr, tok_f32, MP, P, nullptr))) return rc;
+      }
       const int proj_epi = c.proj_relu ? EPI_LN_LEAKY_F32_TOK : EPI_LN_F32_TOK;
       auto tap = [&](size_t pi, float* out, int cols) -> int {
         const AaclipHandle::ProjFold& pf = h->proj[pi];
@@ -1181,8 +1214,9 @@ int aaclip_forward(AaclipHandle* h, const float* images, int32_t B, void* worksp
   }
   if (cls_out != nullptr) {
     ProfScope ps(h, AACLIP_PROF_OTHER, 0.0, st);
-    launch_pdl(gather_cls_kernel, dim3(B), dim3(256), 0, st, static_cast<const float*>(x), cls_out, N, W);
-    LAUNCH_CHECK("gather_cls_kernel"); ++launches;
+    if (bf) launch_pdl(gather_row_hl_kernel<true>, dim3(B), dim3(256), 0, st, static_cast<const uint16_t*>(run.x16), static_cast<const uint16_t*>(run.xlo), cls_out, N, W, static_cast<const int32_t*>(nullptr));
+    else launch_pdl(gather_row_hl_kernel<false>, dim3(B), dim3(256), 0, st, static_cast<const uint16_t*>(run.x16), static_cast<const uint16_t*>(run.xlo), cls_out, N, W, static_cast<const int32_t*>(nullptr));
+    LAUNCH_CHECK("gather_row_hl_kernel"); ++launches;
   }
   h->last_launches = launches + run.sat.launches;
   return AACLIP_OK;
@@ -1338,9 +1372,9 @@ int aaclip_seg_normalize(AaclipHandle* h, int32_t enable) {
   return AACLIP_OK;
 }
 
-int aaclip_adapter(int32_t dtype, float* x, void* x16, const void* W16, int32_t M, int32_t D, float weight,
+int aaclip_adapter(int32_t dtype, void* x_hi, void* x_lo, const void* W16, int32_t M, int32_t D, float weight,
                    void* workspace, size_t workspace_bytes, float* stats_out, void* stream) {
-  if (!x || !x16 || !W16 || !workspace || !stats_out) return fail(AACLIP_EINVAL, "aaclip_adapter: null argument");
+  if (!x_hi || !x_lo || !W16 || !workspace || !stats_out) return fail(AACLIP_EINVAL, "aaclip_adapter: null argument");
   if (dtype != AACLIP_DT_F16 && dtype != AACLIP_DT_BF16) return fail(AACLIP_EINVAL, "aaclip_adapter: bad dtype %d", dtype);
   if (M <= 0 || (D != 768 && D != 1024)) return fail(AACLIP_EINVAL, "aaclip_adapter: D=%d unsupported (768 or 1024)", D);
   const int np = kStatPartials(D);
@@ -1348,8 +1382,44 @@ int aaclip_adapter(int32_t dtype, float* x, void* x16, const void* W16, int32_t 
   if (workspace_bytes < need) return fail(AACLIP_EINVAL, "aaclip_adapter: workspace too small (%zu < %zu)", workspace_bytes, need);
   BlockRun run;
   run.prof = nullptr; run.bf16 = dtype == AACLIP_DT_BF16; run.W = D; run.st = static_cast<cudaStream_t>(stream);
-  run.x = x; run.x16 = static_cast<uint16_t*>(x16); run.abuf = static_cast<float*>(workspace); run.stats = stats_out;
+  run.x16 = static_cast<uint16_t*>(x_hi); run.xlo = static_cast<uint16_t*>(x_lo);
+  run.abuf = static_cast<float*>(workspace); run.stats = stats_out;
   return run.adapter(static_cast<const uint16_t*>(W16), M, weight);
+}
+
+int aaclip_split_hilo(int32_t dtype, const float* x, void* x_hi, void* x_lo, int64_t n, void* stream) {
+  if (!x || !x_hi || !x_lo || n < 0 || n % 4 != 0) return fail(AACLIP_EINVAL, "aaclip_split_hilo: bad argument");
+  if (dtype != AACLIP_DT_F16 && dtype != AACLIP_DT_BF16) return fail(AACLIP_EINVAL, "aaclip_split_hilo: bad dtype %d", dtype);
+  if (n == 0) return AACLIP_OK;
+  const unsigned grid = static_cast<unsigned>((n / 4 + 255) / 256 < 148 * 8 ? (n / 4 + 255) / 256 : 148 * 8);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == AACLIP_DT_BF16) f32_to_hilo_kernel<true><<<grid, 256, 0, st>>>(x, static_cast<uint16_t*>(x_hi), static_cast<uint16_t*>(x_lo), static_cast<size_t>(n / 4));
+  else f32_to_hilo_kernel<false><<<grid, 256, 0, st>>>(x, static_cast<uint16_t*>(x_hi), static_cast<uint16_t*>(x_lo), static_cast<size_t>(n / 4));
+  LAUNCH_CHECK("f32_to_hilo_kernel");
+  return AACLIP_OK;
+}
+
+int aaclip_join_hilo(int32_t dtype, const void* x_hi, const void* x_lo, float* x, int64_t n, void* stream) {
+  if (!x || !x_hi || !x_lo || n < 0 || n % 4 != 0) return fail(AACLIP_EINVAL, "aaclip_join_hilo: bad argument");
+  if (dtype != AACLIP_DT_F16 && dtype != AACLIP_DT_BF16) return fail(AACLIP_EINVAL, "aaclip_join_hilo: bad dtype %d", dtype);
+  if (n == 0) return AACLIP_OK;
+  const unsigned grid = static_cast<unsigned>((n / 4 + 255) / 256 < 148 * 8 ? (n / 4 + 255) / 256 : 148 * 8);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == AACLIP_DT_BF16) hilo_to_f32_kernel<true><<<grid, 256, 0, st>>>(static_cast<const uint16_t*>(x_hi), static_cast<const uint16_t*>(x_lo), x, static_cast<size_t>(n / 4));
+  else hilo_to_f32_kernel<false><<<grid, 256, 0, st>>>(static_cast<const uint16_t*>(x_hi), static_cast<const uint16_t*>(x_lo), x, static_cast<size_t>(n / 4));
+  LAUNCH_CHECK("hilo_to_f32_kernel");
+  return AACLIP_OK;
+}
+
+int aaclip_gemm16_resid_hl(int32_t dtype, const void* A, const void* W, int32_t M, int32_t N, int32_t K,
+                           const float* bias, void* x_hi, void* x_lo, float* stats_out, int32_t ldo, void* stream) {
+  if (!A || !W || !bias || !x_hi || !x_lo) return fail(AACLIP_EINVAL, "aaclip_gemm16_resid_hl: null argument");
+  if (dtype != AACLIP_DT_F16 && dtype != AACLIP_DT_BF16) return fail(AACLIP_EINVAL, "aaclip_gemm16_resid_hl: bad dtype %d", dtype);
+  if (ldo < N || ldo % 8 != 0) return fail(AACLIP_EINVAL, "aaclip_gemm16_resid_hl: ldo must be >= N and a multiple of 8");
+  if (stats_out && N / kStatCols > 16) return fail(AACLIP_EINVAL, "aaclip_gemm16_resid_hl: statistics need N <= %d (16 partials)", 16 * kStatCols);
+  GemmEpi e;
+  e.bias = bias; e.out_16 = static_cast<uint16_t*>(x_hi); e.out_lo = static_cast<uint16_t*>(x_lo); e.stats_out = stats_out; e.ldo = ldo;
+  return launch_gemm(EPI_BIAS_RESID_HL, dtype == AACLIP_DT_BF16, A, W, M, N, K, e, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"
@@ -1532,24 +1602,26 @@ int aaclip_encode_text(AaclipTextHandle* h, const int32_t* tokens, int32_t n, vo
   BlockRun run;
   if (h->sat_on) { run.sat.counter = h->sat_counter; run.sat.bf16 = bf; }
   run.prof = nullptr; run.bf16 = bf; run.items = n; run.tokens = T; run.W = W; run.F = F; run.causal = 1; run.act = c.act;
-  run.x = (float*)(wsb + ws.core.x); run.x16 = (uint16_t*)(wsb + ws.core.x16); run.qkv = (uint16_t*)(wsb + ws.core.qkv);
+  run.x16 = (uint16_t*)(wsb + ws.core.x16); run.xlo = (uint16_t*)(wsb + ws.core.xlo); run.qkv = (uint16_t*)(wsb + ws.core.qkv);
   run.att = (uint16_t*)(wsb + ws.core.att); run.hid = (uint16_t*)(wsb + ws.core.hid);
   run.abuf = (float*)(wsb + ws.core.abuf); run.stats = (float*)(wsb + ws.core.stats); run.st = st;
+  float* x32 = (float*)(wsb + ws.core.x);  // fp32 staging of the embedding
   float* eot = (float*)(wsb + ws.eot);
   uint16_t* eot16 = (uint16_t*)(wsb + ws.eot16);
 
   // token + positional embedding (model/adapter.py:277-281); an identity-LayerNorm pass (NORMALIZE=false) then
-  // produces the raw 16-bit copy and the LayerNorm partials block 0's folded ln_1 needs
-  launch_pdl(text_embed_kernel, dim3(M), dim3(192), 0, st, tokens, static_cast<const float*>(h->tok_emb), static_cast<const float*>(h->pos), run.x, T, W, c.vocab);
+  // produces the (hi, lo) form of the stream and the LayerNorm partials block 0's folded ln_1 needs
+  launch_pdl(text_embed_kernel, dim3(M), dim3(192), 0, st, tokens, static_cast<const float*>(h->tok_emb), static_cast<const float*>(h->pos), x32, T, W, c.vocab);
   LAUNCH_CHECK("text_embed_kernel");
-  if ((rc = launch_layernorm(bf, run.x, nullptr, nullptr, run.x16, nullptr, M, W, 0, /*normalize=*/false, st, run.stats, kStatPartials(W)))) return rc;
+  if ((rc = launch_layernorm(bf, x32, nullptr, nullptr, run.x16, nullptr, M, W, 0, /*normalize=*/false, st, run.stats, kStatPartials(W), run.xlo))) return rc;
   run.sat.scan(run.x16, static_cast<size_t>(M) * W, st);
   // 12 causal residual attention blocks + adapters (model/adapter.py:284-295)
   for (int i = 0; i < c.layers; ++i)
     if ((rc = run.run(h->blk[i], i < c.adapt_until ? h->w_adapter[i] : nullptr, c.adapt_weight))) return rc;
   // EOT row -> ln_final -> SimpleProj + LeakyReLU (model/adapter.py:296-298)
-  launch_pdl(text_gather_eot_kernel, dim3(n), dim3(192), 0, st, tokens, static_cast<const float*>(run.x), eot, T, W);
-  LAUNCH_CHECK("text_gather_eot_kernel");
+  if (bf) launch_pdl(text_gather_eot_hl_kernel<true>, dim3(n), dim3(192), 0, st, tokens, static_cast<const uint16_t*>(run.x16), static_cast<const uint16_t*>(run.xlo), eot, T, W);
+  else launch_pdl(text_gather_eot_hl_kernel<false>, dim3(n), dim3(192), 0, st, tokens, static_cast<const uint16_t*>(run.x16), static_cast<const uint16_t*>(run.xlo), eot, T, W);
+  LAUNCH_CHECK("text_gather_eot_hl_kernel");
   if ((rc = launch_layernorm(bf, eot, h->lnf_g, h->lnf_b, eot16, nullptr, n, W, 0, true, st))) return rc;
   run.sat.scan(eot16, static_cast<size_t>(n) * W, st);
   { GemmEpi e; e.out_f32 = out; e.ldo = E;

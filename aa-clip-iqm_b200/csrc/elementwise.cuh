@@ -130,7 +130,10 @@ template <int D, bool NORMALIZE, bool BF16>
 __global__ void layernorm_kernel(const float* x, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, uint16_t* __restrict__ out_bf16,
                                  float* out_f32, int rows, int skipP, float eps,
-                                 float* __restrict__ stats_out = nullptr, int np = 0) {
+                                 float* __restrict__ stats_out = nullptr, int np = 0,
+                                 uint16_t* __restrict__ out_lo = nullptr) {
+  // out_lo != nullptr: the result enters the residual stream in its (hi, lo) form: out_bf16 receives the hi plane (the
+  // rounded 16-bit value = the GEMM operand) and out_lo the rounded remainder (ptx::pack16_hilo)
   ptx::pdl_trigger();
   ptx::pdl_wait();
   constexpr int V = D / 128;  // float4 per lane
@@ -169,7 +172,18 @@ __global__ void layernorm_kernel(const float* x, const float* __restrict__ gamma
       v[j].w = (v[j].w - mean) * rstd * g.w + bb.w;
     }
   }
-  if (out_bf16 != nullptr) {
+  if (out_bf16 != nullptr && out_lo != nullptr) {
+    uint2* oh = reinterpret_cast<uint2*>(out_bf16 + static_cast<size_t>(warp) * D);
+    uint2* ol = reinterpret_cast<uint2*>(out_lo + static_cast<size_t>(warp) * D);
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      uint2 hi, lo;
+      ptx::pack16_hilo<BF16>(v[j].x, v[j].y, hi.x, lo.x);
+      ptx::pack16_hilo<BF16>(v[j].z, v[j].w, hi.y, lo.y);
+      oh[lane + 32 * j] = hi;
+      ol[lane + 32 * j] = lo;
+    }
+  } else if (out_bf16 != nullptr) {
     uint2* o = reinterpret_cast<uint2*>(out_bf16 + static_cast<size_t>(warp) * D);
 #pragma unroll
     for (int j = 0; j < V; ++j)
@@ -245,26 +259,30 @@ __global__ void adapter_blend_kernel(float* __restrict__ x, const float* __restr
   }
 }
 
-// The same blend fed by the adapter GEMM's EPI_LEAKY_16_SQ epilogue: a arrives in the 16-bit operand dtype and its
-// squared norm as `np` per-row partials (sum, sumsq) of the unrounded values (fixed order: batch-invariant).
+// The blend of the 16-bit modes. a arrives from the adapter GEMM's EPI_LEAKY_16_SQ epilogue in the operand dtype with
+// its squared norm as `np` per-row partials (sum, sumsq) of the unrounded values (fixed order: batch-invariant); the
+// residual stream is read and rewritten in its (hi, lo) form (ptx::pack16_hilo), hi being the next GEMM's operand:
+// 10 bytes per element (2 + 2 + 2 read, 2 + 2 written). One scale per row: a is already rounded to 16 bits, so the
+// reference's per-element order a*|x|/|a| buys nothing here (the fp32-accuracy mode keeps it).
 template <int D, bool BF16>
-__global__ void adapter_blend16_kernel(float* __restrict__ x, const uint16_t* __restrict__ a16,
-                                       const float* __restrict__ a_stats, int rows, float w, float one_minus_w,
-                                       uint16_t* __restrict__ x16, float* __restrict__ stats_out, int np) {
+__global__ void adapter_blend_hl_kernel(uint16_t* __restrict__ x_hi, uint16_t* __restrict__ x_lo,
+                                        const uint16_t* __restrict__ a16, const float* __restrict__ a_stats, int rows,
+                                        float w, float one_minus_w, float* __restrict__ stats_out, int np) {
   ptx::pdl_trigger();
   ptx::pdl_wait();
   constexpr int V = D / 128;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
-  float4* xr = reinterpret_cast<float4*>(x + static_cast<size_t>(warp) * D);
+  uint2* hr = reinterpret_cast<uint2*>(x_hi + static_cast<size_t>(warp) * D);
+  uint2* lr = reinterpret_cast<uint2*>(x_lo + static_cast<size_t>(warp) * D);
   const uint2* ar = reinterpret_cast<const uint2*>(a16 + static_cast<size_t>(warp) * D);
   float4 xv[V];
   uint2 aw[V];
   float sx = 0.f;
 #pragma unroll
   for (int j = 0; j < V; ++j) {
-    xv[j] = xr[lane + 32 * j];
+    xv[j] = ptx::unpack_hilo4<BF16>(hr[lane + 32 * j], lr[lane + 32 * j]);
     aw[j] = ar[lane + 32 * j];
     sx += (xv[j].x * xv[j].x + xv[j].y * xv[j].y) + (xv[j].z * xv[j].z + xv[j].w * xv[j].w);
   }
@@ -273,8 +291,6 @@ __global__ void adapter_blend16_kernel(float* __restrict__ x, const uint16_t* __
     const float2* ap = reinterpret_cast<const float2*>(a_stats) + static_cast<size_t>(warp) * np;
     for (int i = 0; i < np; ++i) sa += __ldg(ap + i).y;   // every lane: same order, same value
   }
-  // (one scale per row: a is already rounded to 16 bits here, so the reference's per-element order a*|x|/|a| buys
-  // nothing; the fp32-accuracy mode keeps it)
   const float r = w * (sqrtf(warp_sum(sx)) / sqrtf(sa));
   float s = 0.f, q = 0.f;
 #pragma unroll
@@ -287,9 +303,11 @@ __global__ void adapter_blend16_kernel(float* __restrict__ x, const uint16_t* __
     o.y = fmaf(r, a1, one_minus_w * xv[j].y);
     o.z = fmaf(r, a2, one_minus_w * xv[j].z);
     o.w = fmaf(r, a3, one_minus_w * xv[j].w);
-    xr[lane + 32 * j] = o;
-    reinterpret_cast<uint2*>(x16 + static_cast<size_t>(warp) * D)[lane + 32 * j] =
-        make_uint2(ptx::pack16<BF16>(o.x, o.y), ptx::pack16<BF16>(o.z, o.w));
+    uint2 hi, lo;
+    ptx::pack16_hilo<BF16>(o.x, o.y, hi.x, lo.x);
+    ptx::pack16_hilo<BF16>(o.z, o.w, hi.y, lo.y);
+    hr[lane + 32 * j] = hi;
+    lr[lane + 32 * j] = lo;
     s += (o.x + o.y) + (o.z + o.w);
     q += (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w);
   }
@@ -297,6 +315,33 @@ __global__ void adapter_blend16_kernel(float* __restrict__ x, const uint16_t* __
   q = warp_sum(q);
   float2* o = reinterpret_cast<float2*>(stats_out) + static_cast<size_t>(warp) * np;
   if (lane < np) o[lane] = (lane == 0) ? make_float2(s, q) : make_float2(0.f, 0.f);
+}
+
+// fp32 -> (hi, lo) planes (ptx::pack16_hilo); exported as aaclip_split_hilo for the building-block tests
+template <bool BF16>
+__global__ void f32_to_hilo_kernel(const float* __restrict__ x, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo,
+                                   size_t n4) {
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    uint2 h, l;
+    ptx::pack16_hilo<BF16>(v.x, v.y, h.x, l.x);
+    ptx::pack16_hilo<BF16>(v.z, v.w, h.y, l.y);
+    reinterpret_cast<uint2*>(hi)[i] = h;
+    reinterpret_cast<uint2*>(lo)[i] = l;
+  }
+}
+
+// (hi, lo) planes -> fp32 (exports of the residual stream: the CLS rows, the rows the fp32 token export normalises)
+template <bool BF16>
+__global__ void hilo_to_f32_kernel(const uint16_t* __restrict__ hi, const uint16_t* __restrict__ lo,
+                                   float* __restrict__ out, size_t n4) {
+  ptx::pdl_trigger();
+  ptx::pdl_wait();
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    reinterpret_cast<float4*>(out)[i] =
+        ptx::unpack_hilo4<BF16>(reinterpret_cast<const uint2*>(hi)[i], reinterpret_cast<const uint2*>(lo)[i]);
 }
 
 // Validation pass for the 16-bit operand mode (aaclip_saturation_check): counts the elements of a 16-bit activation
@@ -662,6 +707,35 @@ __global__ void text_gather_eot_kernel(const int32_t* __restrict__ ids, const fl
   const float4* src = reinterpret_cast<const float4*>(x + (static_cast<size_t>(s) * ctx + s_best) * D);
   float4* dst = reinterpret_cast<float4*>(out + static_cast<size_t>(s) * D);
   for (int i = threadIdx.x; i < D / 4; i += blockDim.x) dst[i] = src[i];
+}
+
+// the same gather from the (hi, lo) form of the residual stream (16-bit modes)
+template <bool BF16>
+__global__ void text_gather_eot_hl_kernel(const int32_t* __restrict__ ids, const uint16_t* __restrict__ x_hi,
+                                          const uint16_t* __restrict__ x_lo, float* __restrict__ out, int ctx, int D) {
+  ptx::pdl_trigger();
+  ptx::pdl_wait();
+  const int s = blockIdx.x;
+  __shared__ int s_best;
+  if (threadIdx.x < 32) {
+    int best_v = INT_MIN, best_i = 0;
+    for (int t = threadIdx.x; t < ctx; t += 32) {
+      const int v = ids[s * ctx + t];
+      if (v > best_v) { best_v = v; best_i = t; }     // strided scan keeps the first maximum per lane
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const int ov = __shfl_xor_sync(0xffffffffu, best_v, o), oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+      if (ov > best_v || (ov == best_v && oi < best_i)) { best_v = ov; best_i = oi; }
+    }
+    if (threadIdx.x == 0) s_best = best_i;
+  }
+  __syncthreads();
+  const size_t row = (static_cast<size_t>(s) * ctx + s_best) * D;
+  const uint2* h = reinterpret_cast<const uint2*>(x_hi + row);
+  const uint2* l = reinterpret_cast<const uint2*>(x_lo + row);
+  float4* dst = reinterpret_cast<float4*>(out + static_cast<size_t>(s) * D);
+  for (int i = threadIdx.x; i < D / 4; i += blockDim.x) dst[i] = ptx::unpack_hilo4<BF16>(h[i], l[i]);
 }
 
 // Prompt-ensemble anchors, forward_utils.py:155-161: for group g (rows offsets[g] .. offsets[g+1]-1 of emb):

@@ -44,12 +44,17 @@ enum EpiMode : int {
   // out_f32[b*P + t - 1] -- x[1:] of every image, without a LayerNorm pass or a token copy
   EPI_LN_F32_TOK = 12,        // out_f32 = rstd*(acc - mean*colsum) + bias'
   EPI_LN_LEAKY_F32_TOK = 13,  // ... followed by LeakyReLU(0.01) (--relu)
+  // residual update on the (hi, lo) form of the stream: x = hi + lo (two 16-bit planes, ptx::pack16_hilo);
+  // x += acc + bias; hi (== the 16-bit operand copy the next GEMM reads) and lo are rewritten in place, plus the
+  // LayerNorm partials of the new rows. 8 bytes per element per update instead of the 10 of EPI_BIAS_RESID_F32.
+  EPI_BIAS_RESID_HL = 14,
 };
 
 struct GemmEpi {
   const float* bias = nullptr;        // [N]
   float* out_f32 = nullptr;           // [*, ldo]
-  uint16_t* out_16 = nullptr;         // [*, ldo] fp16 or bf16 (the operand dtype)
+  uint16_t* out_16 = nullptr;         // [*, ldo] fp16 or bf16 (the operand dtype); EPI_BIAS_RESID_HL: the hi plane (in / out)
+  uint16_t* out_lo = nullptr;         // EPI_BIAS_RESID_HL: the lo plane (in / out)
   const float* pos = nullptr;         // EPI_PATCH_F32: positional embedding [(P+1), N]
   int ldo = 0;                        // leading dimension of the outputs, in elements
   int patches = 0;                    // EPI_PATCH_F32: P
@@ -118,7 +123,12 @@ __host__ __device__ constexpr bool epi_has_bias() {
   return EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_QGELU_BF16 ||
          EPI == EPI_BIAS_RESID_F32 || EPI == EPI_BIAS_F32 || EPI == EPI_LN_BIAS_BF16 ||
          EPI == EPI_LN_BIAS_GELU_BF16 || EPI == EPI_LN_BIAS_QGELU_BF16 || EPI == EPI_LN_F32_TOK ||
-         EPI == EPI_LN_LEAKY_F32_TOK;
+         EPI == EPI_LN_LEAKY_F32_TOK || EPI == EPI_BIAS_RESID_HL;
+}
+
+template <int EPI>
+__host__ __device__ constexpr bool epi_is_resid() {    // adds the residual row the caller loads
+  return EPI == EPI_BIAS_RESID_F32 || EPI == EPI_BIAS_RESID_HL;
 }
 
 template <int EPI>
@@ -128,7 +138,7 @@ __host__ __device__ constexpr bool epi_is_tok() {      // token-tap projections:
 
 template <int EPI>
 __host__ __device__ constexpr bool epi_has_stats() {   // emits per-row (sum, sumsq) partials of what it wrote
-  return EPI == EPI_BIAS_RESID_F32 || EPI == EPI_LEAKY_16_SQ;
+  return EPI == EPI_BIAS_RESID_F32 || EPI == EPI_LEAKY_16_SQ || EPI == EPI_BIAS_RESID_HL;
 }
 
 template <int EPI>
@@ -167,6 +177,15 @@ __device__ __forceinline__ float4 epilogue_apply(bool ok, float4 v, int row, int
                 (epi_is_ln<EPI>() && !epi_is_tok<EPI>()) || EPI == EPI_LEAKY_16_SQ) {
     const uint2 w = make_uint2(ptx::pack16<BF16>(v.x, v.y), ptx::pack16<BF16>(v.z, v.w));
     if (ok) *reinterpret_cast<uint2*>(e.out_16 + static_cast<size_t>(row) * e.ldo + n) = w;
+  } else if constexpr (EPI == EPI_BIAS_RESID_HL) {
+    v.x += resid.x; v.y += resid.y; v.z += resid.z; v.w += resid.w;   // residual (hi + lo) loaded by the caller
+    uint2 hi, lo;
+    ptx::pack16_hilo<BF16>(v.x, v.y, hi.x, lo.x);
+    ptx::pack16_hilo<BF16>(v.z, v.w, hi.y, lo.y);
+    if (ok) {
+      *reinterpret_cast<uint2*>(e.out_16 + static_cast<size_t>(row) * e.ldo + n) = hi;
+      *reinterpret_cast<uint2*>(e.out_lo + static_cast<size_t>(row) * e.ldo + n) = lo;
+    }
   } else if constexpr (EPI == EPI_BIAS_RESID_F32) {
     v.x += resid.x; v.y += resid.y; v.z += resid.z; v.w += resid.w;   // residual loaded by the caller
     const uint2 w = make_uint2(ptx::pack16<BF16>(v.x, v.y), ptx::pack16<BF16>(v.z, v.w));
@@ -351,6 +370,17 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const int m_lin = tile / n_tiles, n_blk = tile - m_lin * n_tiles;
       const int m_pair = epi.descending ? m_pairs - 1 - m_lin : m_lin;
       const int row0 = (2 * m_pair + static_cast<int>(rank)) * BM + q * 32;
+      if constexpr (EPI == EPI_BIAS_RESID_HL && AACLIP_GEMM_RESID_PREFETCH) {
+        // (hi, lo) form: COLS_PER_WARP 16-bit elements per plane and row = COLS_PER_WARP / 64 lines of 128 B each
+        if (num_kb <= AACLIP_GEMM_RESID_PREFETCH_MAXKB && row0 + lane < M) {
+          const size_t off = static_cast<size_t>(row0 + lane) * epi.ldo + n_blk * BN + cg * COLS_PER_WARP;
+#pragma unroll
+          for (int i = 0; i < COLS_PER_WARP / 64; ++i) {
+            ptx::prefetch_l2(epi.out_16 + off + i * 64);
+            ptx::prefetch_l2(epi.out_lo + off + i * 64);
+          }
+        }
+      }
       if constexpr (EPI == EPI_BIAS_RESID_F32 && AACLIP_GEMM_RESID_PREFETCH)
         // The residual rows this warp will add come from HBM (the stream is 180 MB, far beyond L2): pull them into L2
         // now, while the MMAs of this tile are still running, so that the loads in the chunk loop below are L2 hits
@@ -429,12 +459,21 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #ifdef AACLIP_GEMM_DBG_NORESID   // what-if (timing only, wrong results): no residual read
             dst[j] = make_float4(0.f, 0.f, 0.f, 0.f);
 #else
-            dst[j] = (rr < M) ? *reinterpret_cast<const float4*>(epi.out_f32 + static_cast<size_t>(rr) * epi.ldo + n)
-                              : make_float4(0.f, 0.f, 0.f, 0.f);
+            if constexpr (EPI == EPI_BIAS_RESID_HL) {
+              uint2 hi = make_uint2(0u, 0u), lo = make_uint2(0u, 0u);
+              if (rr < M) {
+                hi = *reinterpret_cast<const uint2*>(epi.out_16 + static_cast<size_t>(rr) * epi.ldo + n);
+                lo = *reinterpret_cast<const uint2*>(epi.out_lo + static_cast<size_t>(rr) * epi.ldo + n);
+              }
+              dst[j] = ptx::unpack_hilo4<BF16>(hi, lo);
+            } else {
+              dst[j] = (rr < M) ? *reinterpret_cast<const float4*>(epi.out_f32 + static_cast<size_t>(rr) * epi.ldo + n)
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
 #endif
           }
         };
-        if constexpr (EPI == EPI_BIAS_RESID_F32) load_resid(resid_a, 0);
+        if constexpr (epi_is_resid<EPI>()) load_resid(resid_a, 0);
         uint32_t r[32];
         ptx::tmem_ld_32x32b_x32(t_base + c * 32, r);
         ptx::tmem_ld_wait();
@@ -447,14 +486,14 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         for (int u = 0; u < 8; ++u)
           ptx::sts128(stage_u32 + lane * 128 + ((u ^ (lane & 7)) << 4), r[4 * u], r[4 * u + 1], r[4 * u + 2],
                       r[4 * u + 3]);
-        if constexpr (EPI == EPI_BIAS_RESID_F32) load_resid(resid_b, 4);
+        if constexpr (epi_is_resid<EPI>()) load_resid(resid_b, 4);
         __syncwarp();
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int rr = j * 4 + sub;
           const float4 v = ptx::lds128(stage_u32 + rr * 128 + ((unit ^ (rr & 7)) << 4));
           const bool ok = row0 + rr < M;
-          if constexpr (EPI == EPI_BIAS_RESID_F32) {
+          if constexpr (epi_is_resid<EPI>()) {
             const float4 x = epilogue_apply<EPI, BF16>(ok, v, row0 + rr, n, epi, bias4, j < 4 ? resid_a[j & 3] : resid_b[j & 3]);
             st_s[j] += (x.x + x.y) + (x.z + x.w);      // rows >= M accumulate garbage that is never stored
             st_q[j] += (x.x * x.x + x.y * x.y) + (x.z * x.z + x.w * x.w);

@@ -371,6 +371,25 @@ __device__ __forceinline__ void unpack16(uint32_t w, float& lo, float& hi) {
         : "r"(w));
   }
 }
+// fp32 pair -> (hi, lo) 16-bit pairs with hi + lo == the pair to ~22 bits (fp16) / 16 bits (bf16): hi is the rounded
+// 16-bit value -- the GEMM operand -- and lo the rounded remainder. The residual stream is kept in this form
+// (gemm_tcgen05.cuh: EPI_BIAS_RESID_HL): 4 bytes per element per update instead of fp32 + a separate 16-bit copy.
+template <bool BF16>
+__device__ __forceinline__ void pack16_hilo(float a, float b, uint32_t& hi, uint32_t& lo) {
+  hi = pack16<BF16>(a, b);
+  float ha, hb;
+  unpack16<BF16>(hi, ha, hb);
+  lo = pack16<BF16>(a - ha, b - hb);
+}
+template <bool BF16>
+__device__ __forceinline__ float4 unpack_hilo4(uint2 hi, uint2 lo) {
+  float h0, h1, h2, h3, l0, l1, l2, l3;
+  unpack16<BF16>(hi.x, h0, h1);
+  unpack16<BF16>(hi.y, h2, h3);
+  unpack16<BF16>(lo.x, l0, l1);
+  unpack16<BF16>(lo.y, l2, l3);
+  return make_float4(h0 + l0, h1 + l1, h2 + l2, h3 + l3);
+}
 template <bool BF16>
 __device__ __forceinline__ uint16_t cvt16(float v) {
   return static_cast<uint16_t>(pack16<BF16>(v, 0.f) & 0xFFFFu);

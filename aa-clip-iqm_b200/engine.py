@@ -230,18 +230,56 @@ def score_maps(seg: Sequence[torch.Tensor], text: torch.Tensor, img_size: int, t
     return maps, score
 
 
-def adapter(x: torch.Tensor, x16: torch.Tensor, w16: torch.Tensor, weight: float) -> torch.Tensor:
-    """Residual adapter + blend of one block in place (aaclip_adapter): x [M,D] fp32, x16 its raw 16-bit copy (updated),
-    w16 [D,D] packed fc.0.weight. Returns the LayerNorm partials [M, D/stat_columns, 2] of the new x."""
-    _need_cuda(x, x16, w16)
-    assert x.dtype == torch.float32 and x16.dtype == w16.dtype and x.is_contiguous() and x16.is_contiguous()
-    M, D = x.shape
+def split_hilo(x: torch.Tensor, dtype: torch.dtype = torch.float16) -> Tuple[torch.Tensor, torch.Tensor]:
+    """fp32 -> the (hi, lo) form of the residual stream: hi = x rounded to `dtype`, lo = the rounded remainder
+    (aaclip_split_hilo)."""
+    _need_cuda(x)
+    x = x.contiguous().float()
+    hi = torch.empty(x.shape, dtype=dtype, device=x.device)
+    lo = torch.empty(x.shape, dtype=dtype, device=x.device)
+    _lib.check(_lib.load().aaclip_split_hilo(_dt(dtype), _ptr(x), _ptr(hi), _ptr(lo), x.numel(), _stream()),
+               "aaclip_split_hilo")
+    return hi, lo
+
+
+def join_hilo(hi: torch.Tensor, lo: torch.Tensor) -> torch.Tensor:
+    """(hi, lo) -> fp32 (aaclip_join_hilo)."""
+    _need_cuda(hi, lo)
+    assert hi.dtype == lo.dtype and hi.shape == lo.shape and hi.is_contiguous() and lo.is_contiguous()
+    x = torch.empty(hi.shape, dtype=torch.float32, device=hi.device)
+    _lib.check(_lib.load().aaclip_join_hilo(_dt(hi), _ptr(hi), _ptr(lo), _ptr(x), hi.numel(), _stream()),
+               "aaclip_join_hilo")
+    return x
+
+
+def gemm16_resid_hl(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, x_hi: torch.Tensor, x_lo: torch.Tensor,
+                    want_stats: bool = True) -> Optional[torch.Tensor]:
+    """x (hi / lo planes, in place) += A W^T + bias (aaclip_gemm16_resid_hl). Returns the LayerNorm partials
+    [M, N/stat_columns, 2] of the new rows (or None)."""
+    _need_cuda(a, w, bias, x_hi, x_lo)
+    assert a.dtype == w.dtype == x_hi.dtype == x_lo.dtype and a.is_contiguous() and w.is_contiguous()
+    assert x_hi.is_contiguous() and x_lo.is_contiguous()
+    M, K = a.shape
+    N = w.shape[0]
+    lib = _lib.load()
+    stats = torch.empty((M, N // lib.aaclip_stat_columns(), 2), dtype=torch.float32, device=a.device) if want_stats else None
+    _lib.check(lib.aaclip_gemm16_resid_hl(_dt(a), _ptr(a), _ptr(w), M, N, K, _ptr(bias.contiguous().float()), _ptr(x_hi),
+                                          _ptr(x_lo), _ptr(stats), N, _stream()), "aaclip_gemm16_resid_hl")
+    return stats
+
+
+def adapter(x_hi: torch.Tensor, x_lo: torch.Tensor, w16: torch.Tensor, weight: float) -> torch.Tensor:
+    """Residual adapter + blend of one block in place (aaclip_adapter) on the (hi, lo) form of the stream; w16 [D,D]
+    packed fc.0.weight. Returns the LayerNorm partials [M, D/stat_columns, 2] of the new x."""
+    _need_cuda(x_hi, x_lo, w16)
+    assert x_hi.dtype == x_lo.dtype == w16.dtype and x_hi.is_contiguous() and x_lo.is_contiguous()
+    M, D = x_hi.shape
     lib = _lib.load()
     np_ = D // lib.aaclip_stat_columns()
-    stats = torch.empty((M, np_, 2), dtype=torch.float32, device=x.device)
+    stats = torch.empty((M, np_, 2), dtype=torch.float32, device=x_hi.device)
     ws_bytes = M * D * 2 + M * np_ * 8
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
-    _lib.check(lib.aaclip_adapter(_dt(x16), _ptr(x), _ptr(x16), _ptr(w16.contiguous()), M, D, float(weight), _ptr(ws),
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x_hi.device)
+    _lib.check(lib.aaclip_adapter(_dt(x_hi), _ptr(x_hi), _ptr(x_lo), _ptr(w16.contiguous()), M, D, float(weight), _ptr(ws),
                                   ws_bytes, _ptr(stats), _stream()), "aaclip_adapter")
     return stats
 

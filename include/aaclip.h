@@ -320,17 +320,31 @@ int aaclip_gemm16_ln_tok(int32_t dtype, const void* A, const void* W16, int32_t 
                          const float* bias_f, const float* colsum, const float* stats, int32_t n_partials,
                          int32_t ln_width, int32_t patches, float* out_f32, int32_t ldo, void* stream);
 
-/* Residual GEMM: x[M,N] (fp32, in place) += A W^T + bias; optionally also the raw 16-bit copy of the new x and its
- * LayerNorm partials stats_out [M][N/aaclip_stat_columns()][2] (the inputs of the next folded-LN GEMM). */
+/* Residual GEMM on an fp32 stream: x[M,N] (fp32, in place) += A W^T + bias; optionally also the raw 16-bit copy of the
+ * new x and its LayerNorm partials stats_out [M][N/aaclip_stat_columns()][2]. (Rounds 1-2a; aaclip_forward now uses the
+ * hi / lo form, aaclip_gemm16_resid_hl. Kept as a building block.) */
 int aaclip_gemm16_resid(int32_t dtype, const void* A, const void* W, int32_t M, int32_t N, int32_t K,
                         const float* bias, float* x, void* x16_out, float* stats_out, int32_t ldo, void* stream);
 
+/* The residual stream of the 16-bit modes is kept as two 16-bit planes: hi = the value rounded to `dtype` (which is
+ * also the A operand of the GEMMs that consume the stream) and lo = the rounded remainder, x = hi + lo to ~22 bits
+ * (fp16) -- 8 instead of 10 bytes per element and update against an fp32 stream with a separate 16-bit copy.
+ * aaclip_split_hilo / aaclip_join_hilo convert n elements (n % 4 == 0) between fp32 and that form. */
+int aaclip_split_hilo(int32_t dtype, const float* x, void* x_hi, void* x_lo, int64_t n, void* stream);
+int aaclip_join_hilo(int32_t dtype, const void* x_hi, const void* x_lo, float* x, int64_t n, void* stream);
+
+/* Residual GEMM on that form, exactly what aaclip_forward launches for out_proj / c_proj (model/transformer.py:254-257):
+ * x[M,N] (hi / lo planes, in place) += A W^T + bias; stats_out [M][N/aaclip_stat_columns()][2] = LayerNorm partials of
+ * the new rows (the inputs of the next folded-LN GEMM), optional. */
+int aaclip_gemm16_resid_hl(int32_t dtype, const void* A, const void* W, int32_t M, int32_t N, int32_t K,
+                           const float* bias, void* x_hi, void* x_lo, float* stats_out, int32_t ldo, void* stream);
+
 /* Residual adapter + blend of one block (model/adapter.py:163-170, model/adapter_modules.py:6-13), exactly the two
  * launches aaclip_forward issues:  a = LeakyReLU_0.01(x W^T);  a <- a |x|_2 / |a|_2 per row;  x <- weight a + (1-weight) x.
- *   x [M,D] fp32 in place;  x16 [M,D] `dtype`: in = the raw 16-bit copy of x (the GEMM operand), out = copy of the new x;
+ *   x_hi / x_lo [M,D] `dtype`: the residual stream, in place (x_hi is the GEMM operand);
  *   W16 [D,D] `dtype` (aaclip_pack16 of fc.0.weight);  stats_out [M][D/aaclip_stat_columns()][2] LayerNorm partials of
  *   the new x;  workspace >= M*D*2 + M*(D/aaclip_stat_columns())*8 bytes.  D in {768, 1024}. */
-int aaclip_adapter(int32_t dtype, float* x, void* x16, const void* W16, int32_t M, int32_t D, float weight,
+int aaclip_adapter(int32_t dtype, void* x_hi, void* x_lo, const void* W16, int32_t M, int32_t D, float weight,
                    void* workspace, size_t workspace_bytes, float* stats_out, void* stream);
 
 /* Fused multi-head attention: qkv `dtype` [B,N,3*D] -> out `dtype` [B,N,D]; head dim 64; softmax scale 1/8. */

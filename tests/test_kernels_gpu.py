@@ -218,32 +218,77 @@ def test_score_maps_raw_normalises_in_the_similarity_pass(eng):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+def test_hilo_form_of_the_residual_stream(eng, dtype):
+    """x -> (hi, lo) -> x: hi is x rounded to the operand dtype (what the GEMMs read), hi + lo reproduces x to the
+    square of the format's unit roundoff; exact for values the format holds."""
+    _lib, engine = eng
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn(1000, 1024, device="cuda", generator=g) * 3.0
+    x[::17, 3] = 275.0 + x[::17, 3]                     # massive-activation sized entries
+    x[5, :8] = torch.tensor([0.0, 1.0, -2.5, 65504.0, 1e-6, -1e-6, 3.0e-5, 0.125], device="cuda")
+    hi, lo = engine.split_hilo(x, dtype)
+    assert torch.equal(hi, x.to(dtype))
+    back = engine.join_hilo(hi, lo)
+    # |hi + lo - x| <= eps^2 |x| (two roundings), with the absolute floor of the format's smallest subnormal
+    floor = 2.0 ** -24 if dtype == torch.float16 else 1e-38
+    assert ((back - x).abs() <= 4 * EPS[dtype] ** 2 * x.abs() + floor).all()
+    exact = torch.randn(64, 1024, device="cuda", generator=g).to(dtype).float()
+    h2, l2 = engine.split_hilo(exact, dtype)
+    assert torch.equal(engine.join_hilo(h2, l2), exact) and int(l2.float().abs().max().item()) == 0
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("M,N,K", [(300, 1024, 1024), (2740, 1024, 4096), (77 * 3, 768, 768)])
+def test_residual_gemm_on_hilo_stream(eng, M, N, K, dtype):
+    """aaclip_gemm16_resid_hl (what the tower launches for out_proj / c_proj): x += A W^T + b on the (hi, lo) planes,
+    against fp32 torch on the same 16-bit operands; hi must be exactly the rounded new x; the LayerNorm partials must
+    describe the new rows."""
+    _lib, engine = eng
+    a, w, b = _ab(M, N, K, dtype)
+    g = torch.Generator(device="cuda").manual_seed(M + K)
+    x = torch.randn(M, N, device="cuda", generator=g) * 2.0 + 0.5
+    hi, lo = engine.split_hilo(x, dtype)
+    x_in = engine.join_hilo(hi, lo)
+    ref = x_in + a.float() @ w.float().t() + b
+    stats = engine.gemm16_resid_hl(a, w, b, hi, lo)
+    out = engine.join_hilo(hi, lo)
+    assert (out - ref).abs().max().item() < 1e-3 + 8 * EPS[dtype] ** 2 * ref.abs().max().item()
+    assert (hi.float() - ref).abs().max().item() <= 1.01 * EPS[dtype] * ref.abs().max().item() + 1e-3
+    cols = _lib.load().aaclip_stat_columns()
+    assert stats.shape == (M, N // cols, 2)
+    assert torch.allclose(stats[..., 0].sum(1), ref.sum(1), atol=5e-3, rtol=1e-5)
+    assert torch.allclose(stats[..., 1].sum(1), (ref * ref).sum(1), atol=5e-2, rtol=1e-5)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("M,D", [(300, 1024), (2740, 1024), (77 * 3, 768)])
 def test_adapter_gemm_and_blend(eng, M, D, dtype):
-    """aaclip_adapter (GEMM with the LeakyReLU + 16-bit store + sum-of-squares epilogue, then the blend kernel) against
-    model/adapter.py:163-170 in fp32 on the same 16-bit operands; also the outputs the next block consumes: the raw
-    16-bit copy of the new x and its LayerNorm partials."""
+    """aaclip_adapter (GEMM with the LeakyReLU + 16-bit store + sum-of-squares epilogue, then the blend kernel on the
+    (hi, lo) form of the stream) against model/adapter.py:163-170 in fp32 on the same 16-bit operands; also the
+    outputs the next block consumes: the hi plane = the rounded new x, and its LayerNorm partials."""
     _lib, engine = eng
     g = torch.Generator(device="cuda").manual_seed(M + D)
     x = torch.randn(M, D, device="cuda", generator=g) * 1.3 + 0.2
     w = (torch.randn(D, D, device="cuda", generator=g) * D ** -0.5).to(dtype)
-    x16 = x.to(dtype)
-    a = F.leaky_relu(x16.float() @ w.float().t(), 0.01)
+    hi, lo = engine.split_hilo(x, dtype)
+    x = engine.join_hilo(hi, lo)                          # the value the stream actually holds
+    a = F.leaky_relu(hi.float() @ w.float().t(), 0.01)
     a = a * x.norm(dim=-1, keepdim=True) / a.norm(dim=-1, keepdim=True)
     ref = 0.1 * a + 0.9 * x
-    xo, x16o = x.clone(), x16.clone()
-    stats = engine.adapter(xo, x16o, w, 0.1)
-    tol = 4 * EPS[dtype] * 0.1 * a.abs().max().item() + 1e-5      # a is rounded once to 16 bits, then weighted by 0.1
-    assert (xo - ref).abs().max().item() < tol
-    assert torch.equal(x16o, xo.to(dtype))
+    hi_in, lo_in = hi.clone(), lo.clone()
+    stats = engine.adapter(hi, lo, w, 0.1)
+    xo = engine.join_hilo(hi, lo)
+    tol = 4 * EPS[dtype] * 0.1 * a.abs().max().item() + 8 * EPS[dtype] ** 2 * ref.abs().max().item() + 1e-5
+    assert (xo - ref).abs().max().item() < tol          # a is rounded once to 16 bits, then weighted by 0.1
+    assert (hi.float() - xo).abs().max().item() <= 1.01 * EPS[dtype] * xo.abs().max().item()
     cols = _lib.load().aaclip_stat_columns()
     assert stats.shape == (M, D // cols, 2)
-    assert torch.allclose(stats[..., 0].sum(1), xo.sum(1), atol=2e-3, rtol=1e-5)
-    assert torch.allclose(stats[..., 1].sum(1), (xo * xo).sum(1), atol=2e-3, rtol=1e-5)
+    assert torch.allclose(stats[..., 0].sum(1), xo.sum(1), atol=5e-3, rtol=1e-4)
+    assert torch.allclose(stats[..., 1].sum(1), (xo * xo).sum(1), atol=5e-2, rtol=1e-4)
     # row-local: a row alone gives the same bits as the row inside the batch
-    x1, x161 = x[7:8].clone(), x16[7:8].clone()
-    engine.adapter(x1, x161, w, 0.1)
-    assert torch.equal(x1[0], xo[7])
+    h1, l1 = hi_in[7:8].clone(), lo_in[7:8].clone()
+    engine.adapter(h1, l1, w, 0.1)
+    assert torch.equal(h1[0], hi[7]) and torch.equal(l1[0], lo[7])
 
 
 # ---------------------------------------------------------------------------------------------------------
