@@ -178,7 +178,16 @@ __device__ __forceinline__ float4 epilogue_apply(bool ok, float4 v, int row, int
     const uint2 w = make_uint2(ptx::pack16<BF16>(v.x, v.y), ptx::pack16<BF16>(v.z, v.w));
     if (ok) *reinterpret_cast<uint2*>(e.out_16 + static_cast<size_t>(row) * e.ldo + n) = w;
   } else if constexpr (EPI == EPI_BIAS_RESID_HL) {
-    v.x += resid.x; v.y += resid.y; v.z += resid.z; v.w += resid.w;   // residual (hi + lo) loaded by the caller
+    // `resid` carries the raw words of the residual row: (hi.x, hi.y, lo.x, lo.y) of these four elements. Added with the
+    // mixed-precision FHADD (16-bit operand + fp32 -> fp32): two instructions per element, no conversions.
+    {
+      const uint32_t h0 = __float_as_uint(resid.x), h1 = __float_as_uint(resid.y);
+      const uint32_t l0 = __float_as_uint(resid.z), l1 = __float_as_uint(resid.w);
+      v.x = ptx::add16<BF16, 0>(l0, ptx::add16<BF16, 0>(h0, v.x));
+      v.y = ptx::add16<BF16, 1>(l0, ptx::add16<BF16, 1>(h0, v.y));
+      v.z = ptx::add16<BF16, 0>(l1, ptx::add16<BF16, 0>(h1, v.z));
+      v.w = ptx::add16<BF16, 1>(l1, ptx::add16<BF16, 1>(h1, v.w));
+    }
     uint2 hi, lo;
     ptx::pack16_hilo<BF16>(v.x, v.y, hi.x, lo.x);
     ptx::pack16_hilo<BF16>(v.z, v.w, hi.y, lo.y);
@@ -465,7 +474,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 hi = *reinterpret_cast<const uint2*>(epi.out_16 + static_cast<size_t>(rr) * epi.ldo + n);
                 lo = *reinterpret_cast<const uint2*>(epi.out_lo + static_cast<size_t>(rr) * epi.ldo + n);
               }
-              dst[j] = ptx::unpack_hilo4<BF16>(hi, lo);
+              dst[j] = make_float4(__uint_as_float(hi.x), __uint_as_float(hi.y), __uint_as_float(lo.x), __uint_as_float(lo.y));
             } else {
               dst[j] = (rr < M) ? *reinterpret_cast<const float4*>(epi.out_f32 + static_cast<size_t>(rr) * epi.ldo + n)
                                 : make_float4(0.f, 0.f, 0.f, 0.f);

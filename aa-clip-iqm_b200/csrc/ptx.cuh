@@ -371,15 +371,41 @@ __device__ __forceinline__ void unpack16(uint32_t w, float& lo, float& hi) {
         : "r"(w));
   }
 }
+// Mixed-precision add / fma of sm_100 (FHADD / FHFMA: one 16-bit operand, fp32 result, no separate conversion):
+//   add16<BF16, HALF>(w, c)  = c + half HALF of the packed pair w        rsub16<BF16, HALF>(w, v) = v - that half (exact
+//   in fp32 before the single rounding of the result)
+template <bool BF16, int HALF>
+__device__ __forceinline__ float add16(uint32_t w, float c) {
+  float d;
+  if constexpr (BF16) {
+    if constexpr (HALF == 0) asm("{\n\t.reg .b16 l, u;\n\tmov.b32 {l, u}, %1;\n\tadd.rn.f32.bf16 %0, l, %2;\n\t}" : "=f"(d) : "r"(w), "f"(c));
+    else asm("{\n\t.reg .b16 l, u;\n\tmov.b32 {l, u}, %1;\n\tadd.rn.f32.bf16 %0, u, %2;\n\t}" : "=f"(d) : "r"(w), "f"(c));
+  } else {
+    if constexpr (HALF == 0) asm("{\n\t.reg .b16 l, u;\n\tmov.b32 {l, u}, %1;\n\tadd.rn.f32.f16 %0, l, %2;\n\t}" : "=f"(d) : "r"(w), "f"(c));
+    else asm("{\n\t.reg .b16 l, u;\n\tmov.b32 {l, u}, %1;\n\tadd.rn.f32.f16 %0, u, %2;\n\t}" : "=f"(d) : "r"(w), "f"(c));
+  }
+  return d;
+}
+template <bool BF16, int HALF>
+__device__ __forceinline__ float rsub16(uint32_t w, float v) {
+  float d;
+  if constexpr (BF16) {
+    if constexpr (HALF == 0) asm("{\n\t.reg .b16 l, u, m;\n\tmov.b32 {l, u}, %1;\n\tmov.b16 m, 0xBF80;\n\tfma.rn.f32.bf16 %0, l, m, %2;\n\t}" : "=f"(d) : "r"(w), "f"(v));
+    else asm("{\n\t.reg .b16 l, u, m;\n\tmov.b32 {l, u}, %1;\n\tmov.b16 m, 0xBF80;\n\tfma.rn.f32.bf16 %0, u, m, %2;\n\t}" : "=f"(d) : "r"(w), "f"(v));
+  } else {
+    if constexpr (HALF == 0) asm("{\n\t.reg .b16 l, u, m;\n\tmov.b32 {l, u}, %1;\n\tmov.b16 m, 0xBC00;\n\tfma.rn.f32.f16 %0, l, m, %2;\n\t}" : "=f"(d) : "r"(w), "f"(v));
+    else asm("{\n\t.reg .b16 l, u, m;\n\tmov.b32 {l, u}, %1;\n\tmov.b16 m, 0xBC00;\n\tfma.rn.f32.f16 %0, u, m, %2;\n\t}" : "=f"(d) : "r"(w), "f"(v));
+  }
+  return d;
+}
+
 // fp32 pair -> (hi, lo) 16-bit pairs with hi + lo == the pair to ~22 bits (fp16) / 16 bits (bf16): hi is the rounded
 // 16-bit value -- the GEMM operand -- and lo the rounded remainder. The residual stream is kept in this form
 // (gemm_tcgen05.cuh: EPI_BIAS_RESID_HL): 4 bytes per element per update instead of fp32 + a separate 16-bit copy.
 template <bool BF16>
 __device__ __forceinline__ void pack16_hilo(float a, float b, uint32_t& hi, uint32_t& lo) {
   hi = pack16<BF16>(a, b);
-  float ha, hb;
-  unpack16<BF16>(hi, ha, hb);
-  lo = pack16<BF16>(a - ha, b - hb);
+  lo = pack16<BF16>(rsub16<BF16, 0>(hi, a), rsub16<BF16, 1>(hi, b));
 }
 template <bool BF16>
 __device__ __forceinline__ float4 unpack_hilo4(uint2 hi, uint2 lo) {
