@@ -49,11 +49,12 @@ for (N, epi, nm) in [(3072, _lib.EPI_LN_BIAS_BF16, "qkv  LN-fold bias->f16"), (4
                                  torch.ones(1024, device=dev), torch.zeros(1024, device=dev))
     ms = timeit(lambda: engine.gemm16_ln(x16, w16, epi, bf, cs, stats, 1024))
     print(f"gemm {nm:22s} M={M} N={N} K=1024: {ms:.3f} ms  {2.0 * M * N * 1024 / ms / 1e9:7.1f} TFLOP/s", flush=True)
-for (K, nm) in [(1024, "out  resid+x16+stats"), (4096, "proj resid+x16+stats")]:
+hi, lo = engine.split_hilo(x)
+for (K, nm) in [(1024, "out  resid (hi,lo)+stats"), (4096, "proj resid (hi,lo)+stats")]:
     a = (torch.randn(M, K, device=dev) * 0.5).half()
     w = (torch.randn(1024, K, device=dev) * K ** -0.5).half()
     bias = torch.randn(1024, device=dev) * 0.1
-    ms = timeit(lambda: engine.gemm16_resid(a, w, bias, x))
+    ms = timeit(lambda: engine.gemm16_resid_hl(a, w, bias, hi, lo))
     print(f"gemm {nm:22s} M={M} N=1024 K={K}: {ms:.3f} ms  {2.0 * M * 1024 * K / ms / 1e9:7.1f} TFLOP/s", flush=True)
 
 qkv = torch.randn(B, 1370, 3072, device=dev).half()
