@@ -216,6 +216,9 @@ int launch_gemm(int epi_mode, bool bf16, const void* A, const void* W, int M, in
   }
 }
 
+// one round-robin slot counter for every attention launch of the process (both operand dtypes, every device)
+std::atomic<unsigned> g_attn_next_slot{0};
+
 template <bool BF16>
 int launch_attention_t(const CUtensorMap& tq, void* out, int B, int N, int D, int causal, cudaStream_t st,
                        int descending) {
@@ -226,10 +229,9 @@ int launch_attention_t(const CUtensorMap& tq, void* out, int B, int N, int D, in
   // persistent CTAs draw (image, head, 256 query rows) items from a counter slot that the kernel leaves zeroed; slots
   // are handed out round-robin, so launches in flight on different streams (or captured in different graphs) do not
   // share one unless more than SCHED_SLOTS of them are pending at once
-  static std::atomic<unsigned> next_slot{0};
   AttnSched* sched = nullptr;
   CUDA_TRY(cudaGetSymbolAddress(reinterpret_cast<void**>(&sched), g_attn_sched));
-  sched += next_slot.fetch_add(1, std::memory_order_relaxed) % attn_cfg::SCHED_SLOTS;
+  sched += g_attn_next_slot.fetch_add(1, std::memory_order_relaxed) % attn_cfg::SCHED_SLOTS;
   const int items = B * (D / attn_cfg::HD) * ((N + attn_cfg::BQ * attn_cfg::QT - 1) / (attn_cfg::BQ * attn_cfg::QT));
   // the output as a 3-D tensor [B][N][D] for the bulk stores: one 32-row x 64-column box per softmax warp and item
   CUtensorMap to;
