@@ -152,6 +152,20 @@ def test_attention_persistent_schedule(eng):
     torch.cuda.synchronize()
     for a, b in outs:
         assert torch.equal(a, ref) and torch.equal(b, ref_other)
+    # the two operand dtypes are separate kernel instantiations but draw their slots from ONE counter
+    other_bf = other.bfloat16()
+    ref_bf = engine.attention(other_bf).clone()
+    torch.cuda.synchronize()
+    outs = []
+    for _ in range(4):
+        with torch.cuda.stream(s1):
+            a = engine.attention(big)
+        with torch.cuda.stream(s2):
+            b = engine.attention(other_bf)
+        outs.append((a, b))
+    torch.cuda.synchronize()
+    for a, b in outs:
+        assert torch.equal(a, ref) and torch.equal(b, ref_bf)
     small = (torch.randn(1, 130, 3 * 64, device="cuda", generator=g)).half()
     first = engine.attention(small).clone()
     for _ in range(600):
